@@ -1,0 +1,195 @@
+// bvh.cuh — compressed 8-wide BVH node layout + the ray/box and ray/triangle tests of device_cuda.
+//
+// Replaces the reference's calls into the (un-vendored, binary-only) Intel Embree 2.15:
+//   rtcIntersect  devices/device_singleray/integrators/pathtraceintegrator.cpp:72
+//   rtcOccluded   devices/device_singleray/integrators/pathtraceintegrator.cpp:160
+// Node format follows Ylitie/Karras/Laine, "Efficient Incoherent Ray Traversal on GPUs Through
+// Compressed Wide BVHs" (HPG 2017): 80 bytes = origin (12) + 3 exponents + imask (4) + child base,
+// triangle base (8) + 8 meta bytes + 6 x 8 quantised planes (48).  Triangles are 48 bytes
+// (3 x float4) with geomID / primID / flags in the w lanes.
+//
+// Arithmetic contract of the triangle test: "YRT-PLUECKER-1" (stated in oracle/embree2_shim.cpp,
+// which holds the CPU twin used by the oracle) — bit-exact (t,u,v,geomID,primID).
+#pragma once
+#include "common.cuh"
+
+namespace yrt {
+
+struct __align__(16) Node8 {
+    float px, py, pz;
+    uint8_t ex, ey, ez, imask;
+    uint32_t childBase, triBase;
+    uint8_t meta[8];
+    uint8_t qlox[8], qloy[8], qloz[8], qhix[8], qhiy[8], qhiz[8];
+};
+static_assert(sizeof(Node8) == 80, "Node8 must be 80 bytes");
+
+#define YRT_TRI_FLAG_CULL 1u
+#define YRT_STACK_SIZE 96
+#define YRT_BOX_PAD 9.5367431640625e-07f     // 2^-20
+
+struct HitRec { float t, u, v; int geomID, primID; V3 Ng; };
+
+#if defined(__CUDACC__)
+
+// edge(s,e).D with explicit fused multiply-adds (mirrors edgeFn in oracle/embree2_shim.cpp)
+YRT_D float edge_fn(V3 s, V3 e, V3 D) {
+    const float cx = __fmaf_rn(s.y, e.z, -__fmul_rn(s.z, e.y));
+    const float cy = __fmaf_rn(s.z, e.x, -__fmul_rn(s.x, e.z));
+    const float cz = __fmaf_rn(s.x, e.y, -__fmul_rn(s.y, e.x));
+    return __fmaf_rn(cz, D.z, __fmaf_rn(cy, D.y, __fmul_rn(cx, D.x)));
+}
+
+// Returns true and fills (t,u,v,Ng) if the supporting-plane hit lies inside the triangle.
+// The caller applies the (tnear, tbest, id tie-break) acceptance rule and the cull filter.
+YRT_D bool tri_test(V3 O, V3 D, V3 p0, V3 p1, V3 p2, float& t, float& u, float& v, V3& Ng, float& den) {
+    const V3 v0 = p0 - O, v1 = p1 - O, v2 = p2 - O;
+    const V3 e0 = v2 - v0, e1 = v0 - v1, e2 = v1 - v2;
+    const float U = edge_fn(v2 + v0, e0, D);
+    const float V = edge_fn(v0 + v1, e1, D);
+    const float W = edge_fn(v1 + v2, e2, D);
+    const float mn = fminf(fminf(U, V), W), mx = fmaxf(fmaxf(U, V), W);
+    if (!(mn >= 0.f || mx <= 0.f)) return false;
+    const float UVW = (U + V) + W;
+    if (UVW == 0.f) return false;
+    const V3 a = p0 - p1, b = p2 - p0;
+    Ng = cross(a, b);                                   // separate mul/sub: the cull filter's arithmetic (trianglemesh_full.cpp:112-116)
+    den = dot(Ng, D);
+    if (den == 0.f) return false;
+    const float T = dot(v0, Ng);
+    t = T / den; u = U / UVW; v = V / UVW;
+    return true;
+}
+
+struct RayPre {                  // per-ray constants of the box test
+    V3 O, D, idir;
+    uint32_t octinv;             // bit 4/2/1 set where dir.x/y/z >= 0
+};
+
+YRT_D RayPre ray_prepare(V3 O, V3 D) {
+    RayPre r; r.O = O; r.D = D;
+    const float tiny = 1e-18f;
+    const float dx = fabsf(D.x) < tiny ? copysignf(tiny, D.x) : D.x;
+    const float dy = fabsf(D.y) < tiny ? copysignf(tiny, D.y) : D.y;
+    const float dz = fabsf(D.z) < tiny ? copysignf(tiny, D.z) : D.z;
+    r.idir = V3(1.0f / dx, 1.0f / dy, 1.0f / dz);
+    r.octinv = (D.x >= 0.f ? 4u : 0u) | (D.y >= 0.f ? 2u : 0u) | (D.z >= 0.f ? 1u : 0u);
+    return r;
+}
+
+YRT_D float byte_to_float(uint32_t packed, int i) {     // exact u8 -> float without I2F
+    return __uint_as_float(__byte_perm(packed, 0x4B000000u, 0x7650 + i)) - 8388608.0f;
+}
+
+// Intersects the 8 quantised child boxes of one node; returns the CWBVH hit mask:
+// bits 24..31 inner children at position 24 + (slot ^ octinv), bits 0..23 leaf triangles.
+YRT_D uint32_t node_test(const uint4 n0, const uint4 n1, const uint4 n2, const uint4 n3, const uint4 n4,
+                         const RayPre& r, float tnear, float tbest) {
+    const V3 p(__uint_as_float(n0.x), __uint_as_float(n0.y), __uint_as_float(n0.z));
+    const uint32_t e = n0.w;
+    const float sx = __uint_as_float((e & 0xffu) << 23) * r.idir.x;
+    const float sy = __uint_as_float(((e >> 8) & 0xffu) << 23) * r.idir.y;
+    const float sz = __uint_as_float(((e >> 16) & 0xffu) << 23) * r.idir.z;
+    const float ox = (p.x - r.O.x) * r.idir.x, oy = (p.y - r.O.y) * r.idir.y, oz = (p.z - r.O.z) * r.idir.z;
+    const float padx = fabsf(ox) * YRT_BOX_PAD, pady = fabsf(oy) * YRT_BOX_PAD, padz = fabsf(oz) * YRT_BOX_PAD;
+    const float oxn = ox - padx, oxf = ox + padx, oyn = oy - pady, oyf = oy + pady, ozn = oz - padz, ozf = oz + padz;
+    const bool nx = r.idir.x < 0.f, ny = r.idir.y < 0.f, nz = r.idir.z < 0.f;
+    const uint32_t octinv4 = r.octinv * 0x01010101u;
+    const float tfarPadded = tbest * (1.0f + YRT_BOX_PAD);
+    uint32_t hitmask = 0;
+#pragma unroll
+    for (int half = 0; half < 2; half++) {
+        const uint32_t meta4 = half ? n1.w : n1.z;
+        const uint32_t qlox = half ? n2.y : n2.x, qloy = half ? n2.w : n2.z;
+        const uint32_t qloz = half ? n3.y : n3.x, qhix = half ? n3.w : n3.z;
+        const uint32_t qhiy = half ? n4.y : n4.x, qhiz = half ? n4.w : n4.z;
+        const uint32_t nearx = nx ? qhix : qlox, farx = nx ? qlox : qhix;
+        const uint32_t neary = ny ? qhiy : qloy, fary = ny ? qloy : qhiy;
+        const uint32_t nearz = nz ? qhiz : qloz, farz = nz ? qloz : qhiz;
+        const uint32_t isInner4 = (meta4 & (meta4 << 1)) & 0x10101010u;
+        const uint32_t innerMask4 = (isInner4 >> 4) * 0xffu;            // 0xff per inner byte
+        const uint32_t bitIndex4 = (meta4 ^ (octinv4 & innerMask4)) & 0x1f1f1f1fu;
+        const uint32_t childBits4 = (meta4 >> 5) & 0x07070707u;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const float tnx = __fmaf_rn(byte_to_float(nearx, i), sx, oxn);
+            const float tny = __fmaf_rn(byte_to_float(neary, i), sy, oyn);
+            const float tnz = __fmaf_rn(byte_to_float(nearz, i), sz, ozn);
+            const float tfx = __fmaf_rn(byte_to_float(farx, i), sx, oxf);
+            const float tfy = __fmaf_rn(byte_to_float(fary, i), sy, oyf);
+            const float tfz = __fmaf_rn(byte_to_float(farz, i), sz, ozf);
+            const float tmin = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, tnear));
+            const float tmax = fminf(fminf(tfx, tfy), fminf(tfz, tfarPadded));
+            if (tmin <= tmax) {
+                const uint32_t bits = (childBits4 >> (8 * i)) & 0xffu;
+                const uint32_t idx = (bitIndex4 >> (8 * i)) & 0xffu;
+                hitmask |= bits << idx;
+            }
+        }
+    }
+    return hitmask;
+}
+
+struct TraceCounters { uint32_t nodes, tris; };
+
+// While-while traversal of the compressed BVH8.  ANY: rtcOccluded semantics (first accepted hit ends).
+// Closest-hit acceptance is order independent: (t, geomID, primID) lexicographic minimum.
+template <bool ANY, bool COUNT>
+YRT_D bool trace_ray(const uint4* __restrict__ nodes, const float4* __restrict__ tris, uint32_t numNodes,
+                     V3 O, V3 D, float tnear, float tfar, HitRec& hit, TraceCounters* cnt) {
+    hit.geomID = -1; hit.primID = -1; hit.t = tfar;
+    if (numNodes == 0 || !(tnear <= tfar)) return false;   // NaN tfar: no hit
+    const RayPre r = ray_prepare(O, D);
+    uint2 stack[YRT_STACK_SIZE];
+    int sp = 0;
+    float tbest = tfar;
+    bool have = false;
+    // root = "child 7^octinv of a virtual parent with imask 0": popc(0) = 0 -> node index 0
+    uint2 G = make_uint2(0u, 0x80000000u);
+    uint2 T = make_uint2(0u, 0u);
+    while (true) {
+        {   // invariant: G has at least one pending inner child bit here
+            const uint32_t bit = 31u - __clz(G.y);
+            G.y &= ~(1u << bit);
+            const uint32_t slot = (bit - 24u) ^ r.octinv;
+            const uint32_t nodeIdx = G.x + __popc((G.y & 0xffu) & ~(0xffffffffu << slot));
+            if (G.y & 0xff000000u) {
+                if (sp < YRT_STACK_SIZE) stack[sp++] = G;
+            }
+            const uint4* np = nodes + 5ull * nodeIdx;
+            const uint4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
+            if (COUNT) cnt->nodes++;
+            const uint32_t hm = node_test(n0, n1, n2, n3, n4, r, tnear, tbest);
+            G = make_uint2(n1.x, (hm & 0xff000000u) | (n0.w >> 24));
+            T = make_uint2(n1.y, hm & 0x00ffffffu);
+        }
+
+        while (T.y) {
+            const uint32_t bit = 31u - __clz(T.y);
+            T.y &= ~(1u << bit);
+            const float4* tp = tris + 3ull * (T.x + bit);
+            const float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
+            if (COUNT) cnt->tris++;
+            float t, u, v, den; V3 Ng;
+            if (!tri_test(O, D, V3(a.x, a.y, a.z), V3(b.x, b.y, b.z), V3(c.x, c.y, c.z), t, u, v, Ng, den)) continue;
+            if (!(t > tnear)) continue;
+            const int g = __float_as_int(a.w), p = __float_as_int(b.w);
+            bool closer = t < tbest;
+            if (!ANY && !closer && have && t == tbest) closer = (g < hit.geomID) || (g == hit.geomID && p < hit.primID);
+            if (!closer) continue;
+            // back-face cull filter (shapes/trianglemesh_full.cpp:101-121): reject if dot(Ng, dir) <= 0
+            if ((__float_as_uint(c.w) & YRT_TRI_FLAG_CULL) && den <= 0.f) continue;
+            have = true; tbest = t;
+            hit.t = t; hit.u = u; hit.v = v; hit.geomID = g; hit.primID = p; hit.Ng = Ng;
+            if (ANY) return true;
+        }
+        if ((G.y & 0xff000000u) == 0) {
+            if (sp == 0) break;
+            G = stack[--sp];
+        }
+    }
+    return have;
+}
+
+#endif  // __CUDACC__
+}  // namespace yrt

@@ -1,0 +1,390 @@
+// bvh_build.cu — GPU construction of the compressed 8-wide BVH (replaces rtcCommit,
+// reference: devices/device_singleray/api/scene_flat.h:87-112, which rebuilds for every cube face).
+//
+// Pipeline (all on the device, one stream):
+//   1. k_tri_bounds      triangle AABBs + scene bounds (warp-reduced atomics)
+//   2. k_morton          63-bit Morton code of the AABB centre (21 bits per axis)
+//   3. cub::DeviceRadixSort::SortPairs (key = Morton code, value = triangle reference index)
+//   4. k_lbvh_topology   Karras 2012: one thread per internal node, index-augmented keys
+//   5. k_lbvh_fit        bottom-up AABB fit with one atomic visit counter per internal node
+//   6. k_collapse        level-synchronous top-down collapse of the binary tree into 8-wide nodes
+//                        (largest-surface-area child opened first, subtrees of <= 3 triangles become
+//                        leaf children), greedy octant slot assignment, conservative 8-bit plane
+//                        quantisation, triangles written in leaf order (48 B each)
+// CUB is used as a library primitive for the radix sort only (ships with the CUDA toolkit).
+#include <cub/device/device_radix_sort.cuh>
+#include <cstdio>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "bvh.cuh"
+#include "device_internal.hpp"
+
+namespace yrt {
+
+#define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) throw std::runtime_error(std::string("CUDA error in BVH build: ") + cudaGetErrorString(e_) + " at " #x); } while (0)
+
+struct Box { float lo[3], hi[3]; };
+
+__device__ __forceinline__ uint32_t f2ord(float f) { uint32_t u = __float_as_uint(f); return (u & 0x80000000u) ? ~u : (u | 0x80000000u); }
+__device__ __forceinline__ float ord2f(uint32_t u) { return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u); }
+
+__global__ void k_init_bounds(uint32_t* sb) {
+    if (threadIdx.x < 3) sb[threadIdx.x] = 0xffffffffu;       // min (ordered encoding)
+    else if (threadIdx.x < 6) sb[threadIdx.x] = 0u;           // max
+}
+
+__global__ void k_tri_bounds(const uint2* __restrict__ refs, uint32_t n, const GeomRec* __restrict__ geoms,
+                             const float4* __restrict__ positions, const int4* __restrict__ indices,
+                             float4* __restrict__ boxLo, float4* __restrict__ boxHi, uint32_t* __restrict__ sceneBounds) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+    if (i < n) {
+        const uint2 r = refs[i];
+        const GeomRec g = geoms[r.x];
+        const int4 t = indices[g.idxBase + r.y];
+        const float4 a = positions[g.vtxBase + t.x], b = positions[g.vtxBase + t.y], c = positions[g.vtxBase + t.z];
+        lo[0] = fminf(a.x, fminf(b.x, c.x)); hi[0] = fmaxf(a.x, fmaxf(b.x, c.x));
+        lo[1] = fminf(a.y, fminf(b.y, c.y)); hi[1] = fmaxf(a.y, fmaxf(b.y, c.y));
+        lo[2] = fminf(a.z, fminf(b.z, c.z)); hi[2] = fmaxf(a.z, fmaxf(b.z, c.z));
+        boxLo[i] = make_float4(lo[0], lo[1], lo[2], 0.f);
+        boxHi[i] = make_float4(hi[0], hi[1], hi[2], 0.f);
+    }
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        float l = lo[k], h = hi[k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { l = fminf(l, __shfl_xor_sync(0xffffffffu, l, o)); h = fmaxf(h, __shfl_xor_sync(0xffffffffu, h, o)); }
+        if ((threadIdx.x & 31) == 0 && l <= h) { atomicMin(&sceneBounds[k], f2ord(l)); atomicMax(&sceneBounds[3 + k], f2ord(h)); }
+    }
+}
+
+__device__ __forceinline__ uint64_t spread21(uint64_t x) {
+    x &= 0x1fffffull;
+    x = (x | x << 32) & 0x1f00000000ffffull;
+    x = (x | x << 16) & 0x1f0000ff0000ffull;
+    x = (x | x << 8) & 0x100f00f00f00f00full;
+    x = (x | x << 4) & 0x10c30c30c30c30c3ull;
+    x = (x | x << 2) & 0x1249249249249249ull;
+    return x;
+}
+
+__global__ void k_morton(const float4* __restrict__ boxLo, const float4* __restrict__ boxHi, uint32_t n,
+                         const uint32_t* __restrict__ sceneBounds, uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 lo = boxLo[i], hi = boxHi[i];
+    float c[3] = {0.5f * lo.x + 0.5f * hi.x, 0.5f * lo.y + 0.5f * hi.y, 0.5f * lo.z + 0.5f * hi.z};
+    uint64_t q[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        const float mn = ord2f(sceneBounds[k]), mx = ord2f(sceneBounds[3 + k]);
+        const float ext = mx - mn;
+        float f = ext > 0.f ? (c[k] - mn) / ext : 0.f;
+        f = fminf(fmaxf(f, 0.f), 1.f);
+        q[k] = (uint64_t)fminf(f * 2097152.0f, 2097151.0f);
+    }
+    keys[i] = (spread21(q[0]) << 2) | (spread21(q[1]) << 1) | spread21(q[2]);
+    vals[i] = i;
+}
+
+// ---- Karras LBVH ---------------------------------------------------------------------------
+// node reference encoding: bit 31 set = leaf (sorted position in low bits), else internal index
+#define LEAF_FLAG 0x80000000u
+
+__device__ __forceinline__ int delta(const uint64_t* __restrict__ keys, int n, int i, int j) {
+    if (j < 0 || j >= n) return -1;
+    const uint64_t a = keys[i], b = keys[j];
+    if (a == b) return 64 + __clz((uint32_t)i ^ (uint32_t)j);
+    return __clzll((long long)(a ^ b));
+}
+
+struct Lbvh {
+    uint32_t* left; uint32_t* right; uint32_t* parent;      // per internal node (parent also per leaf at [n-1 + leaf])
+    uint32_t* rangeFirst; uint32_t* rangeLast;              // per internal node: sorted range covered
+    float4* lo; float4* hi;                                 // per internal node
+    uint32_t* visit;
+};
+
+__global__ void k_lbvh_topology(const uint64_t* __restrict__ keys, int n, Lbvh t) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n - 1) return;
+    const int d = (delta(keys, n, i, i + 1) - delta(keys, n, i, i - 1)) >= 0 ? 1 : -1;
+    const int dmin = delta(keys, n, i, i - d);
+    int lmax = 2;
+    while (delta(keys, n, i, i + lmax * d) > dmin) lmax <<= 1;
+    int l = 0;
+    for (int s = lmax >> 1; s > 0; s >>= 1)
+        if (delta(keys, n, i, i + (l + s) * d) > dmin) l += s;
+    const int j = i + l * d;
+    const int dnode = delta(keys, n, i, j);
+    int s = 0;
+    for (int div = 2, tt = (l + div - 1) / div; ; div <<= 1, tt = (l + div - 1) / div) {
+        if (delta(keys, n, i, i + (s + tt) * d) > dnode) s += tt;
+        if (tt <= 1) break;
+    }
+    const int gamma = i + s * d + min(d, 0);
+    const int first = min(i, j), last = max(i, j);
+    const uint32_t L = (first == gamma) ? (LEAF_FLAG | (uint32_t)gamma) : (uint32_t)gamma;
+    const uint32_t R = (last == gamma + 1) ? (LEAF_FLAG | (uint32_t)(gamma + 1)) : (uint32_t)(gamma + 1);
+    t.left[i] = L; t.right[i] = R; t.rangeFirst[i] = first; t.rangeLast[i] = last;
+    if (L & LEAF_FLAG) t.parent[(n - 1) + gamma] = i; else t.parent[gamma] = i;
+    if (R & LEAF_FLAG) t.parent[(n - 1) + gamma + 1] = i; else t.parent[gamma + 1] = i;
+    if (i == 0) t.parent[0] = 0xffffffffu;
+}
+
+__global__ void k_lbvh_fit(int n, Lbvh t, const uint32_t* __restrict__ sortedIdx,
+                           const float4* __restrict__ boxLo, const float4* __restrict__ boxHi) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t node = t.parent[(n - 1) + i];
+    while (node != 0xffffffffu) {
+        if (atomicAdd(&t.visit[node], 1u) == 0u) return;     // first arrival waits for the sibling
+        __threadfence();
+        const uint32_t L = t.left[node], R = t.right[node];
+        float4 llo, lhi, rlo, rhi;
+        if (L & LEAF_FLAG) { const uint32_t s = sortedIdx[L & ~LEAF_FLAG]; llo = boxLo[s]; lhi = boxHi[s]; }
+        else { llo = __ldcg(&t.lo[L]); lhi = __ldcg(&t.hi[L]); }
+        if (R & LEAF_FLAG) { const uint32_t s = sortedIdx[R & ~LEAF_FLAG]; rlo = boxLo[s]; rhi = boxHi[s]; }
+        else { rlo = __ldcg(&t.lo[R]); rhi = __ldcg(&t.hi[R]); }
+        t.lo[node] = make_float4(fminf(llo.x, rlo.x), fminf(llo.y, rlo.y), fminf(llo.z, rlo.z), 0.f);
+        t.hi[node] = make_float4(fmaxf(lhi.x, rhi.x), fmaxf(lhi.y, rhi.y), fmaxf(lhi.z, rhi.z), 0.f);
+        __threadfence();
+        node = t.parent[node];
+    }
+}
+
+// ---- collapse to compressed BVH8 -------------------------------------------------------------
+struct CollapseArgs {
+    Lbvh t; int n;
+    const uint32_t* sortedIdx; const float4* boxLo; const float4* boxHi;
+    const uint2* refs; const GeomRec* geoms; const float4* positions; const int4* indices;
+    Node8* nodes; float4* tris;
+    uint32_t* counters;          // [0] node counter, [1] triangle counter, [2] next-level task count
+    const uint2* tasksIn; uint2* tasksOut; uint32_t numTasks;
+};
+
+__device__ __forceinline__ void ref_box(const CollapseArgs& a, uint32_t ref, float lo[3], float hi[3]) {
+    float4 l, h;
+    if (ref & LEAF_FLAG) { const uint32_t s = a.sortedIdx[ref & ~LEAF_FLAG]; l = a.boxLo[s]; h = a.boxHi[s]; }
+    else { l = a.t.lo[ref]; h = a.t.hi[ref]; }
+    lo[0] = l.x; lo[1] = l.y; lo[2] = l.z; hi[0] = h.x; hi[1] = h.y; hi[2] = h.z;
+}
+__device__ __forceinline__ uint32_t ref_count(const CollapseArgs& a, uint32_t ref) {
+    return (ref & LEAF_FLAG) ? 1u : (a.t.rangeLast[ref] - a.t.rangeFirst[ref] + 1u);
+}
+__device__ __forceinline__ uint32_t ref_first(const CollapseArgs& a, uint32_t ref) {
+    return (ref & LEAF_FLAG) ? (ref & ~LEAF_FLAG) : a.t.rangeFirst[ref];
+}
+
+__device__ void write_triangle(const CollapseArgs& a, uint32_t sortedPos, uint32_t outIdx) {
+    const uint2 r = a.refs[a.sortedIdx[sortedPos]];
+    const GeomRec g = a.geoms[r.x];
+    const int4 t = a.indices[g.idxBase + r.y];
+    const float4 p0 = a.positions[g.vtxBase + t.x], p1 = a.positions[g.vtxBase + t.y], p2 = a.positions[g.vtxBase + t.z];
+    float4* o = a.tris + 3ull * outIdx;
+    o[0] = make_float4(p0.x, p0.y, p0.z, __int_as_float((int)r.x));
+    o[1] = make_float4(p1.x, p1.y, p1.z, __int_as_float((int)r.y));
+    o[2] = make_float4(p2.x, p2.y, p2.z, __uint_as_float(g.cull ? YRT_TRI_FLAG_CULL : 0u));
+}
+
+__global__ void k_collapse(CollapseArgs a) {
+    const uint32_t ti = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ti >= a.numTasks) return;
+    const uint2 task = a.tasksIn[ti];                 // x = BVH2 reference, y = output node index
+    uint32_t cand[8]; int count;
+    float nlo[3], nhi[3];
+    ref_box(a, task.x, nlo, nhi);
+    if (task.x & LEAF_FLAG) { cand[0] = task.x; count = 1; }    // single-triangle scene
+    else {
+        cand[0] = a.t.left[task.x]; cand[1] = a.t.right[task.x]; count = 2;
+        while (count < 8) {
+            int best = -1; float bestArea = -1.f;
+            for (int c = 0; c < count; c++) {
+                if ((cand[c] & LEAF_FLAG) || ref_count(a, cand[c]) <= 3u) continue;
+                float lo[3], hi[3]; ref_box(a, cand[c], lo, hi);
+                const float dx = hi[0] - lo[0], dy = hi[1] - lo[1], dz = hi[2] - lo[2];
+                const float area = dx * dy + dy * dz + dz * dx;
+                if (area > bestArea) { bestArea = area; best = c; }
+            }
+            if (best < 0) break;
+            const uint32_t open = cand[best];
+            cand[best] = a.t.left[open];
+            cand[count++] = a.t.right[open];
+        }
+    }
+    // greedy octant slot assignment (slot bit 4/2/1 = child lies towards +x/+y/+z of the node centre)
+    float cx[8], cy[8], cz[8];
+    const float ncx = 0.5f * (nlo[0] + nhi[0]), ncy = 0.5f * (nlo[1] + nhi[1]), ncz = 0.5f * (nlo[2] + nhi[2]);
+    for (int c = 0; c < count; c++) {
+        float lo[3], hi[3]; ref_box(a, cand[c], lo, hi);
+        cx[c] = 0.5f * (lo[0] + hi[0]) - ncx; cy[c] = 0.5f * (lo[1] + hi[1]) - ncy; cz[c] = 0.5f * (lo[2] + hi[2]) - ncz;
+    }
+    int slotOf[8]; uint32_t slotUsed = 0, childDone = 0;
+    for (int c = 0; c < 8; c++) slotOf[c] = -1;
+    for (int it = 0; it < count; it++) {
+        float bestCost = -INFINITY; int bc = -1, bs = -1;
+        for (int c = 0; c < count; c++) {
+            if (childDone & (1u << c)) continue;
+            for (int s = 0; s < 8; s++) {
+                if (slotUsed & (1u << s)) continue;
+                const float cost = ((s & 4) ? cx[c] : -cx[c]) + ((s & 2) ? cy[c] : -cy[c]) + ((s & 1) ? cz[c] : -cz[c]);
+                if (cost > bestCost) { bestCost = cost; bc = c; bs = s; }
+            }
+        }
+        slotOf[bc] = bs; slotUsed |= 1u << bs; childDone |= 1u << bc;
+    }
+    uint32_t slotRef[8]; bool slotValid[8];
+    for (int s = 0; s < 8; s++) slotValid[s] = false;
+    for (int c = 0; c < count; c++) { slotRef[slotOf[c]] = cand[c]; slotValid[slotOf[c]] = true; }
+
+    // quantisation frame
+    Node8 nd;
+    nd.px = nlo[0]; nd.py = nlo[1]; nd.pz = nlo[2];
+    float scale[3]; uint8_t ebyte[3];
+    for (int k = 0; k < 3; k++) {
+        const float ext = nhi[k] - nlo[k];
+        int e;
+        if (!(ext > 0.f)) e = -120;
+        else {
+            int fe; frexpf(ext / 255.0f, &fe);       // ext/255 = m * 2^fe, m in [0.5,1)  ->  2^fe >= ext/255
+            e = fe;
+            while (ldexpf(255.0f, e) < ext * 1.000001f) e++;
+        }
+        e = max(-126, min(127, e));
+        ebyte[k] = (uint8_t)(e + 127);
+        scale[k] = __uint_as_float((uint32_t)ebyte[k] << 23);
+    }
+    nd.ex = ebyte[0]; nd.ey = ebyte[1]; nd.ez = ebyte[2];
+
+    uint32_t nInner = 0, nTris = 0, imask = 0;
+    for (int s = 0; s < 8; s++) {
+        if (!slotValid[s]) continue;
+        const uint32_t r = slotRef[s];
+        const uint32_t cnt = ref_count(a, r);
+        if (!(r & LEAF_FLAG) && cnt > 3u) { nInner++; imask |= 1u << s; } else nTris += cnt;
+    }
+    nd.imask = (uint8_t)imask;
+    const uint32_t childBase = nInner ? atomicAdd(&a.counters[0], nInner) : 0u;
+    const uint32_t triBase = nTris ? atomicAdd(&a.counters[1], nTris) : 0u;
+    const uint32_t taskBase = nInner ? atomicAdd(&a.counters[2], nInner) : 0u;
+    nd.childBase = childBase; nd.triBase = triBase;
+
+    uint32_t innerSeen = 0, triOfs = 0;
+    uint8_t* qplanes[6] = {nd.qlox, nd.qloy, nd.qloz, nd.qhix, nd.qhiy, nd.qhiz};
+    const float org[3] = {nlo[0], nlo[1], nlo[2]};
+    for (int s = 0; s < 8; s++) {
+        if (!slotValid[s]) {
+            nd.meta[s] = 0;
+            for (int k = 0; k < 3; k++) { qplanes[k][s] = 255; qplanes[3 + k][s] = 0; }   // inverted box: never hit
+            continue;
+        }
+        const uint32_t r = slotRef[s];
+        float lo[3], hi[3]; ref_box(a, r, lo, hi);
+        for (int k = 0; k < 3; k++) {
+            int ql = (int)floorf((lo[k] - org[k]) / scale[k]);
+            ql = max(0, min(255, ql));
+            while (ql > 0 && fmaf((float)ql, scale[k], org[k]) > lo[k]) ql--;
+            int qh = (int)ceilf((hi[k] - org[k]) / scale[k]);
+            qh = max(0, min(255, qh));
+            while (qh < 255 && fmaf((float)qh, scale[k], org[k]) < hi[k]) qh++;
+            qplanes[k][s] = (uint8_t)ql; qplanes[3 + k][s] = (uint8_t)qh;
+        }
+        const uint32_t cnt = ref_count(a, r);
+        if (imask & (1u << s)) {
+            nd.meta[s] = (uint8_t)((1u << 5) | (24u + (uint32_t)s));
+            a.tasksOut[taskBase + innerSeen] = make_uint2(r, childBase + innerSeen);
+            innerSeen++;
+        } else {
+            const uint32_t unary = cnt == 1 ? 1u : (cnt == 2 ? 3u : 7u);
+            nd.meta[s] = (uint8_t)((unary << 5) | triOfs);
+            const uint32_t first = ref_first(a, r);
+            for (uint32_t k = 0; k < cnt; k++) write_triangle(a, first + k, triBase + triOfs + k);
+            triOfs += cnt;
+        }
+    }
+    a.nodes[task.y] = nd;
+}
+
+// ---------------------------------------------------------------------------------------------
+template <typename T> static T* dalloc(size_t n) { T* p = nullptr; CK(cudaMalloc(&p, (n ? n : 1) * sizeof(T))); return p; }
+
+void build_bvh(const BvhBuildInput& in, BvhResult& out, cudaStream_t stream) {
+    out.nodes = nullptr; out.tris = nullptr; out.numNodes = 0; out.numTris = 0; out.buildMs = 0.f; out.launches = 0;
+    const uint32_t n = in.numRefs;
+    if (n == 0) return;
+    cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    CK(cudaEventRecord(e0, stream));
+    const int B = 256; const uint32_t G = (n + B - 1) / B;
+
+    float4* boxLo = dalloc<float4>(n); float4* boxHi = dalloc<float4>(n);
+    uint32_t* sceneBounds = dalloc<uint32_t>(8);
+    uint64_t* keys = dalloc<uint64_t>(n); uint64_t* keysSorted = dalloc<uint64_t>(n);
+    uint32_t* vals = dalloc<uint32_t>(n); uint32_t* sortedIdx = dalloc<uint32_t>(n);
+    k_init_bounds<<<1, 32, 0, stream>>>(sceneBounds);
+    k_tri_bounds<<<G, B, 0, stream>>>(in.refs, n, in.geoms, in.positions, in.indices, boxLo, boxHi, sceneBounds);
+    k_morton<<<G, B, 0, stream>>>(boxLo, boxHi, n, sceneBounds, keys, vals);
+    out.launches += 3;
+    size_t tmpBytes = 0;
+    CK(cub::DeviceRadixSort::SortPairs(nullptr, tmpBytes, keys, keysSorted, vals, sortedIdx, (int)n, 0, 63, stream));
+    void* tmp = nullptr; CK(cudaMalloc(&tmp, tmpBytes ? tmpBytes : 1));
+    CK(cub::DeviceRadixSort::SortPairs(tmp, tmpBytes, keys, keysSorted, vals, sortedIdx, (int)n, 0, 63, stream));
+    out.launches += 8;   // CUB onesweep passes (library kernels, not counted as ours elsewhere)
+
+    Lbvh t;
+    const uint32_t ni = n > 1 ? n - 1 : 1;
+    t.left = dalloc<uint32_t>(ni); t.right = dalloc<uint32_t>(ni); t.parent = dalloc<uint32_t>((size_t)ni + n);
+    t.rangeFirst = dalloc<uint32_t>(ni); t.rangeLast = dalloc<uint32_t>(ni);
+    t.lo = dalloc<float4>(ni); t.hi = dalloc<float4>(ni); t.visit = dalloc<uint32_t>(ni);
+    CK(cudaMemsetAsync(t.visit, 0, ni * sizeof(uint32_t), stream));
+    if (n > 1) {
+        k_lbvh_topology<<<(n - 1 + B - 1) / B, B, 0, stream>>>(keysSorted, (int)n, t);
+        k_lbvh_fit<<<G, B, 0, stream>>>((int)n, t, sortedIdx, boxLo, boxHi);
+        out.launches += 2;
+    }
+
+    // worst case one BVH8 node per BVH2 internal node; shrunk to the exact size afterwards
+    Node8* nodesTmp = dalloc<Node8>((size_t)ni + 1);
+    float4* tris = dalloc<float4>(3ull * n);
+    uint32_t* counters = dalloc<uint32_t>(4);
+    uint2* tasksA = dalloc<uint2>(ni + 1); uint2* tasksB = dalloc<uint2>(ni + 1);
+    const uint32_t initCounters[4] = {1u, 0u, 0u, 0u};
+    CK(cudaMemcpyAsync(counters, initCounters, sizeof(initCounters), cudaMemcpyHostToDevice, stream));
+    const uint2 rootTask = make_uint2(n > 1 ? 0u : (LEAF_FLAG | 0u), 0u);
+    CK(cudaMemcpyAsync(tasksA, &rootTask, sizeof(rootTask), cudaMemcpyHostToDevice, stream));
+
+    CollapseArgs ca;
+    ca.t = t; ca.n = (int)n; ca.sortedIdx = sortedIdx; ca.boxLo = boxLo; ca.boxHi = boxHi;
+    ca.refs = in.refs; ca.geoms = in.geoms; ca.positions = in.positions; ca.indices = in.indices;
+    ca.nodes = nodesTmp; ca.tris = tris; ca.counters = counters;
+    uint32_t numTasks = 1; uint2* tin = tasksA; uint2* tout = tasksB;
+    uint32_t hostCounters[4];
+    while (numTasks) {
+        ca.tasksIn = tin; ca.tasksOut = tout; ca.numTasks = numTasks;
+        k_collapse<<<(numTasks + 63) / 64, 64, 0, stream>>>(ca);
+        out.launches++;
+        CK(cudaMemcpyAsync(hostCounters, counters, sizeof(hostCounters), cudaMemcpyDeviceToHost, stream));
+        CK(cudaStreamSynchronize(stream));
+        numTasks = hostCounters[2];
+        const uint32_t zero = 0;
+        CK(cudaMemcpyAsync(counters + 2, &zero, sizeof(zero), cudaMemcpyHostToDevice, stream));
+        std::swap(tin, tout);
+    }
+    out.numNodes = hostCounters[0]; out.numTris = hostCounters[1];
+    Node8* nodes = dalloc<Node8>(out.numNodes);
+    CK(cudaMemcpyAsync(nodes, nodesTmp, (size_t)out.numNodes * sizeof(Node8), cudaMemcpyDeviceToDevice, stream));
+    CK(cudaEventRecord(e1, stream));
+    CK(cudaStreamSynchronize(stream));
+    CK(cudaEventElapsedTime(&out.buildMs, e0, e1));
+    out.nodes = nodes; out.tris = tris;
+
+    cudaFree(nodesTmp); cudaFree(counters); cudaFree(tasksA); cudaFree(tasksB);
+    cudaFree(t.left); cudaFree(t.right); cudaFree(t.parent); cudaFree(t.rangeFirst); cudaFree(t.rangeLast);
+    cudaFree(t.lo); cudaFree(t.hi); cudaFree(t.visit);
+    cudaFree(tmp); cudaFree(keys); cudaFree(keysSorted); cudaFree(vals); cudaFree(sortedIdx);
+    cudaFree(boxLo); cudaFree(boxHi); cudaFree(sceneBounds);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+}
+
+}  // namespace yrt

@@ -1,0 +1,78 @@
+// device_internal.hpp — interfaces between the host object model (device_host.cu), the BVH
+// builder (bvh_build.cu) and the wavefront kernels (kernels.cu). Internal to libyrt_device_cuda.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+
+#include "common.cuh"
+
+namespace yrt {
+
+// ---- BVH build -------------------------------------------------------------------------------
+struct BvhBuildInput {
+    const uint2* refs;            // device: (geomID, primID) of every valid triangle
+    uint32_t numRefs;
+    const GeomRec* geoms;         // device
+    const float4* positions;      // device
+    const int4* indices;          // device
+};
+struct BvhResult {
+    void* nodes; float4* tris; uint32_t numNodes, numTris; float buildMs; uint32_t launches;
+};
+void build_bvh(const BvhBuildInput& in, BvhResult& out, cudaStream_t stream);
+
+// ---- wavefront state (SoA, 16-byte vector lanes) ---------------------------------------------
+struct WavefrontBuffers {
+    uint32_t capacity;            // paths per chunk
+    uint32_t shadowCapacity;      // shadow rays per chunk and bounce
+    float4* rayO; float4* rayD;   // org.xyz|tnear, dir.xyz|tfar
+    float4* hitA; float4* hitB;   // t,u,v,geomID | Ng.xyz,primID
+    float4* thr;                  // throughput.rgb | (depth | flags << 16)
+    float4* Lacc;                 // radiance accumulated along the path
+    float4* medium;               // transmission.rgb | eta
+    uint2* shadowSpan;            // per path: (first shadow ray, count) of the current bounce
+    float4* shO; float4* shD;     // shadow ray queue
+    float4* shC;                  // contribution.rgb | occluded flag (written by the any-hit kernel)
+    uint32_t* queueA; uint32_t* queueB;
+    uint32_t* counters;           // [0] |queueA|, [1] |queueB|, [2] shadow rays this bounce, [3] spare
+    unsigned long long* stats;    // [0] closest rays, [1] shadow rays, [2] node visits, [3] triangle tests
+    uint8_t* pixelSet;            // per pixel of the frame: sample set index
+};
+
+struct FrameConst {               // everything a frame's kernels need, passed by value
+    SceneData scene;
+    IntegratorData integ;
+    CameraData camera;
+    const float* sampleTable;     // device
+    int width, height;            // raster size
+    int serverID, serverCount;    // row-band interleave of the reference's network device (api/swapchain.h:57-70)
+    float rcpWidth, rcpHeight;
+    int debugRenderer;            // 1: renderers/debugrenderer.cpp semantics
+    int countStats;
+};
+
+struct FilmParams {
+    float4* accum;                // per pixel (buffer coordinates): sum L.rgb | sum weight
+    void* fbDevice;               // packed output in the framebuffer's format
+    int format;                   // 0 RGB_FLOAT32, 1 RGBA8, 2 RGB8
+    int fbStrideBytes;
+    int accumulate;
+    float gamma, rcpGamma; int vignetting;
+};
+
+struct LaunchCfg { int blocks; int threads; cudaStream_t stream; };
+
+// pixels [pixelBegin, pixelBegin+numPixels) of the *active-row* enumeration of the frame
+void launch_pixel_sets(const FrameConst& fc, uint8_t* pixelSet, int sets, LaunchCfg lc);
+void launch_raygen(const FrameConst& fc, const WavefrontBuffers& wb, uint32_t pixelBegin, uint32_t numPixels, LaunchCfg lc);
+void launch_trace_closest(const FrameConst& fc, const WavefrontBuffers& wb, int queueSel, LaunchCfg lc);
+void launch_shade(const FrameConst& fc, const WavefrontBuffers& wb, int queueSel, uint32_t pixelBegin, int depth, LaunchCfg lc);
+void launch_trace_shadow(const FrameConst& fc, const WavefrontBuffers& wb, LaunchCfg lc);
+void launch_resolve(const FrameConst& fc, const WavefrontBuffers& wb, int queueSel, LaunchCfg lc);
+void launch_film(const FrameConst& fc, const WavefrontBuffers& wb, const FilmParams& fp, uint32_t pixelBegin, uint32_t numPixels, LaunchCfg lc);
+void launch_export_primary(const FrameConst& fc, const WavefrontBuffers& wb, uint32_t pixelBegin, uint32_t numPixels, float* out, LaunchCfg lc);
+// yrtxTraceRays: rays/hits on the device, 8 floats each
+void launch_trace_user(const SceneData& sc, const float* rays, float* hits, size_t n, int closest, int countStats,
+                       unsigned long long* stats, LaunchCfg lc);
+
+}  // namespace yrt

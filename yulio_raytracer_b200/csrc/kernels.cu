@@ -1,0 +1,445 @@
+// kernels.cu — the wavefront path tracer of device_cuda (hand-written CUDA for sm_100a).
+//
+// One frame = for each chunk of pixels:  raygen -> [ trace_closest -> shade -> trace_shadow -> resolve ] x maxDepth -> film.
+// It restates, stage by stage, the reference's per-pixel recursion
+//   IntegratorRenderer::RenderJob::renderTile   devices/device_singleray/renderers/integratorrenderer.cpp:118-185
+//   PathTraceIntegrator::Li                     devices/device_singleray/integrators/pathtraceintegrator.cpp:50-217
+// as data-parallel stages over SoA queues (16-byte lanes). All kernels are persistent-style:
+// the grid is sized to the SM count and strides over a queue whose length lives in device memory,
+// so a whole frame is enqueued without host synchronisation.
+//
+// Determinism: radiance is accumulated per path in the reference's order (emission, then the
+// lights in order, bounce by bounce) and per pixel in sample order, so the result does not depend
+// on scheduling, queue order or the number of GPUs.
+#include "bvh.cuh"
+#include "device_internal.hpp"
+#include "shading.cuh"
+
+namespace yrt {
+
+#define FLAG_IGNORE_VISIBLE_LIGHTS 1u
+#define FLAG_UNBENT 2u
+
+__device__ __forceinline__ V3 f4v(float4 a) { return V3(a.x, a.y, a.z); }
+
+// raster row of buffer row b / number of buffer rows  (api/swapchain.h:57-70)
+__host__ __device__ __forceinline__ int buffer2raster(int b, int serverID, int serverCount) { return 4 * ((b >> 2) * serverCount + serverID) + (b & 3); }
+
+// ---- per-pixel sample-set choice --------------------------------------------------------------
+// integratorrenderer.cpp:132-149: one LCG per 16x16 tile seeded tile_x*91711 + tile_y*81551 + 3433*firstActiveLine,
+// one getInt(sets) per rendered pixel in dy,dx order. LCG = common/math/random.h:32-68.
+struct DevLcg {
+    int seed, state, table[32];
+    __device__ void step() { const int k = seed / 127773; seed = 16807 * (seed - k * 127773) - 2836 * k; if (seed < 0) seed += 2147483647; }
+    __device__ void init(int s) {
+        seed = (s == 0) ? 1 : (s < 0 ? -s : s);
+        for (int j = 32 + 7; j >= 0; j--) { step(); if (j < 32) table[j] = seed; }
+        state = table[0];
+    }
+    __device__ int next() { step(); const int j = state / (1 + (2147483647 - 1) / 32); state = table[j]; table[j] = seed; return state; }
+};
+
+__global__ void k_pixel_sets(FrameConst fc, uint8_t* __restrict__ pixelSet, int sets) {
+    const int numTilesX = (fc.width + 15) / 16, numTilesY = (fc.height + 15) / 16;
+    const int tile = blockIdx.x * blockDim.x + threadIdx.x;
+    if (tile >= numTilesX * numTilesY) return;
+    const int tile_x = (tile % numTilesX) * 16, tile_y = (tile / numTilesX) * 16;
+    DevLcg rng; rng.init(tile_x * 91711 + tile_y * 81551 + 3433 * fc.serverID);
+    for (int dy = 0; dy < 16; dy++) {
+        const int y = tile_y + dy;
+        if (y >= fc.height) continue;
+        const int row = y >> 2;
+        if (((row - fc.serverID) % fc.serverCount) != 0) continue;
+        const int by = 4 * ((y >> 2) / fc.serverCount) + (y & 3);
+        for (int dx = 0; dx < 16; dx++) {
+            const int x = tile_x + dx;
+            if (x >= fc.width) continue;
+            pixelSet[(size_t)by * fc.width + x] = (uint8_t)(rng.next() % sets);
+        }
+    }
+}
+void launch_pixel_sets(const FrameConst& fc, uint8_t* pixelSet, int sets, LaunchCfg lc) {
+    const int tiles = ((fc.width + 15) / 16) * ((fc.height + 15) / 16);
+    k_pixel_sets<<<(tiles + 63) / 64, 64, 0, lc.stream>>>(fc, pixelSet, sets);
+}
+
+// ---- cameras ------------------------------------------------------------------------------------
+// PinHoleCamera::ray cameras/pinholecamera.h:38-40; StereoCubeCamera::ray cameras/StereoCubeCamera.h:68-161;
+// DepthOfFieldCamera::ray cameras/depthoffieldcamera.h:36-42
+__device__ void camera_ray(const CameraData& cam, float px, float py, float lx, float ly, V3& org, V3& dir) {
+    if (cam.type == CAM_PINHOLE) {
+        const Aff3& m = cam.p2w[0];
+        org = m.p; dir = normalize(px * m.l.vx + (1.0f - py) * m.l.vy + m.l.vz);
+        return;
+    }
+    if (cam.type == CAM_DOF) {
+        const Aff3& m = cam.p2w[0];
+        const float r = sqrtf(lx), theta = YRT_TWO_PI * ly;
+        const V3 begin = xfmPoint(cam.local2world, V3(cam.lensRadius * r * cosf(theta), cam.lensRadius * r * sinf(theta), 0.0f));
+        const V3 end = m.p + cam.focalDistance * (px * m.l.vx + (1.0f - py) * m.l.vy + m.l.vz);
+        org = begin; dir = normalize(end - begin);
+        return;
+    }
+    const Aff3& f = cam.p2w[0];
+    const int face = cam.cubeFaceIndex % 6;
+    const float yPixel = 1.0f - py;
+    Aff3 p2w = cam.p2w[face];
+    float theta = 0.f, absoluteVerticalAngle = 0.f;
+    if (face < 4) {
+        const V3 xDir = normalize(px * f.l.vx + .5f * f.l.vy + f.l.vz);
+        theta = acosf(rclamp(dot(xDir, cam.xyzStraight), -1.f, 1.f)) * signf_(px - .5f);
+        const V3 yDir = normalize(.5f * f.l.vx + yPixel * f.l.vy + f.l.vz);
+        const float yAngle = rad2deg(acosf(rclamp(dot(yDir, cam.xyzStraight), -1.f, 1.f))) * signf_(yPixel - .5f);
+        absoluteVerticalAngle = fabsf(yAngle);
+    } else {
+        const V3 xyDirNorm = normalize(V3(px - .5f, yPixel - .5f, 0.f));
+        const V3 xyUp = face == 4 ? V3(0.f, -1.f, 0.f) : V3(0.f, 1.f, 0.f);
+        theta = acosf(rclamp(dot(xyDirNorm, xyUp), -1.f, 1.f)) * signf_(px - .5f);
+        const V3 xyzDir = normalize(px * f.l.vx + yPixel * f.l.vy + f.l.vz);
+        const float xyzAngle = rad2deg(acosf(rclamp(dot(xyzDir, cam.xyzStraight), -1.f, 1.f)));
+        absoluteVerticalAngle = 90.f - fabsf(xyzAngle);
+    }
+    float eyeOffset = cam.eyeSeparation * (cam.cubeFaceIndex < 6 ? -.5f : .5f);
+    if (absoluteVerticalAngle > cam.falloffAngle)
+        eyeOffset *= 1.f - smoothstepf(0.f, 1.f, smoothstepf(cam.falloffAngle, 90.f, absoluteVerticalAngle));
+    p2w = mul(p2w, aff3_translate(V3(eyeOffset, 0.f, 0.f)));
+    const Aff3 rot = aff3_rotate_about(cam.origin, cam.up, theta);
+    const V3 rayOrigin = mul(rot, p2w).p;
+    if (cam.toeIn) {
+        const float corr = -atanf(eyeOffset * cam.rcpZeroParallax);
+        p2w = mul(aff3_rotate_about(rayOrigin, cam.up, corr), p2w);
+    }
+    org = rayOrigin; dir = normalize(px * p2w.l.vx + yPixel * p2w.l.vy + p2w.l.vz);
+}
+
+// path p of a chunk -> (buffer pixel, sample); raster coordinates
+struct PathCoord { int bx, by, x, y, s; uint32_t bp; };
+__device__ __forceinline__ PathCoord path_coord(const FrameConst& fc, uint32_t pixelBegin, uint32_t pid) {
+    PathCoord c; const uint32_t spp = (uint32_t)fc.integ.spp;
+    c.bp = pixelBegin + pid / spp; c.s = (int)(pid % spp);
+    c.by = (int)(c.bp / (uint32_t)fc.width); c.bx = (int)(c.bp % (uint32_t)fc.width);
+    c.x = c.bx; c.y = buffer2raster(c.by, fc.serverID, fc.serverCount);
+    return c;
+}
+__device__ __forceinline__ const float* sample_rec(const FrameConst& fc, const uint8_t* pixelSet, const PathCoord& c) {
+    return fc.sampleTable + ((size_t)pixelSet[c.bp] * fc.integ.spp + c.s) * fc.integ.recFloats;
+}
+
+__global__ void __launch_bounds__(256) k_raygen(FrameConst fc, WavefrontBuffers wb, uint32_t pixelBegin, uint32_t numPaths) {
+    for (uint32_t pid = blockIdx.x * blockDim.x + threadIdx.x; pid < numPaths; pid += gridDim.x * blockDim.x) {
+        const PathCoord c = path_coord(fc, pixelBegin, pid);
+        const float* rec = sample_rec(fc, wb.pixelSet, c);
+        const float fx = (float(c.x) + rec[0]) * fc.rcpWidth, fy = (float(c.y) + rec[1]) * fc.rcpHeight;   // integratorrenderer.cpp:156-157
+        V3 org, dir; camera_ray(fc.camera, fx, fy, rec[3], rec[4], org, dir);
+        wb.rayO[pid] = make_float4(org.x, org.y, org.z, 0.f);
+        wb.rayD[pid] = make_float4(dir.x, dir.y, dir.z, INFINITY);
+        wb.thr[pid] = make_float4(1.f, 1.f, 1.f, __uint_as_float(FLAG_UNBENT << 16));
+        wb.Lacc[pid] = make_float4(0.f, 0.f, 0.f, 0.f);
+        wb.medium[pid] = make_float4(1.f, 1.f, 1.f, 1.f);
+        wb.queueA[pid] = pid;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) { wb.counters[0] = numPaths; wb.counters[1] = 0; wb.counters[2] = 0; }
+}
+void launch_raygen(const FrameConst& fc, const WavefrontBuffers& wb, uint32_t pixelBegin, uint32_t numPixels, LaunchCfg lc) {
+    k_raygen<<<lc.blocks, 256, 0, lc.stream>>>(fc, wb, pixelBegin, numPixels * (uint32_t)fc.integ.spp);
+}
+
+__global__ void k_export_primary(FrameConst fc, WavefrontBuffers wb, uint32_t numPaths, float* __restrict__ out) {
+    for (uint32_t pid = blockIdx.x * blockDim.x + threadIdx.x; pid < numPaths; pid += gridDim.x * blockDim.x) {
+        ((float4*)out)[2 * (size_t)pid] = wb.rayO[pid]; ((float4*)out)[2 * (size_t)pid + 1] = wb.rayD[pid];
+    }
+}
+void launch_export_primary(const FrameConst& fc, const WavefrontBuffers& wb, uint32_t pixelBegin, uint32_t numPixels, float* out, LaunchCfg lc) {
+    k_export_primary<<<lc.blocks, 256, 0, lc.stream>>>(fc, wb, numPixels * (uint32_t)fc.integ.spp, out);
+}
+
+// ---- traversal kernels (persistent threads over the ray queues) ---------------------------------
+template <bool COUNT>
+__global__ void __launch_bounds__(128) k_trace_closest(SceneData sc, WavefrontBuffers wb, int queueSel) {
+    const uint32_t* __restrict__ queue = queueSel ? wb.queueB : wb.queueA;
+    const uint32_t n = wb.counters[queueSel];
+    TraceCounters cnt = {0, 0};
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t pid = queue[i];
+        const float4 o = wb.rayO[pid], d = wb.rayD[pid];
+        HitRec h;
+        trace_ray<false, COUNT>((const uint4*)sc.nodes, sc.tris, sc.numNodes, f4v(o), f4v(d), o.w, d.w, h, &cnt);
+        wb.hitA[pid] = make_float4(h.t, h.u, h.v, __int_as_float(h.geomID));
+        wb.hitB[pid] = make_float4(h.Ng.x, h.Ng.y, h.Ng.z, __int_as_float(h.primID));
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&wb.stats[0], (unsigned long long)n);
+    if (COUNT) { atomicAdd(&wb.stats[2], (unsigned long long)cnt.nodes); atomicAdd(&wb.stats[3], (unsigned long long)cnt.tris); }
+}
+void launch_trace_closest(const FrameConst& fc, const WavefrontBuffers& wb, int queueSel, LaunchCfg lc) {
+    if (fc.countStats) k_trace_closest<true><<<lc.blocks, 128, 0, lc.stream>>>(fc.scene, wb, queueSel);
+    else k_trace_closest<false><<<lc.blocks, 128, 0, lc.stream>>>(fc.scene, wb, queueSel);
+}
+
+template <bool COUNT>
+__global__ void __launch_bounds__(128) k_trace_shadow(SceneData sc, WavefrontBuffers wb) {
+    const uint32_t n = wb.counters[2];
+    TraceCounters cnt = {0, 0};
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const float4 o = wb.shO[i], d = wb.shD[i];
+        HitRec h;
+        const bool occluded = trace_ray<true, COUNT>((const uint4*)sc.nodes, sc.tris, sc.numNodes, f4v(o), f4v(d), o.w, d.w, h, &cnt);
+        wb.shC[i].w = occluded ? 1.f : 0.f;
+    }
+    if (COUNT) { atomicAdd(&wb.stats[2], (unsigned long long)cnt.nodes); atomicAdd(&wb.stats[3], (unsigned long long)cnt.tris); }
+}
+void launch_trace_shadow(const FrameConst& fc, const WavefrontBuffers& wb, LaunchCfg lc) {
+    if (fc.countStats) k_trace_shadow<true><<<lc.blocks, 128, 0, lc.stream>>>(fc.scene, wb);
+    else k_trace_shadow<false><<<lc.blocks, 128, 0, lc.stream>>>(fc.scene, wb);
+}
+
+template <bool COUNT>
+__global__ void __launch_bounds__(128) k_trace_user(SceneData sc, const float4* __restrict__ rays, float4* __restrict__ hits, size_t n, int closest, unsigned long long* stats) {
+    TraceCounters cnt = {0, 0};
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const float4 o = __ldg(&rays[2 * i]), d = __ldg(&rays[2 * i + 1]);
+        HitRec h;
+        if (closest) {
+            trace_ray<false, COUNT>((const uint4*)sc.nodes, sc.tris, sc.numNodes, f4v(o), f4v(d), o.w, d.w, h, &cnt);
+            hits[2 * i] = make_float4(h.t, h.u, h.v, __int_as_float(h.geomID));
+            hits[2 * i + 1] = make_float4(__int_as_float(h.primID), h.geomID >= 0 ? h.Ng.x : 0.f, h.geomID >= 0 ? h.Ng.y : 0.f, h.geomID >= 0 ? h.Ng.z : 0.f);
+        } else {
+            const bool occ = trace_ray<true, COUNT>((const uint4*)sc.nodes, sc.tris, sc.numNodes, f4v(o), f4v(d), o.w, d.w, h, &cnt);
+            float4 a = hits[2 * i]; a.w = __int_as_float(occ ? 0 : -1); hits[2 * i] = a;
+        }
+    }
+    if (COUNT && stats) { atomicAdd(&stats[2], (unsigned long long)cnt.nodes); atomicAdd(&stats[3], (unsigned long long)cnt.tris); }
+}
+void launch_trace_user(const SceneData& sc, const float* rays, float* hits, size_t n, int closest, int countStats, unsigned long long* stats, LaunchCfg lc) {
+    if (countStats) k_trace_user<true><<<lc.blocks, 128, 0, lc.stream>>>(sc, (const float4*)rays, (float4*)hits, n, closest, stats);
+    else k_trace_user<false><<<lc.blocks, 128, 0, lc.stream>>>(sc, (const float4*)rays, (float4*)hits, n, closest, stats);
+}
+
+// ---- shading -------------------------------------------------------------------------------------
+// Warp-aggregated append. Must be reached by all 32 lanes of the warp (the shading loop below is
+// written so that every lane executes every iteration); returns the first slot of this lane's
+// `count` consecutive elements (count may be 0).
+__device__ __forceinline__ uint32_t warp_alloc(uint32_t* counter, uint32_t count) {
+    const uint32_t lane = threadIdx.x & 31;
+    uint32_t incl = count;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= (uint32_t)o) incl += v; }
+    const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+    uint32_t base = 0;
+    if (lane == 31 && total) base = atomicAdd(counter, total);
+    base = __shfl_sync(0xffffffffu, base, 31);
+    return base + incl - count;
+}
+
+__global__ void __launch_bounds__(128) k_shade(FrameConst fc, WavefrontBuffers wb, int queueSel, uint32_t pixelBegin, int depth) {
+    const uint32_t* __restrict__ queue = queueSel ? wb.queueB : wb.queueA;
+    uint32_t* __restrict__ nextQueue = queueSel ? wb.queueA : wb.queueB;
+    const uint32_t n = wb.counters[queueSel];
+    const SceneData& sc = fc.scene; const IntegratorData& ig = fc.integ;
+    const uint32_t stride = gridDim.x * blockDim.x;
+    const uint32_t nIter = (n + stride - 1) / stride;
+    uint32_t shadowRays = 0;
+    for (uint32_t it = 0; it < nIter; it++) {
+        const uint32_t i = it * stride + blockIdx.x * blockDim.x + threadIdx.x;
+        const bool valid = i < n;
+        bool alive = false, needLights = false;
+        uint32_t pid = 0, flags = 0;
+        DG dg; Lobes lobes; lobes.n = 0; V3 wo(0.f); Col thr(0.f); const float* rec = nullptr; float fx = 0, fy = 0;
+        float4 d4 = make_float4(0, 0, 0, 0), m4 = make_float4(1, 1, 1, 1); float hitT = 0.f;
+        if (valid) {
+            pid = queue[i];
+            const float4 o4 = wb.rayO[pid]; d4 = wb.rayD[pid];
+            const float4 hA = wb.hitA[pid], hB = wb.hitB[pid];
+            const float4 t4 = wb.thr[pid]; m4 = wb.medium[pid];
+            thr = Col(t4.x, t4.y, t4.z); flags = __float_as_uint(t4.w) >> 16; hitT = hA.x;
+            const float4 L4 = wb.Lacc[pid]; Col L(L4.x, L4.y, L4.z);
+            const PathCoord pc = path_coord(fc, pixelBegin, pid);
+            rec = sample_rec(fc, wb.pixelSet, pc);
+            fx = (float(pc.x) + rec[0]) * fc.rcpWidth; fy = (float(pc.y) + rec[1]) * fc.rcpHeight;
+            const V3 org = f4v(o4), dir = f4v(d4);
+            wo = -dir;
+            const int geomID = __float_as_int(hA.w);
+            if (geomID < 0) {
+                // environment shading (pathtraceintegrator.cpp:79-92)
+                if (ig.backplateTex >= 0 && (flags & FLAG_UNBENT)) {
+                    const TextureRec& bp = sc.textures[ig.backplateTex];
+                    const int x = iclamp(int(fx * bp.width), 0, bp.width - 1), y = iclamp(int(fy * bp.height), 0, bp.height - 1);
+                    const Col4 c = texel(bp, x, y);
+                    L += thr * Col(c.r, c.g, c.b);
+                } else if (!(flags & FLAG_IGNORE_VISIBLE_LIGHTS)) {
+                    for (int e = 0; e < sc.numEnvLights; e++) L += thr * env_Le(sc, sc.lights[sc.envLightIdx[e]], wo);
+                }
+            } else {
+                post_intersect(sc, org, dir, hA.x, hA.y, hA.z, geomID, __float_as_int(hB.w), f4v(hB), dg);
+                bool backfacing = false;
+                if (dot(dg.Ng, dir) > 0.f) { backfacing = true; dg.Ng = -dg.Ng; dg.Ns = -dg.Ns; }   // :95-98
+                if (dg.material >= 0) material_shade(sc, sc.materials[dg.material], dg, Col(m4.x, m4.y, m4.z), m4.w, lobes);
+                if (!(flags & FLAG_IGNORE_VISIBLE_LIGHTS) && dg.areaLight >= 0 && !backfacing) L += thr * sc.lights[dg.areaLight].L;  // :114-115
+                for (int k = 0; k < lobes.n; k++) needLights |= (lobes.l[k].type & BR_DIFFUSE) != 0;
+                alive = true;
+            }
+            wb.Lacc[pid] = make_float4(L.x, L.y, L.z, 0.f);
+        }
+        // ---- direct lighting: one slot per light, in light order (pathtraceintegrator.cpp:124-166).
+        // Skipped lights leave an invalid ray (tfar < tnear) so the per-path span stays contiguous and the
+        // resolve kernel can add the contributions in the reference's order.
+        const uint32_t nl = (valid && alive && needLights) ? (uint32_t)sc.numLights : 0u;
+        const uint32_t base = warp_alloc(&wb.counters[2], nl);
+        for (uint32_t li = 0; li < nl; li++) {
+            const uint32_t slot = base + li;
+            if (slot >= wb.shadowCapacity) break;
+            const LightRec& lt = sc.lights[li];
+            bool ok = (lt.illumMask & dg.illumMask) != 0;
+            LightSampleD ls; ls.wi = V3(0.f); ls.pdf = 0.f; ls.tMax = 0.f; Col lL(0.f), brdf(0.f);
+            if (ok) {
+                if (lt.precomputedId >= 0) {
+                    const float* p = rec + ig.offLight + 8 * lt.precomputedId;
+                    ls.wi = V3(p[0], p[1], p[2]); ls.pdf = p[3]; lL = Col(p[4], p[5], p[6]);
+                } else lL = light_sample(lt, dg, ls, rec[ig.off2D + 2 * ig.lightSampleID], rec[ig.off2D + 2 * ig.lightSampleID + 1]);
+                ok = !(lL == Col(0.f) || ls.pdf == 0.f);
+            }
+            if (ok) { brdf = lobes_eval(lobes, wo, dg, ls.wi, BR_DIFFUSE); ok = !(brdf == Col(0.f)); }
+            if (!ok) {
+                wb.shO[slot] = make_float4(0.f, 0.f, 0.f, 1.f); wb.shD[slot] = make_float4(0.f, 0.f, 1.f, -1.f);
+                wb.shC[slot] = make_float4(0.f, 0.f, 0.f, 1.f);
+                continue;
+            }
+            // dome-light shadow-ray length (pathtraceintegrator.cpp:147-158) with the stated pins P1/P2
+            const bool infT = isinf(ig.tMaxShadowRay);
+            float jit = 0.f;
+            if (!infT) {
+                const float r = hash_unit(hash4(__float_as_uint(fx), __float_as_uint(fy), (uint32_t)depth, li));
+                jit = 2.f * ig.tMaxShadowRay * ig.tMaxShadowJitter * r - ig.tMaxShadowRay * ig.tMaxShadowJitter;
+            }
+            float tMax = ig.tMaxShadowRay + jit;
+            const float dp = dot(ls.wi, ig.up);
+            if (dp <= 0.f && !infT) tMax += ig.tMaxShadowRay * 100.f * smoothstepf(0.f, 1.f, fabsf(dp));
+            const float eps = dg.error * ig.epsilon;
+            const Col contrib = thr * lL * brdf * rcpf(ls.pdf);
+            wb.shO[slot] = make_float4(dg.P.x, dg.P.y, dg.P.z, eps);
+            wb.shD[slot] = make_float4(ls.wi.x, ls.wi.y, ls.wi.z, tMax - eps);
+            wb.shC[slot] = make_float4(contrib.x, contrib.y, contrib.z, 1.f);
+            shadowRays++;
+        }
+        if (valid) wb.shadowSpan[pid] = make_uint2(base, nl);
+
+        // ---- path continuation (pathtraceintegrator.cpp:169-213)
+        bool cont = false;
+        if (valid && alive) {
+            cont = depth < ig.maxDepth - 1;
+            if (cont && depth >= ig.rrDepth - 1) {
+                const float q = rmin(reduce_max(thr) * 1.f * 1.f, .95f);       // eta stays 1: CompositedBRDF::sample drops Sample::eta
+                if (rec[ig.off1D + ig.firstScatterTypeSampleID + depth] >= q) cont = false;
+            }
+            if (cont) {
+                Sample3 smp; uint32_t type;
+                const float* s2 = rec + ig.off2D + 2 * (ig.firstScatterSampleID + depth);
+                const float ss = rec[ig.off1D + ig.firstScatterTypeSampleID + depth];
+                Col c = lobes_sample(lobes, wo, dg, smp, type, s2[0], s2[1], ss, BR_ALL);
+                if (c == Col(0.f) || smp.pdf <= 0.f) cont = false;
+                else {
+                    const Col tr(m4.x, m4.y, m4.z);
+                    if (tr != Col(1.f)) c *= Col(powf(tr.x, hitT), powf(tr.y, hitT), powf(tr.z, hitT));   // :198-201
+                    if (type & BR_TRANSMISSION) {
+                        const MaterialRec& m = sc.materials[dg.material];
+                        if (m.isMediaInterface) {   // Material::nextMedium  materials/material.h:49-52
+                            const bool inside = (tr == m.tInside) && (m4.w == m.etaInside);
+                            m4 = inside ? make_float4(m.tOutside.x, m.tOutside.y, m.tOutside.z, m.etaOutside)
+                                        : make_float4(m.tInside.x, m.tInside.y, m.tInside.z, m.etaInside);
+                        }
+                    }
+                    const Col nthr = thr * c * rcpf(smp.pdf);
+                    uint32_t nflags = 0;
+                    if (type & BR_DIFFUSE) nflags |= FLAG_IGNORE_VISIBLE_LIGHTS;
+                    if ((flags & FLAG_UNBENT) && smp.v == f4v(d4)) nflags |= FLAG_UNBENT;
+                    wb.rayO[pid] = make_float4(dg.P.x, dg.P.y, dg.P.z, dg.error * ig.epsilon);
+                    wb.rayD[pid] = make_float4(smp.v.x, smp.v.y, smp.v.z, INFINITY);
+                    wb.thr[pid] = make_float4(nthr.x, nthr.y, nthr.z, __uint_as_float(nflags << 16));
+                    wb.medium[pid] = m4;
+                    if (reduce_max(nthr) < ig.minContribution) cont = false;     // loop-top test of the next bounce (:66)
+                }
+            }
+        }
+        const uint32_t slot = warp_alloc(&wb.counters[queueSel ^ 1], cont ? 1u : 0u);
+        if (cont) nextQueue[slot] = pid;
+    }
+    // rtcOccluded-equivalent ray count (pathtraceintegrator.cpp:161): valid shadow rays only
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) shadowRays += __shfl_xor_sync(0xffffffffu, shadowRays, o);
+    if ((threadIdx.x & 31) == 0 && shadowRays) atomicAdd(&wb.stats[1], (unsigned long long)shadowRays);
+}
+void launch_shade(const FrameConst& fc, const WavefrontBuffers& wb, int queueSel, uint32_t pixelBegin, int depth, LaunchCfg lc) {
+    k_shade<<<lc.blocks, 128, 0, lc.stream>>>(fc, wb, queueSel, pixelBegin, depth);
+}
+
+// adds the unoccluded light contributions of this bounce in light order, then resets the counters
+__global__ void __launch_bounds__(256) k_resolve(WavefrontBuffers wb, int queueSel) {
+    const uint32_t* __restrict__ queue = queueSel ? wb.queueB : wb.queueA;
+    const uint32_t n = wb.counters[queueSel];
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t pid = queue[i];
+        const uint2 span = wb.shadowSpan[pid];
+        if (!span.y) continue;
+        float4 L4 = wb.Lacc[pid]; Col L(L4.x, L4.y, L4.z);
+        for (uint32_t k = 0; k < span.y; k++) {
+            const uint32_t slot = span.x + k;
+            if (slot >= wb.shadowCapacity) break;
+            const float4 c = wb.shC[slot];
+            if (c.w == 0.f) L += Col(c.x, c.y, c.z);
+        }
+        wb.Lacc[pid] = make_float4(L.x, L.y, L.z, 0.f);
+    }
+}
+__global__ void k_reset_counters(WavefrontBuffers wb, int queueSel) { wb.counters[queueSel] = 0; wb.counters[2] = 0; }
+void launch_resolve(const FrameConst& fc, const WavefrontBuffers& wb, int queueSel, LaunchCfg lc) {
+    k_resolve<<<lc.blocks, 256, 0, lc.stream>>>(wb, queueSel);
+    k_reset_counters<<<1, 1, 0, lc.stream>>>(wb, queueSel);
+}
+
+// ---- film: per-pixel sample sum, accumulation buffer, tone mapping, packing -------------------
+// SwapChain::update -> AccuBuffer::update api/framebuffer.h:289-304; DefaultToneMapper::eval
+// tonemappers/defaulttonemapper.h:38-51; FrameBufferRGB8/RGBA8/RGBFloat32::set api/framebuffer.h:127-129,171-178,220-226
+__global__ void __launch_bounds__(256) k_film(FrameConst fc, WavefrontBuffers wb, FilmParams fp, uint32_t pixelBegin, uint32_t numPixels) {
+    const int spp = fc.integ.spp;
+    for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < numPixels; p += gridDim.x * blockDim.x) {
+        Col L(0.f);
+        for (int s = 0; s < spp; s++) { const float4 l = wb.Lacc[(size_t)p * spp + s]; L += Col(l.x, l.y, l.z); }
+        const uint32_t bp = pixelBegin + p;
+        const int bx = bp % fc.width, by = bp / fc.width;
+        const int y = buffer2raster(by, fc.serverID, fc.serverCount);
+        const float weight = (float)spp;
+        Col L0;
+        if (fp.accumulate) {
+            const float4 cur = fp.accum[bp];
+            const float4 next = make_float4(cur.x + L.x, cur.y + L.y, cur.z + L.z, cur.w + weight);
+            fp.accum[bp] = next;
+            L0 = Col(next.x, next.y, next.z) * rcpf(next.w);
+        } else {
+            fp.accum[bp] = make_float4(L.x, L.y, L.z, weight);
+            L0 = L * rcpf(weight);
+        }
+        Col c = L0;
+        if (fp.gamma != 1.0f) c = Col(powf(c.x, fp.rcpGamma), powf(c.y, fp.rcpGamma), powf(c.z, fp.rcpGamma));
+        if (fp.vignetting) {
+            const float ddx = (float(bx) - 0.5f * float(fc.width)) * rcpf(0.5f * float(fc.width));
+            const float ddy = (float(y) - 0.5f * float(fc.height)) * rcpf(0.5f * float(fc.width));
+            const float d = sqrtf(ddx * ddx + ddy * ddy);
+            c *= powf(cosf(d * 0.5f), 3.0f);
+        }
+        if (fp.format == 0) {
+            float* o = (float*)((char*)fp.fbDevice + (size_t)by * fp.fbStrideBytes) + 3 * bx;
+            o[0] = c.x; o[1] = c.y; o[2] = c.z;
+        } else {
+            const int bpp = fp.format == 1 ? 4 : 3;
+            unsigned char* o = (unsigned char*)fp.fbDevice + (size_t)by * fp.fbStrideBytes + bpp * bx;
+            o[0] = (unsigned char)rclamp(c.x * 255.0f, 0.0f, 255.0f);
+            o[1] = (unsigned char)rclamp(c.y * 255.0f, 0.0f, 255.0f);
+            o[2] = (unsigned char)rclamp(c.z * 255.0f, 0.0f, 255.0f);
+            if (bpp == 4) o[3] = 0;
+        }
+    }
+}
+void launch_film(const FrameConst& fc, const WavefrontBuffers& wb, const FilmParams& fp, uint32_t pixelBegin, uint32_t numPixels, LaunchCfg lc) {
+    k_film<<<lc.blocks, 256, 0, lc.stream>>>(fc, wb, fp, pixelBegin, numPixels);
+}
+
+}  // namespace yrt
