@@ -51,7 +51,9 @@ typedef int yrt_status;               /* 0 = ok */
 /* reference: Device::rtCreateDevice -> create(parms, numThreads, threadsPriority, rtcore_cfg)
  * (devices/device/device.cpp:24-48). `cfg` is the free-form "k=v,k=v" string the front end
  * passes as -rtcore (devices/renderer/renderer.cpp:922-937); keys understood:
- *   gpus=N (default: all visible), gpu=I (first ordinal), chunk=P (paths per wavefront chunk),
+ *   gpu=I (CUDA ordinal, default 0), chunk=P (paths per wavefront chunk, default 2^22), stats=1 (count node
+ *   visits / triangle tests), timers=0|1 (per-stage CUDA events, default 1), rebuild=1 (rebuild the BVH on every
+ *   scene commit like the reference does), serverID=I,serverCount=N (row-band interleave, see yrtSetInt1(NULL,..)),
  *   verbose=0|1.   numThreads / threadsPriority are accepted and ignored (no CPU workers). */
 YRT_API yrt_device* yrtCreateDevice(const char* parms, size_t numThreads, int threadsPriority, const char* cfg);
 YRT_API void        yrtDestroyDevice(yrt_device* dev);                 /* reference: virtual ~Device, device.h:54 */
@@ -125,19 +127,28 @@ YRT_API int        yrtPick(yrt_device*, yrt_handle camera, float x, float y, yrt
  * ("render  F fps, T ms, R mrps", devices/device_singleray/renderers/integratorrenderer.cpp:96-111).
  * ===================================================================================== */
 typedef struct yrtx_frame_stats {
-    double   render_ms;        /* CUDA-event time of the wavefront loop of the last yrtRenderFrame (max over GPUs) */
-    double   build_ms;         /* CUDA-event time of the last scene commit (BVH build) */
-    double   host_ms;          /* wall-clock of the whole last yrtRenderFrame call */
+    double   render_ms;        /* CUDA-event time of the wavefront loop of the last yrtRenderFrame */
+    double   build_ms;         /* CUDA-event time of the last BVH build (scene commit that had to rebuild) */
+    double   host_ms;          /* wall-clock of the whole last yrtRenderFrame call (incl. the D2H copy of the frame) */
     uint64_t rays_closest;     /* rtcIntersect-equivalent rays (pathtraceintegrator.cpp:74) */
     uint64_t rays_shadow;      /* rtcOccluded-equivalent rays (pathtraceintegrator.cpp:161) */
     uint64_t kernel_launches;  /* device_cuda kernels launched by the last yrtRenderFrame */
-    double   trace_ms;         /* CUDA-event time spent in the traversal kernels only */
+    double   trace_ms;         /* CUDA-event time spent in the two traversal kernels */
     uint64_t node_visits;      /* only when cfg has stats=1: BVH8 nodes fetched */
     uint64_t tri_tests;        /* only when cfg has stats=1: triangles tested */
     uint64_t num_triangles;    /* triangles in the committed scene */
     uint64_t num_nodes;        /* BVH8 nodes in the committed scene */
     uint32_t num_gpus;
     uint32_t reserved;
+    double   closest_ms;       /* CUDA-event time of the closest-hit traversal launches */
+    double   shadow_ms;        /* CUDA-event time of the any-hit traversal launches */
+    double   shade_ms;         /* CUDA-event time of the shading + resolve launches */
+    double   raygen_film_ms;   /* CUDA-event time of ray generation + film launches */
+    uint64_t closest_launches; /* number of closest-hit traversal launches */
+    uint64_t shadow_launches;  /* number of any-hit traversal launches */
+    uint64_t h2d_bytes;        /* host->device bytes moved by the last yrtRenderFrame (sample table, constants) */
+    uint64_t d2h_bytes;        /* device->host bytes moved by the last yrtRenderFrame (the frame) */
+    uint64_t bvh_builds;       /* BVH builds since the scene handle was created (F8: commits that did not change geometry reuse it) */
 } yrtx_frame_stats;
 YRT_API yrt_status yrtxGetFrameStats(yrt_device*, yrtx_frame_stats* out);
 
@@ -158,6 +169,13 @@ YRT_API yrt_status yrtxPrimaryRays(yrt_device*, yrt_handle renderer, yrt_handle 
  * (may be NULL to query sizes): {pixel.x, pixel.y, time, lens.x, lens.y, 1D[n1], 2D[2*n2]}. */
 YRT_API yrt_status yrtxSampleTable(yrt_device*, yrt_handle renderer, yrt_handle scene, int iteration,
                                    int* sets, int* spp, int* n1, int* n2, float* table);
+/* Device-resident copy of the current buffer of a framebuffer (what yrtRenderFrame wrote before the D2H copy):
+ * row stride as in the reference (api/framebuffer.h:106,146,195). Used by bench.py to gather row bands
+ * between ranks over NCCL without a host round trip. */
+YRT_API yrt_status yrtxFrameBufferDevice(yrt_device*, yrt_handle frameBuffer, void** devPtr, size_t* bytes, size_t* strideBytes);
+/* readbackEachFrame == 0: yrtRenderFrame leaves the frame on the GPU and yrtMapFrameBuffer copies it on demand
+ * (default 1: the frame is in the host buffer when yrtRenderFrame returns, as in the reference). */
+YRT_API yrt_status yrtxSetReadback(yrt_device*, int readbackEachFrame);
 
 #ifdef __cplusplus
 }

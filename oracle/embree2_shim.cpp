@@ -256,6 +256,7 @@ std::atomic<uint64_t> g_nodeVisits{0}, g_triTests{0}; bool g_countStats = false;
 template <bool ANY>
 static void traverse(Scene* s, RTCRay& ray) {
     if (!s->committed || s->nodes[0].left == 0xffffffffu) return;
+    if (!(ray.tnear <= ray.tfar)) return;                      // empty or NaN interval (pin P2): nothing can be accepted below
     const V3 O = {ray.org[0], ray.org[1], ray.org[2]}, D = {ray.dir[0], ray.dir[1], ray.dir[2]};
     const V3 rd = {1.0f / D.x, 1.0f / D.y, 1.0f / D.z};
     const float tnear = ray.tnear;

@@ -22,7 +22,9 @@ because the shipped behaviour is either undefined, non-deterministic or hardware
 dependent; DESIGN.md "Parity contract" lists them):
   P1 integrators/pathtraceintegrator.cpp:151   libc rand() shared by all threads ->
      counter hash of (pixel.x bits, pixel.y bits, depth, light index)  [SURVEY F6]
-  P2 same line: tMaxShadowRay == +inf makes the jitter NaN -> jitter = 0, tMax = inf [SURVEY F7]
+  P2 same line: tMaxShadowRay == +inf makes the jitter inf - inf = NaN under IEEE rules, so the shadow ray's tfar
+     is NaN. Pinned to exactly that (never to a fast-math reassociation): tfar = NaN, and a NaN interval is
+     empty in both the shim and the CUDA traversal, i.e. such shadow rays are never occluded [SURVEY F7]
   P3 common/math/{math.h,vector3f_sse.h,color_sse.h}: rcp/rsqrt built on the
      *approximate* SSE rcpps/rsqrtps (vendor specific bits) -> the exact 1/x and
      1/sqrt(x) the reference itself uses in its non-SSE branch (math.h:65,69) [SURVEY F5]
@@ -118,9 +120,6 @@ def main():
     patch("devices/device_singleray/integrators/pathtraceintegrator.cpp",
           "const float shadowRayJitterLength = 2.f * tMaxShadowRay * tMaxShadowJitter * random<float>() - tMaxShadowRay * tMaxShadowJitter;",
           "const float shadowRayJitterLength = yrt_oracle_shadow_jitter(tMaxShadowRay, tMaxShadowJitter, state.pixel.x, state.pixel.y, (unsigned)lightPath.depth, (unsigned)i); /* PIN P1+P2 */")
-    patch("devices/device_singleray/integrators/pathtraceintegrator.cpp",
-          "ls.tMax += tMaxShadowRay * 100.f * smoothstep(0.f, 1.f, abs(dotProduct));",
-          "if (!std::isinf(tMaxShadowRay)) ls.tMax += tMaxShadowRay * 100.f * smoothstep(0.f, 1.f, abs(dotProduct)); /* PIN P2: inf*0 = NaN */")
     patch("devices/device_singleray/integrators/pathtraceintegrator.cpp",
           '#include "integrators/pathtraceintegrator.h"',
           '#include "integrators/pathtraceintegrator.h"\n#include "yrt_oracle_pins.h"')

@@ -27,10 +27,10 @@ static inline float yrt_hash_unit(uint32_t h) {            // [0,1)
 }
 
 // ---- P1 + P2: jitter length of the dome-light shadow ray ----
-// reference: 2*tMax*j*rand - tMax*j   (NaN when tMax == +inf)
+// reference: 2*tMax*j*rand - tMax*j   (inf - inf = NaN when tMax == +inf, SURVEY F7: pinned to NaN)
 static inline float yrt_oracle_shadow_jitter(float tMax, float jitter, float px, float py,
                                              unsigned depth, unsigned light) {
-    if (std::isinf(tMax)) return 0.0f;                      // P2
+    if (std::isinf(tMax)) return std::numeric_limits<float>::quiet_NaN();   // P2
     uint32_t bx, by;
     std::memcpy(&bx, &px, 4); std::memcpy(&by, &py, 4);
     const float r = yrt_hash_unit(yrt_hash4(bx, by, depth, light));   // P1

@@ -128,12 +128,13 @@ struct CameraData {
     Aff3 local2world;
 };
 
+#define YRT_NO_ATTR 0xffffffffu
 enum MeshType { MESH_FULL = 0, MESH_NORMALS = 1, MESH_TRIANGLE = 2 };
 struct GeomRec {                 // one per geomID (= one committed shape primitive)
     int type, material, areaLight, cull;
     int illumMask, shadowMask;
-    uint32_t vtxBase, idxBase;   // into positions/normals/uvs (same base) and the int4 index array
-    int hasNormals, hasUVs;
+    uint32_t vtxBase, idxBase;   // into positions and the int4 index array
+    uint32_t nrmBase, uvBase;    // into normals / uvs, YRT_NO_ATTR when the mesh has none
     V3 triNg;                    // MESH_TRIANGLE: normalize(cross(v2-v0, v1-v0))  (shapes/triangle.h:43)
     int pad;
 };

@@ -70,6 +70,8 @@ void launch_shade(const FrameConst& fc, const WavefrontBuffers& wb, int queueSel
 void launch_trace_shadow(const FrameConst& fc, const WavefrontBuffers& wb, LaunchCfg lc);
 void launch_resolve(const FrameConst& fc, const WavefrontBuffers& wb, int queueSel, LaunchCfg lc);
 void launch_film(const FrameConst& fc, const WavefrontBuffers& wb, const FilmParams& fp, uint32_t pixelBegin, uint32_t numPixels, LaunchCfg lc);
+// renderers/debugrenderer.cpp:66-148 (maxDepth 1): primary-hit ID image written straight into the framebuffer
+void launch_debug(const FrameConst& fc, const WavefrontBuffers& wb, const FilmParams& fp, uint32_t numPixels, LaunchCfg lc);
 void launch_export_primary(const FrameConst& fc, const WavefrontBuffers& wb, uint32_t pixelBegin, uint32_t numPixels, float* out, LaunchCfg lc);
 // yrtxTraceRays: rays/hits on the device, 8 floats each
 void launch_trace_user(const SceneData& sc, const float* rays, float* hits, size_t n, int closest, int countStats,

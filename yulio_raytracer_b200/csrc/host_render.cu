@@ -1,0 +1,673 @@
+// host_render.cu — host side of the render path of device_cuda: scene flattening + upload, framebuffers,
+// the per-frame wavefront schedule, and the measurement/parity extensions.
+//
+// Restates the host-side control flow of
+//   BackendSceneFlat::Handle::setPrimitive/create     devices/device_singleray/api/scene_flat.h:63-112
+//   BackendSceneFlat ctor (lights / env lights)        api/scene_flat.h:120-136, api/scene.h:76-86
+//   SwapChain / FrameBuffer                            api/swapchain.h:29-125, api/framebuffer.h:97-230
+//   IntegratorRenderer::renderFrame / RenderJob        renderers/integratorrenderer.cpp:63-116
+//   PathTraceIntegrator::requestSamples                integrators/pathtraceintegrator.cpp:35-47
+//   SamplerFactory::init (light samples)               samplers/sampler.cpp:141-150, lights/hdrilight.cpp:92-102
+// around the CUDA stages in kernels.cu / bvh_build.cu. Nothing here computes radiance on the CPU.
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <map>
+
+#include "device_impl.hpp"
+#include "host_math.hpp"
+
+namespace yrt {
+
+// ------------------------------------------------------------------------------------------------
+// image files: PPM / PFM as the reference reads them (common/image/ppm.cpp:40-110, pfm.cpp:40-95).
+// JPEG/PNG decoding is done by the front end and arrives through rtNewImage.
+// ------------------------------------------------------------------------------------------------
+static void skip_header_space(FILE* f) {
+    for (;;) {
+        const int c = fgetc(f);
+        if (c == '#') { char line[1024]; if (!fgets(line, sizeof(line), f)) return; continue; }
+        if (c != EOF && isspace(c)) continue;
+        if (c != EOF) ungetc(c, f);
+        return;
+    }
+}
+static unsigned char quant8(float v) {              // Color4::set(Col4c&): clamp(c)*255 truncated (color_sse.h:68)
+    const float c = rclamp(v, 0.f, 1.f) * 255.0f;
+    return (unsigned char)(int)c;
+}
+std::shared_ptr<ImageObj> load_image_file(const char* file) {
+    if (!file) return nullptr;
+    const std::string name(file);
+    const size_t dot = name.rfind('.');
+    std::string ext = dot == std::string::npos ? "" : name.substr(dot + 1);
+    for (auto& c : ext) c = (char)tolower((unsigned char)c);
+    if (ext != "ppm" && ext != "pfm") { printf("cannot read file %s: image format %s not supported\n", file, ext.c_str()); return nullptr; }
+    FILE* f = fopen(file, "rb");
+    if (!f) { printf("cannot read file %s: cannot open\n", file); return nullptr; }
+    auto img = std::make_shared<ImageObj>();
+    char magic[8] = {0};
+    bool ok = fscanf(f, "%7s", magic) == 1;
+    if (ok) skip_header_space(f);
+    if (ok && ext == "ppm") {
+        int w = 0, h = 0, maxc = 0;
+        ok = fscanf(f, "%i %i %i", &w, &h, &maxc) == 3 && w > 0 && h > 0 && maxc > 0;
+        if (ok) {
+            fgetc(f);
+            const float rcpMax = 1.0f / float(maxc);
+            img->width = w; img->height = h; img->format = TEX_RGBA8; img->storage.assign((size_t)w * h * 4, 0);
+            unsigned char* o = img->storage.data();
+            const bool text = !strcmp(magic, "P3"), bin = !strcmp(magic, "P6");
+            ok = text || bin;
+            for (size_t i = 0; ok && i < (size_t)w * h; i++) {
+                float rgb[3];
+                if (text) { int r, g, b; ok = fscanf(f, "%i %i %i", &r, &g, &b) == 3; rgb[0] = float(r); rgb[1] = float(g); rgb[2] = float(b); }
+                else if (maxc <= 255) { unsigned char c[3]; ok = fread(c, 3, 1, f) == 1; rgb[0] = c[0]; rgb[1] = c[1]; rgb[2] = c[2]; }
+                else { unsigned short c[3]; ok = fread(c, 6, 1, f) == 1; rgb[0] = c[0]; rgb[1] = c[1]; rgb[2] = c[2]; }
+                for (int k = 0; k < 3; k++) o[4 * i + k] = quant8(rgb[k] * rcpMax);
+                o[4 * i + 3] = 255;
+            }
+        }
+    } else if (ok) {
+        int w = 0, h = 0; float maxc = 0.f;
+        ok = fscanf(f, "%i %i %f", &w, &h, &maxc) == 3 && w > 0 && h > 0 && !(maxc > 0.0f) && !strcmp(magic, "PF");
+        if (ok) {
+            fgetc(f);
+            const float rcpMax = -1.0f / maxc;
+            img->width = w; img->height = h; img->format = TEX_RGB_F32; img->storage.assign((size_t)w * h * 12, 0);
+            float* o = (float*)img->storage.data();
+            ok = fread(o, 12, (size_t)w * h, f) == (size_t)w * h;
+            for (size_t i = 0; ok && i < (size_t)w * h * 3; i++) o[i] = o[i] * rcpMax;
+        }
+    }
+    fclose(f);
+    if (!ok) { printf("cannot read file %s: error reading\n", file); return nullptr; }
+    img->pixels = img->storage.data();
+    return img;
+}
+
+static void image_upload(ImageObj& img, cudaStream_t s) {
+    if (img.devPixels) return;
+    YRT_CK(cudaMalloc(&img.devPixels, img.bytes() ? img.bytes() : 1));
+    if (img.bytes()) YRT_CK(cudaMemcpyAsync(img.devPixels, img.pixels, img.bytes(), cudaMemcpyHostToDevice, s));
+}
+
+// ------------------------------------------------------------------------------------------------
+// scene
+// ------------------------------------------------------------------------------------------------
+SceneHandle::~SceneHandle() { releaseDevice(); }
+void SceneHandle::releaseDevice() {
+    if (nodes) cudaFree(nodes); if (tris) cudaFree(tris);
+    nodes = nullptr; tris = nullptr;
+}
+
+// Shape::transform  shapes/trianglemesh_full.cpp:68-90, trianglemesh_normals.cpp:42-56, triangle.h:47-49
+static std::shared_ptr<ShapeObj> transform_shape(const std::shared_ptr<ShapeObj>& s, const Aff3& xfm) {
+    if (s->type == MESH_TRIANGLE) {
+        auto t = std::make_shared<ShapeObj>(); t->type = MESH_TRIANGLE;
+        t->v0 = xfmPoint(xfm, s->v0); t->v1 = xfmPoint(xfm, s->v1); t->v2 = xfmPoint(xfm, s->v2);
+        t->triNg = normalize(cross(t->v2 - t->v0, t->v1 - t->v0)); t->triNgValid = true;
+        return t;
+    }
+    if (aff3_is_identity(xfm)) return s;
+    auto t = std::make_shared<ShapeObj>();
+    t->type = s->type; t->cullBackFaces = s->cullBackFaces; t->texcoord = s->texcoord; t->triangles = s->triangles;
+    t->position.resize(s->position.size());
+    for (size_t i = 0; i < s->position.size(); i++) t->position[i] = xfmPoint(xfm, s->position[i]);
+    t->normal.resize(s->normal.size());
+    if (!s->normal.empty()) {
+        const Lin3 it = lin3_inverse_transposed(xfm.l);
+        for (size_t i = 0; i < s->normal.size(); i++) t->normal[i] = xfmVector(it, s->normal[i]);
+    }
+    return t;
+}
+
+// Light::transform  lights/*.h (ambient :53, directional :42, distant :51, hdri :44, point :44, spot :48, triangle :58)
+static std::shared_ptr<LightObj> transform_light(const std::shared_ptr<LightObj>& l, const Aff3& xfm) {
+    auto t = std::make_shared<LightObj>(*l);
+    switch (l->type) {
+    case LIGHT_POINT: t->v0 = xfmPoint(xfm, l->v0); break;
+    case LIGHT_SPOT: t->v0 = xfmPoint(xfm, l->v0); t->v1 = xfmVector(xfm, l->v1); break;
+    case LIGHT_DIRECTIONAL: case LIGHT_DISTANT: t->v0 = xfmVector(xfm, l->v0); break;
+    case LIGHT_HDRI: t->local2world = mul(xfm, l->local2world); break;
+    case LIGHT_TRIANGLE: t->v0 = xfmPoint(xfm, l->v0); t->v1 = xfmPoint(xfm, l->v1); t->v2 = xfmPoint(xfm, l->v2); break;
+    default: break;
+    }
+    return t;
+}
+
+void scene_set_primitive(yrt_device* dev, SceneHandle* sc, size_t slot, PrimHandle* prim, const Aff3* overrideXfm) {
+    (void)dev;
+    if (slot >= sc->prims.size()) sc->prims.resize(slot + 1);
+    sc->dirty = true;
+    if (!prim) { sc->prims[slot] = nullptr; return; }
+    const Aff3 xfm = overrideXfm ? *overrideXfm : prim->transform;
+    auto sp = std::make_shared<ScenePrim>();
+    std::shared_ptr<ShapeObj> shape = prim->shape ? prim->shape->inst : nullptr;
+    std::shared_ptr<LightObj> light = prim->light ? prim->light->inst : nullptr;
+    if (light) {                                              // light->shape(): only the triangle light has one
+        shape = nullptr;
+        if (light->type == LIGHT_TRIANGLE) {
+            shape = std::make_shared<ShapeObj>(); shape->type = MESH_TRIANGLE;
+            shape->v0 = light->v0; shape->v1 = light->v1; shape->v2 = light->v2;
+        }
+    }
+    if (shape) shape = transform_shape(shape, xfm);
+    if (light) light = transform_light(light, xfm);
+    sp->shape = shape; sp->light = light;
+    sp->material = prim->material ? prim->material->inst : nullptr;
+    sp->illumMask = prim->illumMask; sp->shadowMask = prim->shadowMask;
+    sc->prims[slot] = sp;
+}
+
+void scene_commit(yrt_device* dev, SceneHandle* sc) {
+    sc->commitCount++;
+    // The reference rebuilds the Embree scene on every commit (scene_flat.h:87-112); the result only
+    // depends on the slots, so an unchanged scene keeps its BVH unless cfg rebuild=1 asks for the reference's cost.
+    if (sc->committed && !sc->dirty && !dev->alwaysRebuild) return;
+    cudaStream_t st = dev->stream;
+
+    std::vector<GeomRec> geoms; std::vector<float4> positions, normals; std::vector<float2> uvs; std::vector<int4> indices;
+    std::vector<uint2> refs; std::vector<MaterialRec> materials; std::vector<LightRec> lights;
+    std::map<const MaterialObj*, int> matIndex; std::map<const TextureObj*, int> texIndex;
+    sc->hostTextures.clear(); sc->imagesInUse.clear(); sc->hdri.clear(); sc->geomOfSlot.assign(sc->prims.size(), -1);
+
+    auto texture_index = [&](const std::shared_ptr<ImageObj>& img, bool bilinear, bool invert) {
+        image_upload(*img, st); sc->imagesInUse.push_back(img);
+        TextureRec t; t.data = img->devPixels; t.width = img->width; t.height = img->height; t.format = img->format;
+        t.bilinear = bilinear ? 1 : 0; t.invert = invert ? 1 : 0; t.pad = 0;
+        sc->hostTextures.push_back(t);
+        return (int)sc->hostTextures.size() - 1;
+    };
+    auto material_index = [&](const std::shared_ptr<MaterialObj>& m) {
+        if (!m) return -1;
+        auto it = matIndex.find(m.get());
+        if (it != matIndex.end()) return it->second;
+        MaterialRec r = m->rec;
+        for (int k = 0; k < 5; k++) {
+            r.tex[k] = -1;
+            const auto& t = m->textures[k];
+            if (!t || !t->image) continue;
+            auto ti = texIndex.find(t.get());
+            if (ti == texIndex.end()) ti = texIndex.emplace(t.get(), texture_index(t->image, t->bilinear, t->invert)).first;
+            r.tex[k] = ti->second;
+        }
+        materials.push_back(r);
+        return matIndex[m.get()] = (int)materials.size() - 1;
+    };
+
+    SceneData d{};
+    d.numEnvLights = 0; d.numPrecomputed = 0;
+    for (size_t slot = 0; slot < sc->prims.size(); slot++) {
+        const auto& p = sc->prims[slot];
+        if (!p) continue;
+        int lightIdx = -1;
+        if (p->light) {                                        // BackendScene::add(light)  api/scene.h:76-79
+            const LightObj& l = *p->light;
+            LightRec r; memset(&r, 0, sizeof(r));
+            r.type = l.type; r.illumMask = p->illumMask; r.shadowMask = p->shadowMask; r.precomputedId = -1;
+            r.L = l.L; r.v0 = l.v0; r.v1 = l.v1; r.v2 = l.v2; r.a = l.a; r.b = l.b; r.image = -1;
+            r.Ng = cross(l.v0 - l.v1, l.v2 - l.v0);           // trianglelight.h:39
+            r.world2local.l = lin3_identity(); r.world2local.p = V3(0.f);
+            r.isEnv = (l.type == LIGHT_AMBIENT || l.type == LIGHT_DISTANT || l.type == LIGHT_HDRI) ? 1 : 0;
+            if (l.type == LIGHT_HDRI) {
+                r.world2local = aff3_inverse(l.local2world);
+                r.image = texture_index(l.image, false, false);
+                r.precomputedId = d.numPrecomputed++;
+                HdriHost h; h.image = l.image; h.L = l.L; h.local2world = l.local2world;
+                const size_t w = (size_t)l.image->width, hgt = (size_t)l.image->height;   // hdrilight.cpp:48-55
+                std::vector<std::vector<float>> imp(hgt, std::vector<float>(w));
+                for (size_t y = 0; y < hgt; y++)
+                    for (size_t x = 0; x < w; x++)
+                        imp[y][x] = sinf(YRT_PI * (y + 0.5f) * rcpf(float(hgt))) * reduce_add(host_texel(*l.image, (long long)x, (long long)y));
+                h.dist.init(imp, w, hgt);
+                sc->hdri.push_back(std::move(h));
+            }
+            lightIdx = (int)lights.size();
+            if (r.isEnv) {
+                if (d.numEnvLights >= 8) throw std::runtime_error("device_cuda: more than 8 environment lights");
+                d.envLightIdx[d.numEnvLights++] = lightIdx;
+            }
+            lights.push_back(r);
+        }
+        if (!p->shape) continue;
+        const ShapeObj& s = *p->shape;
+        GeomRec g; memset(&g, 0, sizeof(g));
+        const int geomID = (int)geoms.size();
+        sc->geomOfSlot[slot] = geomID;
+        g.type = s.type; g.material = material_index(p->material); g.areaLight = lightIdx;
+        g.cull = s.cullBackFaces ? 1 : 0; g.illumMask = p->illumMask; g.shadowMask = p->shadowMask;
+        g.vtxBase = (uint32_t)positions.size(); g.idxBase = (uint32_t)indices.size();
+        g.nrmBase = YRT_NO_ATTR; g.uvBase = YRT_NO_ATTR; g.triNg = V3(0.f);
+        if (s.type == MESH_TRIANGLE) {
+            g.triNg = s.triNg;
+            const V3 v[3] = {s.v0, s.v1, s.v2};
+            for (int k = 0; k < 3; k++) positions.push_back(make_float4(v[k].x, v[k].y, v[k].z, 0.f));
+            indices.push_back(make_int4(0, 1, 2, 0));
+            bool fin = true; for (int k = 0; k < 3; k++) fin &= std::isfinite(v[k].x) && std::isfinite(v[k].y) && std::isfinite(v[k].z);
+            if (fin) refs.push_back(make_uint2((uint32_t)geomID, 0u));
+        } else {
+            const size_t nv = s.position.size();
+            for (const V3& q : s.position) positions.push_back(make_float4(q.x, q.y, q.z, 0.f));
+            if (!s.normal.empty()) { g.nrmBase = (uint32_t)normals.size(); for (const V3& q : s.normal) normals.push_back(make_float4(q.x, q.y, q.z, 0.f)); }
+            if (!s.texcoord.empty()) { g.uvBase = (uint32_t)uvs.size(); for (const float2& q : s.texcoord) uvs.push_back(q); }
+            for (size_t t = 0; t < s.triangles.size(); t++) {
+                const int4 tri = s.triangles[t];
+                indices.push_back(tri);
+                bool okTri = tri.x >= 0 && tri.y >= 0 && tri.z >= 0 && (size_t)tri.x < nv && (size_t)tri.y < nv && (size_t)tri.z < nv;
+                if (okTri) for (int k : {tri.x, tri.y, tri.z}) { const V3& q = s.position[k]; okTri &= std::isfinite(q.x) && std::isfinite(q.y) && std::isfinite(q.z); }
+                if (okTri) refs.push_back(make_uint2((uint32_t)geomID, (uint32_t)t));   // invalid triangles are never hit
+            }
+        }
+        geoms.push_back(g);
+    }
+
+    sc->geoms.upload(geoms, st); sc->positions.upload(positions, st); sc->normals.upload(normals, st); sc->uvs.upload(uvs, st);
+    sc->indices.upload(indices, st); sc->materials.upload(materials, st); sc->lights.upload(lights, st);
+    sc->textures.upload(sc->hostTextures, st);
+    DevBuf<uint2> dRefs; dRefs.upload(refs, st);
+
+    sc->releaseDevice();
+    BvhBuildInput in{dRefs.p, (uint32_t)refs.size(), sc->geoms.p, sc->positions.p, sc->indices.p};
+    BvhResult out{};
+    build_bvh(in, out, st);
+    YRT_CK(cudaStreamSynchronize(st));
+    sc->nodes = out.nodes; sc->tris = out.tris; sc->buildMs = out.buildMs; sc->buildLaunches = out.launches; sc->rebuildCount++;
+
+    d.nodes = sc->nodes; d.tris = sc->tris; d.numNodes = out.numNodes; d.numTris = out.numTris;
+    d.geoms = sc->geoms.p; d.positions = sc->positions.p; d.normals = sc->normals.p; d.uvs = sc->uvs.p; d.indices = sc->indices.p;
+    d.materials = sc->materials.p; d.textures = sc->textures.p; d.lights = sc->lights.p;
+    d.numGeoms = (int)geoms.size(); d.numLights = (int)lights.size();
+    sc->data = d; sc->committed = true; sc->dirty = false;
+    dev->stats.build_ms = out.buildMs; dev->stats.num_triangles = out.numTris; dev->stats.num_nodes = out.numNodes;
+    dev->stats.bvh_builds = sc->rebuildCount;
+    if (dev->verbose) printf("device_cuda: BVH8 build %u triangles -> %u nodes, %.3f ms\n", out.numTris, out.numNodes, out.buildMs);
+}
+
+// ------------------------------------------------------------------------------------------------
+// framebuffers
+// ------------------------------------------------------------------------------------------------
+FrameBufferHandle::~FrameBufferHandle() {
+    for (size_t i = 0; i < host.size(); i++) if (owned[i] && host[i]) cudaFreeHost(host[i]);
+    if (devPacked) cudaFree(devPacked); if (accum) cudaFree(accum);
+}
+
+FrameBufferHandle* framebuffer_create(yrt_device* dev, const char* type, size_t w, size_t h, size_t buffers, void** ptrs) {
+    (void)dev;
+    auto fb = std::unique_ptr<FrameBufferHandle>(new FrameBufferHandle());
+    const std::string t(type ? type : "");
+    if (!strcasecmp(t.c_str(), "RGB_FLOAT32")) { fb->format = 0; fb->strideBytes = w * 12; }          // framebuffer.h:106
+    else if (!strcasecmp(t.c_str(), "RGBA8")) { fb->format = 1; fb->strideBytes = w * 4; }             // framebuffer.h:146
+    else if (!strcasecmp(t.c_str(), "RGB8")) { fb->format = 2; fb->strideBytes = (3 * w + 3) / 4 * 4; } // framebuffer.h:195
+    else throw std::runtime_error("unknown framebuffer type: " + t);
+    fb->type = t; fb->width = w; fb->height = h; fb->depth = buffers ? buffers : 1;
+    for (size_t i = 0; i < fb->depth; i++) {
+        void* p = ptrs ? ptrs[i] : nullptr; bool own = false;
+        if (!p) { YRT_CK(cudaHostAlloc(&p, fb->bytes() ? fb->bytes() : 1, cudaHostAllocDefault)); own = true; }
+        memset(p, 0, fb->bytes());
+        fb->host.push_back(p); fb->owned.push_back(own);
+    }
+    YRT_CK(cudaMalloc(&fb->devPacked, fb->bytes() ? fb->bytes() : 1));
+    YRT_CK(cudaMemset(fb->devPacked, 0, fb->bytes()));
+    YRT_CK(cudaMalloc((void**)&fb->accum, (w * h ? w * h : 1) * sizeof(float4)));
+    YRT_CK(cudaMemset(fb->accum, 0, w * h * sizeof(float4)));
+    return fb.release();
+}
+
+void* framebuffer_map(yrt_device* dev, FrameBufferHandle* fb, int bufID) {
+    if (bufID < 0) bufID = (int)fb->cur;
+    if ((size_t)bufID >= fb->depth) throw std::runtime_error("invalid framebuffer index");
+    if (!dev->readback && fb->pendingBuf == bufID) {
+        YRT_CK(cudaMemcpyAsync(fb->host[bufID], fb->devPacked, fb->bytes(), cudaMemcpyDeviceToHost, dev->stream));
+        YRT_CK(cudaStreamSynchronize(dev->stream));
+        fb->pendingBuf = -1;
+    }
+    return fb->host[bufID];
+}
+
+// ------------------------------------------------------------------------------------------------
+// wavefront storage / timers
+// ------------------------------------------------------------------------------------------------
+template <typename T> static void dev_realloc(T*& p, size_t n) { if (p) cudaFree(p); p = nullptr; YRT_CK(cudaMalloc((void**)&p, (n ? n : 1) * sizeof(T))); }
+
+void WavefrontStorage::ensure(uint32_t capacity, uint32_t shadowCapacity, size_t pixels) {
+    if (capacity > wb.capacity) {
+        dev_realloc(wb.rayO, capacity); dev_realloc(wb.rayD, capacity); dev_realloc(wb.hitA, capacity); dev_realloc(wb.hitB, capacity);
+        dev_realloc(wb.thr, capacity); dev_realloc(wb.Lacc, capacity); dev_realloc(wb.medium, capacity);
+        dev_realloc(wb.shadowSpan, capacity); dev_realloc(wb.queueA, capacity); dev_realloc(wb.queueB, capacity);
+        wb.capacity = capacity;
+    }
+    if (shadowCapacity > wb.shadowCapacity) {
+        dev_realloc(wb.shO, shadowCapacity); dev_realloc(wb.shD, shadowCapacity); dev_realloc(wb.shC, shadowCapacity);
+        wb.shadowCapacity = shadowCapacity;
+    }
+    if (!wb.counters) { dev_realloc(wb.counters, 8); YRT_CK(cudaMemset(wb.counters, 0, 8 * sizeof(uint32_t))); }
+    if (!wb.stats) { dev_realloc(wb.stats, 8); YRT_CK(cudaMemset(wb.stats, 0, 8 * sizeof(unsigned long long))); }
+    if (pixels > pixelSetCapacity) { dev_realloc(wb.pixelSet, pixels); pixelSetCapacity = pixels; }
+}
+void WavefrontStorage::release() {
+    void* ps[] = {wb.rayO, wb.rayD, wb.hitA, wb.hitB, wb.thr, wb.Lacc, wb.medium, wb.shadowSpan, wb.queueA, wb.queueB,
+                  wb.shO, wb.shD, wb.shC, wb.counters, wb.stats, wb.pixelSet};
+    for (void* p : ps) if (p) cudaFree(p);
+    wb = WavefrontBuffers{}; pixelSetCapacity = 0;
+}
+
+cudaEvent_t FrameTimers::get() {
+    if (used == pool.size()) { cudaEvent_t e; YRT_CK(cudaEventCreate(&e)); pool.push_back(e); }
+    return pool[used++];
+}
+void FrameTimers::begin(int kind, cudaStream_t s) { Span sp; sp.kind = kind; sp.a = get(); sp.b = nullptr; YRT_CK(cudaEventRecord(sp.a, s)); spans.push_back(sp); }
+void FrameTimers::end(cudaStream_t s) { Span& sp = spans.back(); sp.b = get(); YRT_CK(cudaEventRecord(sp.b, s)); }
+void FrameTimers::release() { for (auto e : pool) cudaEventDestroy(e); pool.clear(); used = 0; spans.clear(); }
+
+enum { TK_RAYGEN_FILM = 0, TK_CLOSEST = 1, TK_SHADE = 2, TK_SHADOW = 3 };
+
+// ------------------------------------------------------------------------------------------------
+// per-frame setup shared by render_frame / primary_rays / sample_table
+// ------------------------------------------------------------------------------------------------
+struct FrameSetup {
+    FrameConst fc{}; int sets = 64; size_t bufferRows = 0; size_t tableBytes = 0; bool tableUploaded = false;
+};
+
+static const PixelFilter* device_filter(yrt_device* dev, int kind) {
+    if (kind == FILTER_NONE) return nullptr;
+    if (!dev->filterReady[kind]) { dev->filters[kind].init((FilterKind)kind); dev->filterReady[kind] = true; }
+    return &dev->filters[kind];
+}
+
+// SamplerFactory::init + the precomputed light samples; record = {pixel, time, lens, 1D[n1], 2D[n2], light[numPre] x 8}
+static std::vector<float> build_table(yrt_device* dev, RendererObj& R, const SceneHandle* sc, int iteration, int& spp, int& n1, int& n2, int& recFloats) {
+    n1 = R.maxDepth; n2 = 1 + R.maxDepth;                     // requestSamples: pathtraceintegrator.cpp:39-46
+    const SampleTable t = buildSampleTable(R.spp, R.sets, n1, n2, iteration, device_filter(dev, R.filter));
+    spp = t.spp;
+    const int numPre = sc ? (int)sc->hdri.size() : 0;
+    const int base = t.recFloats();
+    recFloats = base + 8 * numPre;
+    std::vector<float> out((size_t)R.sets * spp * recFloats, 0.f);
+    for (int set = 0; set < R.sets; set++)
+        for (int s = 0; s < spp; s++) {
+            float* o = &out[((size_t)set * spp + s) * recFloats];
+            memcpy(o, t.at(set, s), base * sizeof(float));
+            const float sx = o[5 + n1 + 0], sy = o[5 + n1 + 1];   // samples2D[lightSampleID = 0]
+            for (int k = 0; k < numPre; k++) {                    // HDRILight::sample  lights/hdrilight.cpp:92-102
+                const HdriHost& h = sc->hdri[k];
+                float px, py, pdf; h.dist.sample(sx, sy, px, py, pdf);
+                const float W = float(h.image->width), H = float(h.image->height);
+                const float theta = YRT_PI * py * rcpf(H);
+                const float phi = YRT_TWO_PI * (1.0f - px * rcpf(W));
+                const V3 wl(-sinf(theta) * cosf(phi), cosf(theta), -sinf(theta) * sinf(phi));
+                const V3 wi = xfmVector(h.local2world.l, wl);
+                const float wpdf = pdf * rcpf(YRT_TWO_PI * YRT_PI * sinf(theta));
+                long long ix = (long long)px, iy = (long long)py;
+                ix = ix < 0 ? 0 : (ix > h.image->width - 1 ? h.image->width - 1 : ix);
+                iy = iy < 0 ? 0 : (iy > h.image->height - 1 ? h.image->height - 1 : iy);
+                const Col L = h.L * host_texel(*h.image, ix, iy);
+                float* q = o + base + 8 * k;
+                q[0] = wi.x; q[1] = wi.y; q[2] = wi.z; q[3] = wpdf; q[4] = L.x; q[5] = L.y; q[6] = L.z; q[7] = 0.f;
+            }
+        }
+    return out;
+}
+
+static size_t active_rows(int height, int serverID, int serverCount) {
+    size_t n = 0;
+    for (int y = 0; y < height; y++) if ((((y >> 2) - serverID) % serverCount) == 0) n++;
+    return n;
+}
+
+static FrameSetup setup_frame(yrt_device* dev, RendererObj& R, const CameraData& cam, SceneHandle* sc, FrameBufferHandle* fb, int iteration) {
+    FrameSetup fs;
+    FrameConst& fc = fs.fc;
+    if (sc) fc.scene = sc->data;
+    fc.camera = cam;
+    fc.width = (int)fb->width; fc.height = (int)fb->height;
+    fc.serverID = dev->serverID; fc.serverCount = dev->serverCount < 1 ? 1 : dev->serverCount;
+    fc.rcpWidth = rcpf(float(fb->width)); fc.rcpHeight = rcpf(float(fb->height));
+    fc.debugRenderer = R.debug ? 1 : 0; fc.countStats = dev->countStats;
+    fs.bufferRows = active_rows(fc.height, fc.serverID, fc.serverCount);
+    IntegratorData& ig = fc.integ;
+    ig.maxDepth = R.maxDepth; ig.rrDepth = R.rrDepth; ig.minContribution = R.minContribution; ig.epsilon = R.epsilon;
+    ig.tMaxShadowRay = R.tMaxShadowRay; ig.tMaxShadowJitter = R.tMaxShadowJitter; ig.up = R.up;
+    ig.backplateTex = -1; ig.lightSampleID = 0; ig.firstScatterSampleID = 1; ig.firstScatterTypeSampleID = 0;
+    ig.sets = R.sets; fs.sets = R.sets;
+    if (R.debug) { ig.spp = R.spp; ig.recFloats = 0; return fs; }
+
+    // sample table (cached while renderer parameters, iteration and the scene's precomputed lights are unchanged)
+    const uint64_t sceneKey = sc ? sc->rebuildCount * 1315423911ull + (uint64_t)(uintptr_t)sc : 0;
+    TableKey key{R.spp, R.sets, R.maxDepth, R.filter, iteration, sc ? (int)sc->hdri.size() : 0, sceneKey};
+    if (!(key == dev->tableKey) || !dev->sampleTable.p) {
+        int spp, n1, n2, rec;
+        const std::vector<float> tab = build_table(dev, R, sc, iteration, spp, n1, n2, rec);
+        dev->sampleTable.upload(tab, dev->stream);
+        YRT_CK(cudaStreamSynchronize(dev->stream));          // `tab` is pageable and dies here
+        dev->tableKey = key; dev->tableSpp = spp; dev->tableN1 = n1; dev->tableN2 = n2; dev->tableRec = rec;
+        fs.tableBytes = tab.size() * sizeof(float); fs.tableUploaded = true;
+    }
+    R.spp = dev->tableSpp;                                    // SamplerFactory::init rounds samplesPerPixel up for good (sampler.cpp:91)
+    ig.spp = dev->tableSpp; ig.recFloats = dev->tableRec; ig.off1D = 5; ig.off2D = 5 + dev->tableN1;
+    ig.offLight = 5 + dev->tableN1 + 2 * dev->tableN2;
+    fc.sampleTable = dev->sampleTable.p;
+    return fs;
+}
+
+// ------------------------------------------------------------------------------------------------
+// rtRenderFrame
+// ------------------------------------------------------------------------------------------------
+typedef void (*StatusFn)(const void*);
+struct StatusRec { int state; float progress; };               // RendererStatus  devices/device/device.h:341-344
+
+void render_frame(yrt_device* dev, RendererHandle* rh, CameraHandle* ch, SceneHandle* sc, ToneMapperHandle* th, FrameBufferHandle* fb, int accumulate) {
+    const auto tHost0 = std::chrono::steady_clock::now();
+    if (!rh->inst) throw std::runtime_error("invalid renderer value");
+    if (!ch->inst) throw std::runtime_error("invalid camera value");
+    if (!th->inst) throw std::runtime_error("invalid tonemapper value");
+    if (!sc->committed) throw std::runtime_error("invalid scene value");
+    RendererObj& R = *rh->inst;
+    cudaStream_t st = dev->stream;
+    StatusRec status{1, 0.f};                                  // updateStatus(Rendering)  integratorrenderer.cpp:65
+    StatusFn statusFn = (StatusFn)R.statusCallback;
+    if (statusFn) statusFn(&status);
+    if (accumulate == 0) R.iteration = 0;
+    const int iteration = R.iteration++;
+    volatile bool* stopFlag = (volatile bool*)R.stopFlag;      // std::atomic<bool>* in the caller (integratorrenderer.h:100-101)
+    auto stopRequested = [&]() { return stopFlag && *stopFlag; };
+
+    FrameSetup fs = setup_frame(dev, R, *ch->inst, sc, fb, iteration);
+    FrameConst& fc = fs.fc;
+    if (R.backplate && !R.debug) {                             // backplate image joins the scene's texture table on first use
+        int idx = -1;
+        for (size_t i = 0; i < sc->hostTextures.size(); i++) if (sc->hostTextures[i].data == R.backplate->devPixels && R.backplate->devPixels) idx = (int)i;
+        if (idx < 0) {
+            image_upload(*R.backplate, st); sc->extraImages.push_back(R.backplate);
+            TextureRec t; t.data = R.backplate->devPixels; t.width = R.backplate->width; t.height = R.backplate->height;
+            t.format = R.backplate->format; t.bilinear = 0; t.invert = 0; t.pad = 0;
+            sc->hostTextures.push_back(t); idx = (int)sc->hostTextures.size() - 1;
+            sc->textures.release(); sc->textures.upload(sc->hostTextures, st);
+            sc->data.textures = sc->textures.p; fc.scene.textures = sc->textures.p;
+        }
+        fc.integ.backplateTex = idx;
+    }
+
+    const int spp = fc.integ.spp;
+    const size_t numPixels = fs.bufferRows * fb->width;
+    const int nl = fc.scene.numLights > 0 ? fc.scene.numLights : 1;
+    // chunk size: paths per wavefront pass, bounded so that one shadow-ray slot per (path, light) fits
+    uint64_t capacity = dev->chunkPaths;
+    const uint64_t totalPaths = (uint64_t)numPixels * spp;
+    if (capacity > totalPaths) capacity = totalPaths;
+    while (capacity * nl > (1ull << 28) && capacity > 65536) capacity >>= 1;
+    if (capacity < (uint64_t)spp) capacity = spp;
+    const uint32_t pixelsPerChunk = (uint32_t)(capacity / spp);
+    capacity = (uint64_t)pixelsPerChunk * spp;
+    dev->wf.ensure((uint32_t)capacity, (uint32_t)(capacity * nl), numPixels);
+    const WavefrontBuffers& wb = dev->wf.wb;
+
+    LaunchCfg lcTrace{dev->numSMs * 8, 128, st}, lcStream{dev->numSMs * 8, 256, st}, lcShade{dev->numSMs * 6, 128, st};
+    FrameTimers& tm = dev->timers; tm.reset();
+    const bool timers = dev->useTimers != 0;
+    uint64_t launches = 0, closestLaunches = 0, shadowLaunches = 0;
+    YRT_CK(cudaMemsetAsync(wb.stats, 0, 8 * sizeof(unsigned long long), st));
+    cudaEvent_t evStart = tm.get(), evStop = tm.get();
+    YRT_CK(cudaEventRecord(evStart, st));
+
+    FilmParams fp; fp.accum = fb->accum; fp.fbDevice = fb->devPacked; fp.format = fb->format; fp.fbStrideBytes = (int)fb->strideBytes;
+    fp.accumulate = accumulate ? 1 : 0; fp.gamma = th->inst->gamma; fp.rcpGamma = rcpf(th->inst->gamma); fp.vignetting = th->inst->vignetting ? 1 : 0;
+
+    bool stopped = false;
+    if (R.debug) {
+        if (R.maxDepth > 1) throw std::runtime_error("device_cuda: the debug renderer supports maxDepth = 1 only");
+        launch_debug(fc, wb, fp, (uint32_t)numPixels, lcStream); launches++;
+    } else if (numPixels) {
+        launch_pixel_sets(fc, wb.pixelSet, fs.sets, lcStream); launches++;
+        std::vector<cudaEvent_t> chunkDone;
+        size_t chunkIdx = 0;
+        for (size_t pixelBegin = 0; pixelBegin < numPixels; pixelBegin += pixelsPerChunk, chunkIdx++) {
+            // keep two chunks in flight so that stopFlag / statusCallback stay responsive (integratorrenderer.cpp:125,178)
+            if (chunkIdx >= 2) {
+                YRT_CK(cudaEventSynchronize(chunkDone[chunkIdx - 2]));
+                if (statusFn) { status.progress = float(pixelBegin - pixelsPerChunk) / float(numPixels); statusFn(&status); }
+            }
+            if (stopRequested()) { stopped = true; break; }
+            const uint32_t np = (uint32_t)std::min<size_t>(pixelsPerChunk, numPixels - pixelBegin);
+            if (timers) tm.begin(TK_RAYGEN_FILM, st);
+            launch_raygen(fc, wb, (uint32_t)pixelBegin, np, lcStream); launches++;
+            if (timers) tm.end(st);
+            int q = 0;
+            for (int depth = 0; depth < fc.integ.maxDepth; depth++, q ^= 1) {
+                if (timers) tm.begin(TK_CLOSEST, st);
+                launch_trace_closest(fc, wb, q, lcTrace); launches++; closestLaunches++;
+                if (timers) { tm.end(st); tm.begin(TK_SHADE, st); }
+                launch_shade(fc, wb, q, (uint32_t)pixelBegin, depth, lcShade); launches++;
+                if (timers) tm.end(st);
+                if (fc.scene.numLights > 0) {
+                    if (timers) tm.begin(TK_SHADOW, st);
+                    launch_trace_shadow(fc, wb, lcTrace); launches++; shadowLaunches++;
+                    if (timers) { tm.end(st); tm.begin(TK_SHADE, st); }
+                }
+                else if (timers) tm.begin(TK_SHADE, st);
+                launch_resolve(fc, wb, q, lcStream); launches += 2;
+                if (timers) tm.end(st);
+            }
+            if (timers) tm.begin(TK_RAYGEN_FILM, st);
+            launch_film(fc, wb, fp, (uint32_t)pixelBegin, np, lcStream); launches++;
+            if (timers) tm.end(st);
+            cudaEvent_t e = tm.get(); YRT_CK(cudaEventRecord(e, st)); chunkDone.push_back(e);
+        }
+    }
+    YRT_CK(cudaEventRecord(evStop, st));
+    uint64_t d2h = 0;
+    if (dev->readback) {
+        YRT_CK(cudaMemcpyAsync(fb->host[fb->cur], fb->devPacked, fb->bytes(), cudaMemcpyDeviceToHost, st));
+        d2h = fb->bytes(); fb->pendingBuf = -1;
+    } else fb->pendingBuf = (int)fb->cur;
+    unsigned long long hstats[4] = {0, 0, 0, 0};
+    YRT_CK(cudaMemcpyAsync(hstats, wb.stats, sizeof(hstats), cudaMemcpyDeviceToHost, st));
+    YRT_CK(cudaStreamSynchronize(st));
+    YRT_CK(cudaGetLastError());
+
+    yrtx_frame_stats& S = dev->stats;
+    float ms = 0.f; YRT_CK(cudaEventElapsedTime(&ms, evStart, evStop));
+    S.render_ms = ms; S.rays_closest = hstats[0]; S.rays_shadow = hstats[1]; S.node_visits = hstats[2]; S.tri_tests = hstats[3];
+    S.kernel_launches = launches; S.closest_launches = closestLaunches; S.shadow_launches = shadowLaunches;
+    S.closest_ms = S.shadow_ms = S.shade_ms = S.raygen_film_ms = 0.0;
+    for (const auto& sp : tm.spans) {
+        if (!sp.b) continue;
+        float t = 0.f; YRT_CK(cudaEventElapsedTime(&t, sp.a, sp.b));
+        if (sp.kind == TK_CLOSEST) S.closest_ms += t; else if (sp.kind == TK_SHADOW) S.shadow_ms += t;
+        else if (sp.kind == TK_SHADE) S.shade_ms += t; else S.raygen_film_ms += t;
+    }
+    S.trace_ms = S.closest_ms + S.shadow_ms;
+    S.h2d_bytes = fs.tableUploaded ? fs.tableBytes : 0; S.d2h_bytes = d2h;
+    S.num_triangles = fc.scene.numTris; S.num_nodes = fc.scene.numNodes; S.build_ms = sc->buildMs; S.bvh_builds = sc->rebuildCount;
+    S.host_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tHost0).count();
+    if (dev->verbose) {   // the reference's line (integratorrenderer.cpp:101-111), fed from CUDA events and device counters
+        const double dt = ms * 1e-3;
+        printf("render  %.2f fps, %.0f ms, %.3f mrps\n", 1.0 / dt, dt * 1000.0, double(hstats[0] + hstats[1]) / dt * 1e-6);
+    }
+    if (statusFn) { status.state = 2; status.progress = 1.f; statusFn(&status); }   // updateStatus(Done)
+    (void)stopped;
+}
+
+// ------------------------------------------------------------------------------------------------
+// extensions
+// ------------------------------------------------------------------------------------------------
+void trace_rays(yrt_device* dev, SceneHandle* sc, size_t n, const float* rays, void* hits, int closest, int onDevice, float* ms) {
+    if (!sc->committed) throw std::runtime_error("invalid scene value");
+    if (ms) *ms = 0.f;
+    if (!n) return;
+    cudaStream_t st = dev->stream;
+    DevBuf<float> dRays, dHits;
+    const float* rp = rays; float* hp = (float*)hits;
+    if (!onDevice) {
+        dRays.alloc(8 * n); dHits.alloc(8 * n);
+        YRT_CK(cudaMemcpyAsync(dRays.p, rays, 32 * n, cudaMemcpyHostToDevice, st));
+        YRT_CK(cudaMemcpyAsync(dHits.p, hits, 32 * n, cudaMemcpyHostToDevice, st));
+        rp = dRays.p; hp = dHits.p;
+    }
+    dev->wf.ensure(0, 0, 0);
+    if (dev->countStats) YRT_CK(cudaMemsetAsync(dev->wf.wb.stats, 0, 8 * sizeof(unsigned long long), st));
+    cudaEvent_t a, b; YRT_CK(cudaEventCreate(&a)); YRT_CK(cudaEventCreate(&b));
+    LaunchCfg lc{dev->numSMs * 8, 128, st};
+    YRT_CK(cudaEventRecord(a, st));
+    launch_trace_user(sc->data, rp, hp, n, closest, dev->countStats, dev->wf.wb.stats, lc);
+    YRT_CK(cudaEventRecord(b, st));
+    if (!onDevice) YRT_CK(cudaMemcpyAsync(hits, dHits.p, 32 * n, cudaMemcpyDeviceToHost, st));
+    unsigned long long hstats[4] = {0, 0, 0, 0};
+    if (dev->countStats) YRT_CK(cudaMemcpyAsync(hstats, dev->wf.wb.stats, sizeof(hstats), cudaMemcpyDeviceToHost, st));
+    YRT_CK(cudaStreamSynchronize(st));
+    YRT_CK(cudaGetLastError());
+    float t = 0.f; YRT_CK(cudaEventElapsedTime(&t, a, b));
+    cudaEventDestroy(a); cudaEventDestroy(b);
+    if (ms) *ms = t;
+    yrtx_frame_stats& S = dev->stats;
+    S.trace_ms = t; S.kernel_launches = 1; S.node_visits = hstats[2]; S.tri_tests = hstats[3];
+    if (closest) { S.rays_closest = n; S.rays_shadow = 0; S.closest_ms = t; S.closest_launches = 1; S.shadow_launches = 0; }
+    else { S.rays_closest = 0; S.rays_shadow = n; S.shadow_ms = t; S.shadow_launches = 1; S.closest_launches = 0; }
+    S.num_triangles = sc->data.numTris; S.num_nodes = sc->data.numNodes;
+}
+
+void primary_rays(yrt_device* dev, RendererHandle* rh, CameraHandle* ch, FrameBufferHandle* fb, float* rays, int* sets) {
+    if (!rh->inst || !ch->inst) throw std::runtime_error("invalid renderer or camera value");
+    RendererObj& R = *rh->inst;
+    if (R.debug) throw std::runtime_error("device_cuda: yrtxPrimaryRays needs the pathtracer renderer");
+    cudaStream_t st = dev->stream;
+    FrameSetup fs = setup_frame(dev, R, *ch->inst, nullptr, fb, 0);
+    FrameConst& fc = fs.fc;
+    const int spp = fc.integ.spp;
+    const size_t numPixels = fs.bufferRows * fb->width;
+    uint32_t pixelsPerChunk = (uint32_t)std::max<size_t>(1, std::min<size_t>(numPixels, (1u << 22) / (size_t)spp));
+    dev->wf.ensure(pixelsPerChunk * (uint32_t)spp, 1, numPixels);
+    const WavefrontBuffers& wb = dev->wf.wb;
+    LaunchCfg lc{dev->numSMs * 8, 256, st};
+    launch_pixel_sets(fc, wb.pixelSet, fs.sets, lc);
+    DevBuf<float> out; out.alloc((size_t)pixelsPerChunk * spp * 8);
+    for (size_t pixelBegin = 0; pixelBegin < numPixels; pixelBegin += pixelsPerChunk) {
+        const uint32_t np = (uint32_t)std::min<size_t>(pixelsPerChunk, numPixels - pixelBegin);
+        launch_raygen(fc, wb, (uint32_t)pixelBegin, np, lc);
+        launch_export_primary(fc, wb, (uint32_t)pixelBegin, np, out.p, lc);
+        YRT_CK(cudaMemcpyAsync(rays + pixelBegin * spp * 8, out.p, (size_t)np * spp * 32, cudaMemcpyDeviceToHost, st));
+        YRT_CK(cudaStreamSynchronize(st));
+    }
+    if (sets) {
+        std::vector<uint8_t> h(numPixels);
+        YRT_CK(cudaMemcpyAsync(h.data(), wb.pixelSet, numPixels, cudaMemcpyDeviceToHost, st));
+        YRT_CK(cudaStreamSynchronize(st));
+        for (size_t i = 0; i < numPixels; i++) sets[i] = h[i];
+    }
+    YRT_CK(cudaGetLastError());
+}
+
+void sample_table(yrt_device* dev, RendererHandle* rh, SceneHandle* sc, int iteration, int* sets, int* spp, int* n1, int* n2, float* table) {
+    if (!rh->inst) throw std::runtime_error("invalid renderer value");
+    RendererObj R = *rh->inst;                                // by value: querying must not advance the renderer
+    if (R.debug) throw std::runtime_error("device_cuda: the debug renderer has no sample table");
+    int s, a, b, rec;
+    const std::vector<float> tab = build_table(dev, R, (sc && sc->committed) ? sc : nullptr, iteration, s, a, b, rec);
+    if (sets) *sets = R.sets; if (spp) *spp = s; if (n1) *n1 = a; if (n2) *n2 = b;
+    if (table) {
+        const int base = 5 + a + 2 * b;                      // the documented record excludes the light samples
+        for (size_t i = 0; i < (size_t)R.sets * s; i++) memcpy(table + i * base, tab.data() + i * rec, base * sizeof(float));
+    }
+}
+
+}  // namespace yrt

@@ -304,15 +304,16 @@ __global__ void __launch_bounds__(128) k_shade(FrameConst fc, WavefrontBuffers w
                 continue;
             }
             // dome-light shadow-ray length (pathtraceintegrator.cpp:147-158) with the stated pins P1/P2
-            const bool infT = isinf(ig.tMaxShadowRay);
-            float jit = 0.f;
-            if (!infT) {
+            // P2: tMaxShadowRay == +inf makes the reference's expression inf - inf = NaN -> tfar = NaN -> never occluded
+            float tMax;
+            if (isinf(ig.tMaxShadowRay)) tMax = __int_as_float(0x7fc00000);
+            else {
                 const float r = hash_unit(hash4(__float_as_uint(fx), __float_as_uint(fy), (uint32_t)depth, li));
-                jit = 2.f * ig.tMaxShadowRay * ig.tMaxShadowJitter * r - ig.tMaxShadowRay * ig.tMaxShadowJitter;
+                const float jit = 2.f * ig.tMaxShadowRay * ig.tMaxShadowJitter * r - ig.tMaxShadowRay * ig.tMaxShadowJitter;
+                tMax = ig.tMaxShadowRay + jit;
+                const float dp = dot(ls.wi, ig.up);
+                if (dp <= 0.f) tMax += ig.tMaxShadowRay * 100.f * smoothstepf(0.f, 1.f, fabsf(dp));
             }
-            float tMax = ig.tMaxShadowRay + jit;
-            const float dp = dot(ls.wi, ig.up);
-            if (dp <= 0.f && !infT) tMax += ig.tMaxShadowRay * 100.f * smoothstepf(0.f, 1.f, fabsf(dp));
             const float eps = dg.error * ig.epsilon;
             const Col contrib = thr * lL * brdf * rcpf(ls.pdf);
             wb.shO[slot] = make_float4(dg.P.x, dg.P.y, dg.P.z, eps);
@@ -398,6 +399,20 @@ void launch_resolve(const FrameConst& fc, const WavefrontBuffers& wb, int queueS
 // ---- film: per-pixel sample sum, accumulation buffer, tone mapping, packing -------------------
 // SwapChain::update -> AccuBuffer::update api/framebuffer.h:289-304; DefaultToneMapper::eval
 // tonemappers/defaulttonemapper.h:38-51; FrameBufferRGB8/RGBA8/RGBFloat32::set api/framebuffer.h:127-129,171-178,220-226
+__device__ __forceinline__ void pack_pixel(const FilmParams& fp, int bx, int by, Col c) {
+    if (fp.format == 0) {
+        float* o = (float*)((char*)fp.fbDevice + (size_t)by * fp.fbStrideBytes) + 3 * bx;
+        o[0] = c.x; o[1] = c.y; o[2] = c.z;
+    } else {
+        const int bpp = fp.format == 1 ? 4 : 3;
+        unsigned char* o = (unsigned char*)fp.fbDevice + (size_t)by * fp.fbStrideBytes + bpp * bx;
+        o[0] = (unsigned char)rclamp(c.x * 255.0f, 0.0f, 255.0f);
+        o[1] = (unsigned char)rclamp(c.y * 255.0f, 0.0f, 255.0f);
+        o[2] = (unsigned char)rclamp(c.z * 255.0f, 0.0f, 255.0f);
+        if (bpp == 4) o[3] = 0;
+    }
+}
+
 __global__ void __launch_bounds__(256) k_film(FrameConst fc, WavefrontBuffers wb, FilmParams fp, uint32_t pixelBegin, uint32_t numPixels) {
     const int spp = fc.integ.spp;
     for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < numPixels; p += gridDim.x * blockDim.x) {
@@ -425,21 +440,43 @@ __global__ void __launch_bounds__(256) k_film(FrameConst fc, WavefrontBuffers wb
             const float d = sqrtf(ddx * ddx + ddy * ddy);
             c *= powf(cosf(d * 0.5f), 3.0f);
         }
-        if (fp.format == 0) {
-            float* o = (float*)((char*)fp.fbDevice + (size_t)by * fp.fbStrideBytes) + 3 * bx;
-            o[0] = c.x; o[1] = c.y; o[2] = c.z;
-        } else {
-            const int bpp = fp.format == 1 ? 4 : 3;
-            unsigned char* o = (unsigned char*)fp.fbDevice + (size_t)by * fp.fbStrideBytes + bpp * bx;
-            o[0] = (unsigned char)rclamp(c.x * 255.0f, 0.0f, 255.0f);
-            o[1] = (unsigned char)rclamp(c.y * 255.0f, 0.0f, 255.0f);
-            o[2] = (unsigned char)rclamp(c.z * 255.0f, 0.0f, 255.0f);
-            if (bpp == 4) o[3] = 0;
-        }
+        pack_pixel(fp, bx, by, c);
     }
 }
 void launch_film(const FrameConst& fc, const WavefrontBuffers& wb, const FilmParams& fp, uint32_t pixelBegin, uint32_t numPixels, LaunchCfg lc) {
     k_film<<<lc.blocks, 256, 0, lc.stream>>>(fc, wb, fp, pixelBegin, numPixels);
+}
+
+
+// ---- debug renderer (renderers/debugrenderer.cpp:66-148, maxDepth 1) -----------------------------
+// Primary rays through the pixel corners with the fixed lens sample (0.5, 0.5); colour = hash of geomID + primID,
+// written without tone mapping or accumulation.
+__global__ void __launch_bounds__(128) k_debug(FrameConst fc, WavefrontBuffers wb, FilmParams fp, uint32_t numPixels) {
+    const SceneData& sc = fc.scene;
+    unsigned long long rays = 0;
+    for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < numPixels; p += gridDim.x * blockDim.x) {
+        const int bx = p % fc.width, by = p / fc.width;
+        const int y = buffer2raster(by, fc.serverID, fc.serverCount);
+        const float fx = float(bx) * fc.rcpWidth, fy = float(y) * fc.rcpHeight;
+        for (int i = 0; i < fc.integ.spp; i++) {
+            V3 org, dir; camera_ray(fc.camera, fx, fy, 0.5f, 0.5f, org, dir);
+            HitRec h; TraceCounters cnt = {0, 0};
+            if (fc.integ.maxDepth > 0) { trace_ray<false, false>((const uint4*)sc.nodes, sc.tris, sc.numNodes, org, dir, 0.f, INFINITY, h, &cnt); rays++; }
+            else { h.geomID = -1; h.primID = -1; }
+            Col c(1.f);
+            if (h.geomID >= 0) {
+                const int id = h.geomID + h.primID;
+                c = Col(float((3434553u * ((unsigned)(id + 3243))) % 255u) / 255.0f,
+                        float((7342453u * ((unsigned)(id + 8237))) % 255u) / 255.0f,
+                        float((9234454u * ((unsigned)(id + 2343))) % 255u) / 255.0f);
+            }
+            pack_pixel(fp, bx, by, c);
+        }
+    }
+    if (rays) atomicAdd(&wb.stats[0], rays);
+}
+void launch_debug(const FrameConst& fc, const WavefrontBuffers& wb, const FilmParams& fp, uint32_t numPixels, LaunchCfg lc) {
+    k_debug<<<lc.blocks, 128, 0, lc.stream>>>(fc, wb, fp, numPixels);
 }
 
 }  // namespace yrt

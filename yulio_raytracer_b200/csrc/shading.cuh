@@ -60,12 +60,12 @@ YRT_D void post_intersect(const SceneData& sc, V3 org, V3 dir, float t, float u,
         dg.Ng = normalize(rayNg);
         const int4 tri = sc.indices[g.idxBase + primID];
         const float w = 1.0f - u - v;
-        if (g.hasUVs) {
-            const float2 st0 = sc.uvs[g.vtxBase + tri.x], st1 = sc.uvs[g.vtxBase + tri.y], st2 = sc.uvs[g.vtxBase + tri.z];
+        if (g.uvBase != YRT_NO_ATTR) {
+            const float2 st0 = sc.uvs[g.uvBase + tri.x], st1 = sc.uvs[g.uvBase + tri.y], st2 = sc.uvs[g.uvBase + tri.z];
             dg.s = st0.x * w + st1.x * u + st2.x * v; dg.t = st0.y * w + st1.y * u + st2.y * v;
         } else { dg.s = u; dg.t = v; }
-        if (g.hasNormals) {
-            const float4 a = sc.normals[g.vtxBase + tri.x], b = sc.normals[g.vtxBase + tri.y], c = sc.normals[g.vtxBase + tri.z];
+        if (g.nrmBase != YRT_NO_ATTR) {
+            const float4 a = sc.normals[g.nrmBase + tri.x], b = sc.normals[g.nrmBase + tri.y], c = sc.normals[g.nrmBase + tri.z];
             V3 Ns = w * V3(a.x, a.y, a.z) + u * V3(b.x, b.y, b.z) + v * V3(c.x, c.y, c.z);
             const float len2 = dot(Ns, Ns);
             Ns = len2 > 0 ? Ns * rsqrtf_exact(len2) : dg.Ng;

@@ -33,6 +33,9 @@ class FrameStats(C.Structure):
         ("trace_ms", C.c_double), ("node_visits", C.c_uint64), ("tri_tests", C.c_uint64),
         ("num_triangles", C.c_uint64), ("num_nodes", C.c_uint64),
         ("num_gpus", C.c_uint32), ("reserved", C.c_uint32),
+        ("closest_ms", C.c_double), ("shadow_ms", C.c_double), ("shade_ms", C.c_double), ("raygen_film_ms", C.c_double),
+        ("closest_launches", C.c_uint64), ("shadow_launches", C.c_uint64),
+        ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("bvh_builds", C.c_uint64),
     ]
 
 
@@ -74,6 +77,8 @@ _SIGS = {
 _OPTIONAL = {
     "yrtxPrimaryRays": (C.c_int, [H, H, H, C.c_void_p, C.c_void_p]),
     "yrtxSampleTable": (C.c_int, [H, H, C.c_int] + [C.POINTER(C.c_int)] * 4 + [C.c_void_p]),
+    "yrtxFrameBufferDevice": (C.c_int, [H, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
+    "yrtxSetReadback": (C.c_int, [C.c_int]),
 }
 
 #: every symbol include/yrt_device.h declares (checked by tests/test_cabi_exports.py)
@@ -282,6 +287,30 @@ class Device:
         ms = C.c_float(0)
         self._s("yrtxTraceRays", scene, n, rays.ctypes.data, hits.ctypes.data, int(closest), 0, C.byref(ms))
         return hits, ms.value
+
+    def sample_table(self, renderer, scene=None, iteration=0):
+        """Returns (table[sets, spp, rec], n1, n2) with rec = 5 + n1 + 2*n2 (yrtxSampleTable)."""
+        sets, spp, n1, n2 = C.c_int(0), C.c_int(0), C.c_int(0), C.c_int(0)
+        self._s("yrtxSampleTable", renderer, scene, iteration, C.byref(sets), C.byref(spp), C.byref(n1), C.byref(n2), None)
+        rec = 5 + n1.value + 2 * n2.value
+        tab = np.zeros((sets.value, spp.value, rec), np.float32)
+        self._s("yrtxSampleTable", renderer, scene, iteration, C.byref(sets), C.byref(spp), C.byref(n1), C.byref(n2), tab.ctypes.data)
+        return tab, n1.value, n2.value
+
+    def framebuffer_device(self, fb):
+        """(device pointer, bytes, row stride) of the frame the last rtRenderFrame produced (yrtxFrameBufferDevice)."""
+        ptr, nbytes, stride = C.c_void_p(0), C.c_size_t(0), C.c_size_t(0)
+        self._s("yrtxFrameBufferDevice", fb, C.byref(ptr), C.byref(nbytes), C.byref(stride))
+        return ptr.value, nbytes.value, stride.value
+
+    def set_readback(self, each_frame: bool):
+        self._s("yrtxSetReadback", int(each_frame))
+
+    def trace_rays_device(self, scene, rays_ptr: int, hits_ptr: int, n: int, closest: bool = True) -> float:
+        """Device-resident rays/hits (8 floats each); returns the CUDA-event time of the traversal kernel in ms."""
+        ms = C.c_float(0)
+        self._s("yrtxTraceRays", scene, n, rays_ptr, hits_ptr, int(closest), 1, C.byref(ms))
+        return ms.value
 
     def primary_rays(self, renderer, camera, fb, width, height, spp):
         rays = np.zeros((height * width * spp, 8), np.float32)
