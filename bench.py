@@ -151,6 +151,7 @@ def main():
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--cpu-sample", type=int, default=256, help="face resolution of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cfg", default="", help="extra device cfg keys (development A/B only)")
     ap.add_argument("--size", type=int, default=0, help="override the face resolution (profiling runs only; not a bench line)")
     ap.add_argument("--spp", type=int, default=0, help="override samples per pixel (profiling runs only; not a bench line)")
     args = ap.parse_args()
@@ -182,7 +183,7 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    dev = Device.cuda(cfg=f"gpu={local_rank},serverID={rank},serverCount={world}")
+    dev = Device.cuda(cfg=f"gpu={local_rank},serverID={rank},serverCount={world}" + ("," + args.cfg if args.cfg else ""))
     s = build_workload(dev, args.workload, size, spp, depth, "RGB8")
     stride = (3 * size + 3) // 4 * 4
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")

@@ -72,7 +72,7 @@ YRT_D RayPre ray_prepare(V3 O, V3 D) {
     const float dx = fabsf(D.x) < tiny ? copysignf(tiny, D.x) : D.x;
     const float dy = fabsf(D.y) < tiny ? copysignf(tiny, D.y) : D.y;
     const float dz = fabsf(D.z) < tiny ? copysignf(tiny, D.z) : D.z;
-    r.idir = V3(1.0f / dx, 1.0f / dy, 1.0f / dz);
+    r.idir = V3(__frcp_rn(dx), __frcp_rn(dy), __frcp_rn(dz));   // correctly rounded reciprocal == 1.0f / x
     r.octinv = (D.x >= 0.f ? 4u : 0u) | (D.y >= 0.f ? 2u : 0u) | (D.z >= 0.f ? 1u : 0u);
     return r;
 }
@@ -189,6 +189,161 @@ YRT_D bool trace_ray(const uint4* __restrict__ nodes, const float4* __restrict__
         }
     }
     return have;
+}
+
+
+// ------------------------------------------------------------------------------------------------------------
+// trace_stream — persistent, warp-synchronous traversal of a whole ray queue (the production path).
+//
+// Why not one ray per thread for the life of the thread (trace_ray above): the round-1 ncu capture of that loop on
+// incoherent bounce rays showed 8.4 of 32 lanes active per issued instruction (profiles/r1_closest_baseline.md):
+// lanes idle (a) while the slowest ray of the warp finishes and (b) while a few lanes test triangles. Here
+//   * a warp owns 32 ray slots and refills finished slots from a slice of the queue (one atomic per YRT_SLICE rays),
+//   * every macro step the warp votes (two ballots) whether to run the NODE phase (each lane with a pending inner
+//     node pops and tests one compressed node) or the TRIANGLE phase (each lane with pending triangles tests one),
+//     postponing the minority kind of work on the per-lane stack (Aila/Laine speculative traversal, Ylitie et al.
+//     triangle postponing), so both phases run with most lanes participating,
+//   * the first YRT_SM_STACK stack entries live in shared memory, deeper ones spill to local memory.
+// Results are independent of the schedule: closest-hit acceptance is the (t, geomID, primID) minimum, any-hit is
+// an OR over accepted hits, and the triangle arithmetic is YRT-PLUECKER-1 exactly as in trace_ray.
+#define YRT_TRACE_THREADS 128
+#define YRT_SM_STACK 8
+#define YRT_SLICE 256u
+#define YRT_REFILL_MIN 8
+#define YRT_NO_TRI 0xffffffffu
+
+struct TraceTune { int refillMin; int triNum; int triDen; };   // refill when >= refillMin slots idle; triangle phase when triNum*nT >= triDen*nN
+
+template <bool ANY, bool COUNT, class IO>
+YRT_D void trace_stream(const uint4* __restrict__ nodes, const float4* __restrict__ tris, uint32_t numNodes,
+                        uint32_t n, uint32_t* __restrict__ workCounter, IO io, TraceCounters& cnt, const TraceTune tune) {
+    __shared__ uint2 smStack[YRT_SM_STACK * YRT_TRACE_THREADS];
+    uint2 lstack[YRT_STACK_SIZE - YRT_SM_STACK];
+    const unsigned FULL = 0xffffffffu;
+    const unsigned lane = threadIdx.x & 31u, ltmask = (1u << lane) - 1u;
+    uint32_t sliceNext = 0, sliceEnd = 0; bool exhausted = false;
+    // rays claimed per atomic: a full YRT_SLICE for long queues, down to one warp's worth for short ones so that a
+    // late, nearly empty bounce still spreads over all SMs instead of serialising on a few warps
+    const uint32_t totalWarps = (gridDim.x * blockDim.x) >> 5;
+    uint32_t slice = (n / totalWarps) & ~31u;
+    slice = slice < 32u ? 32u : (slice > YRT_SLICE ? YRT_SLICE : slice);
+
+    bool active = false, occluded = false;
+    RayPre r; r.O = V3(0.f); r.D = V3(0.f); r.idir = V3(0.f); r.octinv = 0;
+    float tnear = 0.f, tbest = 0.f, bt = 0.f, bu = 0.f, bv = 0.f;
+    uint32_t bestTri = YRT_NO_TRI, tag = 0;
+    uint2 G = make_uint2(0u, 0u), T = make_uint2(0u, 0u);
+    int sp = 0;
+
+    while (true) {
+        // ---- refill idle slots ---------------------------------------------------------------------
+        const unsigned idleMask = __ballot_sync(FULL, !active);
+        if (idleMask) {
+            const uint32_t nIdle = __popc(idleMask);
+            if (nIdle >= (uint32_t)tune.refillMin && !(exhausted && sliceNext >= sliceEnd)) {
+                if (sliceNext >= sliceEnd) {
+                    uint32_t s = 0;
+                    if (lane == 0) s = atomicAdd(workCounter, slice);
+                    s = __shfl_sync(FULL, s, 0);
+                    if (s >= n) exhausted = true;
+                    else { sliceNext = s; sliceEnd = (n - s < slice) ? n : s + slice; }
+                }
+                const uint32_t avail = sliceEnd > sliceNext ? sliceEnd - sliceNext : 0u;
+                const uint32_t my = __popc(idleMask & ltmask);
+                if (!active && my < avail) {
+                    V3 O, D; float tfar;
+                    tag = io.load(sliceNext + my, O, D, tnear, tfar);
+                    r = ray_prepare(O, D);
+                    tbest = tfar; bt = tfar; bu = 0.f; bv = 0.f; bestTri = YRT_NO_TRI; occluded = false; sp = 0;
+                    T = make_uint2(0u, 0u);
+                    // root = "child 7^octinv of a virtual parent with imask 0"; an empty scene or an empty / NaN
+                    // interval (pin P2) starts with no work and is retired below as a miss
+                    G = make_uint2(0u, (numNodes != 0 && tnear <= tfar) ? 0x80000000u : 0u);
+                    active = true;
+                }
+                sliceNext += nIdle < avail ? nIdle : avail;
+            }
+            if (!__any_sync(FULL, active)) {
+                if (exhausted && sliceNext >= sliceEnd) break;
+                continue;
+            }
+        }
+
+        // ---- vote on the phase ------------------------------------------------------------------------
+        const bool nodeWork = active && (G.y & 0xff000000u) != 0u;
+        const bool triWork = active && T.y != 0u;
+        const int nN = __popc(__ballot_sync(FULL, nodeWork)), nT = __popc(__ballot_sync(FULL, triWork));
+
+        if (nT != 0 && (nN == 0 || tune.triNum * nT >= tune.triDen * nN)) {
+            // ---- TRIANGLE phase: one triangle per participating lane -------------------------------------
+            if (triWork) {
+                const uint32_t bit = 31u - __clz(T.y);
+                T.y &= ~(1u << bit);
+                const uint32_t triIdx = T.x + bit;
+                const float4* tp = tris + 3ull * triIdx;
+                const float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
+                if (COUNT) cnt.tris++;
+                float t, u, v, den; V3 Ng;
+                if (tri_test(r.O, r.D, V3(a.x, a.y, a.z), V3(b.x, b.y, b.z), V3(c.x, c.y, c.z), t, u, v, Ng, den) && t > tnear) {
+                    bool closer = t < tbest;
+                    if (!ANY && !closer && bestTri != YRT_NO_TRI && t == tbest) {      // tie: (geomID, primID) ascending
+                        const int g = __float_as_int(a.w), p = __float_as_int(b.w);
+                        const int bg = __float_as_int(__ldg(tris + 3ull * bestTri).w), bp = __float_as_int(__ldg(tris + 3ull * bestTri + 1).w);
+                        closer = (g < bg) || (g == bg && p < bp);
+                    }
+                    // back-face cull filter (shapes/trianglemesh_full.cpp:101-121): reject if dot(Ng, dir) <= 0
+                    if (closer && !((__float_as_uint(c.w) & YRT_TRI_FLAG_CULL) && den <= 0.f)) {
+                        tbest = t; bt = t; bu = u; bv = v; bestTri = triIdx;
+                        if (ANY) { occluded = true; G.y = 0u; T.y = 0u; sp = 0; }
+                    }
+                }
+            }
+        } else if (nN != 0) {
+            // ---- NODE phase: one compressed node per participating lane --------------------------------
+            if (nodeWork) {
+                if (T.y) {                                       // postpone the pending triangles
+                    if (sp < YRT_SM_STACK) smStack[sp * YRT_TRACE_THREADS + threadIdx.x] = T;
+                    else if (sp < YRT_STACK_SIZE) lstack[sp - YRT_SM_STACK] = T;
+                    if (sp < YRT_STACK_SIZE) sp++;
+                    T.y = 0u;
+                }
+                const uint32_t bit = 31u - __clz(G.y);
+                G.y &= ~(1u << bit);
+                const uint32_t slot = (bit - 24u) ^ r.octinv;
+                const uint32_t nodeIdx = G.x + __popc((G.y & 0xffu) & ~(0xffffffffu << slot));
+                if (G.y & 0xff000000u) {
+                    if (sp < YRT_SM_STACK) smStack[sp * YRT_TRACE_THREADS + threadIdx.x] = G;
+                    else if (sp < YRT_STACK_SIZE) lstack[sp - YRT_SM_STACK] = G;
+                    if (sp < YRT_STACK_SIZE) sp++;
+                }
+                const uint4* np = nodes + 5ull * nodeIdx;
+                const uint4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
+                if (COUNT) cnt.nodes++;
+                const uint32_t hm = node_test(n0, n1, n2, n3, n4, r, tnear, tbest);
+                G = make_uint2(n1.x, (hm & 0xff000000u) | (n0.w >> 24));
+                T = make_uint2(n1.y, hm & 0x00ffffffu);
+            }
+        }
+
+        // ---- normalise: refill (G, T) from the stack or retire the ray ------------------------------------
+        if (active && (G.y & 0xff000000u) == 0u && T.y == 0u) {
+            if (sp > 0) {
+                sp--;
+                const uint2 e = sp < YRT_SM_STACK ? smStack[sp * YRT_TRACE_THREADS + threadIdx.x] : lstack[sp - YRT_SM_STACK];
+                if (e.y & 0xff000000u) G = e; else T = e;
+            } else {
+                if (ANY) io.store_any(tag, occluded);
+                else if (bestTri == YRT_NO_TRI) io.store_closest(tag, bt, 0.f, 0.f, -1, -1, V3(0.f));
+                else {
+                    const float4* tp = tris + 3ull * bestTri;
+                    const float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
+                    const V3 p0(a.x, a.y, a.z), p1(b.x, b.y, b.z), p2(c.x, c.y, c.z);
+                    io.store_closest(tag, bt, bu, bv, __float_as_int(a.w), __float_as_int(b.w), cross(p0 - p1, p2 - p0));
+                }
+                active = false;
+            }
+        }
+    }
 }
 
 #endif  // __CUDACC__

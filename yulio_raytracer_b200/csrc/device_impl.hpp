@@ -116,6 +116,7 @@ struct yrt_device {
     int serverID = 0, serverCount = 1;         // g_serverID / g_serverCount (api/singleray_device.cpp:109-110)
     uint32_t chunkPaths = 1u << 22;
     int countStats = 0, verbose = 0, alwaysRebuild = 0, useTimers = 1;
+    int tuneRefillMin = 8, tuneTriNum = 3, tuneTriDen = 1, tuneSimple = 0;   // cfg refill=,trinum=,triden= (bvh.cuh: TraceTune)
     bool readback = true;                      // copy the frame to the host buffer inside yrtRenderFrame (yrtxSetReadback)
     yrt::WavefrontStorage wf;
     yrt::FrameTimers timers;

@@ -34,7 +34,7 @@ struct WavefrontBuffers {
     float4* shO; float4* shD;     // shadow ray queue
     float4* shC;                  // contribution.rgb | occluded flag (written by the any-hit kernel)
     uint32_t* queueA; uint32_t* queueB;
-    uint32_t* counters;           // [0] |queueA|, [1] |queueB|, [2] shadow rays this bounce, [3] spare
+    uint32_t* counters;           // [0] |queueA|, [1] |queueB|, [2] shadow rays this bounce, [4]/[5]/[6] next unclaimed ray of the closest / any-hit / user traversal launch
     unsigned long long* stats;    // [0] closest rays, [1] shadow rays, [2] node visits, [3] triangle tests
     uint8_t* pixelSet;            // per pixel of the frame: sample set index
 };
@@ -75,6 +75,6 @@ void launch_debug(const FrameConst& fc, const WavefrontBuffers& wb, const FilmPa
 void launch_export_primary(const FrameConst& fc, const WavefrontBuffers& wb, uint32_t pixelBegin, uint32_t numPixels, float* out, LaunchCfg lc);
 // yrtxTraceRays: rays/hits on the device, 8 floats each
 void launch_trace_user(const SceneData& sc, const float* rays, float* hits, size_t n, int closest, int countStats,
-                       unsigned long long* stats, LaunchCfg lc);
+                       unsigned long long* stats, uint32_t* workCounter, LaunchCfg lc);
 
 }  // namespace yrt

@@ -423,6 +423,9 @@ yrt_device* yrtCreateDevice(const char* parms, size_t numThreads, int threadsPri
         dev->useTimers = (int)cfg_int(cfg, "timers", 1);
         dev->serverID = (int)cfg_int(cfg, "serverID", 0);
         dev->serverCount = (int)cfg_int(cfg, "serverCount", 1);
+        dev->tuneRefillMin = (int)cfg_int(cfg, "refill", dev->tuneRefillMin);
+        dev->tuneTriNum = (int)cfg_int(cfg, "trinum", dev->tuneTriNum); dev->tuneTriDen = (int)cfg_int(cfg, "triden", dev->tuneTriDen); dev->tuneSimple = cfg_int(cfg, "trav", 1) == 0;
+        if (dev->tuneRefillMin < 1) dev->tuneRefillMin = 1; if (dev->tuneRefillMin > 32) dev->tuneRefillMin = 32;
         dev->stats.num_gpus = 1;
         return dev;
     } catch (const std::exception& e) { g_lastError = e.what(); return nullptr; }

@@ -419,6 +419,7 @@ static FrameSetup setup_frame(yrt_device* dev, RendererObj& R, const CameraData&
     FrameSetup fs;
     FrameConst& fc = fs.fc;
     if (sc) fc.scene = sc->data;
+    fc.scene.tuneRefillMin = dev->tuneRefillMin; fc.scene.tuneTriNum = dev->tuneTriNum; fc.scene.tuneTriDen = dev->tuneTriDen; fc.scene.tuneSimple = dev->tuneSimple;
     fc.camera = cam;
     fc.width = (int)fb->width; fc.height = (int)fb->height;
     fc.serverID = dev->serverID; fc.serverCount = dev->serverCount < 1 ? 1 : dev->serverCount;
@@ -576,6 +577,17 @@ void render_frame(yrt_device* dev, RendererHandle* rh, CameraHandle* ch, SceneHa
         if (sp.kind == TK_CLOSEST) S.closest_ms += t; else if (sp.kind == TK_SHADOW) S.shadow_ms += t;
         else if (sp.kind == TK_SHADE) S.shade_ms += t; else S.raygen_film_ms += t;
     }
+    if (dev->verbose >= 2) {   // stage times summed over the chunks, per position in the chunk's launch sequence
+        static const char* names[] = {"raygen/film", "closest", "shade", "shadow"};
+        const size_t perChunk = (size_t)(fc.scene.numLights > 0 ? 4 : 3) * fc.integ.maxDepth + 2;
+        std::vector<double> sum(perChunk, 0.0); std::vector<int> kind(perChunk, 0);
+        for (size_t i = 0; i < tm.spans.size(); i++) {
+            const auto& sp = tm.spans[i]; if (!sp.b) continue;
+            float t = 0.f; cudaEventElapsedTime(&t, sp.a, sp.b);
+            sum[i % perChunk] += t; kind[i % perChunk] = sp.kind;
+        }
+        for (size_t i = 0; i < perChunk; i++) printf("  stage %2zu %-12s %9.3f ms\n", i, names[kind[i]], sum[i]);
+    }
     S.trace_ms = S.closest_ms + S.shadow_ms;
     S.h2d_bytes = fs.tableUploaded ? fs.tableBytes : 0; S.d2h_bytes = d2h;
     S.num_triangles = fc.scene.numTris; S.num_nodes = fc.scene.numNodes; S.build_ms = sc->buildMs; S.bvh_builds = sc->rebuildCount;
@@ -609,7 +621,10 @@ void trace_rays(yrt_device* dev, SceneHandle* sc, size_t n, const float* rays, v
     cudaEvent_t a, b; YRT_CK(cudaEventCreate(&a)); YRT_CK(cudaEventCreate(&b));
     LaunchCfg lc{dev->numSMs * 8, 128, st};
     YRT_CK(cudaEventRecord(a, st));
-    launch_trace_user(sc->data, rp, hp, n, closest, dev->countStats, dev->wf.wb.stats, lc);
+    if (n > 0xfffffff0ull) throw std::runtime_error("device_cuda: yrtxTraceRays is limited to 2^32 - 16 rays per call");
+    YRT_CK(cudaMemsetAsync(dev->wf.wb.counters + 6, 0, sizeof(uint32_t), st));
+    SceneData sd = sc->data; sd.tuneRefillMin = dev->tuneRefillMin; sd.tuneTriNum = dev->tuneTriNum; sd.tuneTriDen = dev->tuneTriDen; sd.tuneSimple = dev->tuneSimple;
+    launch_trace_user(sd, rp, hp, n, closest, dev->countStats, dev->wf.wb.stats, dev->wf.wb.counters + 6, lc);
     YRT_CK(cudaEventRecord(b, st));
     if (!onDevice) YRT_CK(cudaMemcpyAsync(hits, dHits.p, 32 * n, cudaMemcpyDeviceToHost, st));
     unsigned long long hstats[4] = {0, 0, 0, 0};

@@ -138,7 +138,7 @@ __global__ void __launch_bounds__(256) k_raygen(FrameConst fc, WavefrontBuffers 
         wb.medium[pid] = make_float4(1.f, 1.f, 1.f, 1.f);
         wb.queueA[pid] = pid;
     }
-    if (blockIdx.x == 0 && threadIdx.x == 0) { wb.counters[0] = numPaths; wb.counters[1] = 0; wb.counters[2] = 0; }
+    if (blockIdx.x == 0 && threadIdx.x == 0) { wb.counters[0] = numPaths; wb.counters[1] = 0; wb.counters[2] = 0; wb.counters[4] = 0; wb.counters[5] = 0; }
 }
 void launch_raygen(const FrameConst& fc, const WavefrontBuffers& wb, uint32_t pixelBegin, uint32_t numPixels, LaunchCfg lc) {
     k_raygen<<<lc.blocks, 256, 0, lc.stream>>>(fc, wb, pixelBegin, numPixels * (uint32_t)fc.integ.spp);
@@ -153,65 +153,121 @@ void launch_export_primary(const FrameConst& fc, const WavefrontBuffers& wb, uin
     k_export_primary<<<lc.blocks, 256, 0, lc.stream>>>(fc, wb, numPixels * (uint32_t)fc.integ.spp, out);
 }
 
-// ---- traversal kernels (persistent threads over the ray queues) ---------------------------------
-template <bool COUNT>
-__global__ void __launch_bounds__(128) k_trace_closest(SceneData sc, WavefrontBuffers wb, int queueSel) {
-    const uint32_t* __restrict__ queue = queueSel ? wb.queueB : wb.queueA;
-    const uint32_t n = wb.counters[queueSel];
-    TraceCounters cnt = {0, 0};
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+// ---- traversal kernels (persistent warps over the ray queues, bvh.cuh: trace_stream) -----------------------
+// counters[4] / [5] / [6]: next unclaimed queue position of the closest-hit / any-hit / user launch
+struct ClosestIO {
+    WavefrontBuffers wb; const uint32_t* __restrict__ queue;
+    __device__ __forceinline__ uint32_t load(uint32_t i, V3& O, V3& D, float& tnear, float& tfar) const {
         const uint32_t pid = queue[i];
         const float4 o = wb.rayO[pid], d = wb.rayD[pid];
-        HitRec h;
-        trace_ray<false, COUNT>((const uint4*)sc.nodes, sc.tris, sc.numNodes, f4v(o), f4v(d), o.w, d.w, h, &cnt);
-        wb.hitA[pid] = make_float4(h.t, h.u, h.v, __int_as_float(h.geomID));
-        wb.hitB[pid] = make_float4(h.Ng.x, h.Ng.y, h.Ng.z, __int_as_float(h.primID));
+        O = f4v(o); D = f4v(d); tnear = o.w; tfar = d.w;
+        return pid;
     }
+    __device__ __forceinline__ void store_closest(uint32_t pid, float t, float u, float v, int g, int p, V3 Ng) const {
+        wb.hitA[pid] = make_float4(t, u, v, __int_as_float(g));
+        wb.hitB[pid] = make_float4(Ng.x, Ng.y, Ng.z, __int_as_float(p));
+    }
+    __device__ __forceinline__ void store_any(uint32_t, bool) const {}
+};
+struct ShadowIO {
+    WavefrontBuffers wb;
+    __device__ __forceinline__ uint32_t load(uint32_t i, V3& O, V3& D, float& tnear, float& tfar) const {
+        const float4 o = wb.shO[i], d = wb.shD[i];
+        O = f4v(o); D = f4v(d); tnear = o.w; tfar = d.w;
+        return i;
+    }
+    __device__ __forceinline__ void store_closest(uint32_t, float, float, float, int, int, V3) const {}
+    __device__ __forceinline__ void store_any(uint32_t i, bool occluded) const { wb.shC[i].w = occluded ? 1.f : 0.f; }
+};
+struct UserIO {
+    const float4* __restrict__ rays; float4* __restrict__ hits;
+    __device__ __forceinline__ uint32_t load(uint32_t i, V3& O, V3& D, float& tnear, float& tfar) const {
+        const float4 o = __ldg(&rays[2ull * i]), d = __ldg(&rays[2ull * i + 1]);
+        O = f4v(o); D = f4v(d); tnear = o.w; tfar = d.w;
+        return i;
+    }
+    __device__ __forceinline__ void store_closest(uint32_t i, float t, float u, float v, int g, int p, V3 Ng) const {
+        hits[2ull * i] = make_float4(t, u, v, __int_as_float(g));
+        hits[2ull * i + 1] = make_float4(__int_as_float(p), Ng.x, Ng.y, Ng.z);
+    }
+    __device__ __forceinline__ void store_any(uint32_t i, bool occluded) const {
+        float4 a = hits[2ull * i]; a.w = __int_as_float(occluded ? 0 : -1); hits[2ull * i] = a;
+    }
+};
+
+// ---- A/B baseline: one ray per thread for the life of the thread (bvh.cuh: trace_ray), cfg trav=0 ------------
+template <bool ANY, class IO>
+__global__ void __launch_bounds__(YRT_TRACE_THREADS) k_trace_simple(SceneData sc, IO io, const uint32_t* __restrict__ nPtr, uint32_t nImm) {
+    const uint32_t n = nPtr ? *nPtr : nImm;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        V3 O, D; float tnear, tfar;
+        const uint32_t tag = io.load(i, O, D, tnear, tfar);
+        HitRec h; TraceCounters cnt;
+        const bool hit = trace_ray<ANY, false>((const uint4*)sc.nodes, sc.tris, sc.numNodes, O, D, tnear, tfar, h, &cnt);
+        if (ANY) io.store_any(tag, hit);
+        else io.store_closest(tag, h.t, hit ? h.u : 0.f, hit ? h.v : 0.f, h.geomID, h.primID, hit ? h.Ng : V3(0.f));
+    }
+}
+
+template <bool COUNT>
+__global__ void __launch_bounds__(YRT_TRACE_THREADS) k_trace_closest(SceneData sc, WavefrontBuffers wb, int queueSel) {
+    const uint32_t n = wb.counters[queueSel];
+    TraceCounters cnt = {0, 0};
+    ClosestIO io{wb, queueSel ? wb.queueB : wb.queueA};
+    trace_stream<false, COUNT>((const uint4*)sc.nodes, sc.tris, sc.numNodes, n, &wb.counters[4], io, cnt, TraceTune{sc.tuneRefillMin, sc.tuneTriNum, sc.tuneTriDen});
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&wb.stats[0], (unsigned long long)n);
     if (COUNT) { atomicAdd(&wb.stats[2], (unsigned long long)cnt.nodes); atomicAdd(&wb.stats[3], (unsigned long long)cnt.tris); }
 }
+__global__ void k_count_closest(WavefrontBuffers wb, int queueSel) { atomicAdd(&wb.stats[0], (unsigned long long)wb.counters[queueSel]); }
 void launch_trace_closest(const FrameConst& fc, const WavefrontBuffers& wb, int queueSel, LaunchCfg lc) {
-    if (fc.countStats) k_trace_closest<true><<<lc.blocks, 128, 0, lc.stream>>>(fc.scene, wb, queueSel);
-    else k_trace_closest<false><<<lc.blocks, 128, 0, lc.stream>>>(fc.scene, wb, queueSel);
+    if (fc.scene.tuneSimple) {
+        ClosestIO io{wb, queueSel ? wb.queueB : wb.queueA};
+        k_trace_simple<false><<<lc.blocks, YRT_TRACE_THREADS, 0, lc.stream>>>(fc.scene, io, &wb.counters[queueSel], 0u);
+        k_count_closest<<<1, 1, 0, lc.stream>>>(wb, queueSel);
+        return;
+    }
+    if (fc.countStats) k_trace_closest<true><<<lc.blocks, YRT_TRACE_THREADS, 0, lc.stream>>>(fc.scene, wb, queueSel);
+    else k_trace_closest<false><<<lc.blocks, YRT_TRACE_THREADS, 0, lc.stream>>>(fc.scene, wb, queueSel);
 }
 
 template <bool COUNT>
-__global__ void __launch_bounds__(128) k_trace_shadow(SceneData sc, WavefrontBuffers wb) {
+__global__ void __launch_bounds__(YRT_TRACE_THREADS) k_trace_shadow(SceneData sc, WavefrontBuffers wb) {
     const uint32_t n = wb.counters[2];
     TraceCounters cnt = {0, 0};
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const float4 o = wb.shO[i], d = wb.shD[i];
-        HitRec h;
-        const bool occluded = trace_ray<true, COUNT>((const uint4*)sc.nodes, sc.tris, sc.numNodes, f4v(o), f4v(d), o.w, d.w, h, &cnt);
-        wb.shC[i].w = occluded ? 1.f : 0.f;
-    }
+    ShadowIO io{wb};
+    trace_stream<true, COUNT>((const uint4*)sc.nodes, sc.tris, sc.numNodes, n, &wb.counters[5], io, cnt, TraceTune{sc.tuneRefillMin, sc.tuneTriNum, sc.tuneTriDen});
     if (COUNT) { atomicAdd(&wb.stats[2], (unsigned long long)cnt.nodes); atomicAdd(&wb.stats[3], (unsigned long long)cnt.tris); }
 }
 void launch_trace_shadow(const FrameConst& fc, const WavefrontBuffers& wb, LaunchCfg lc) {
-    if (fc.countStats) k_trace_shadow<true><<<lc.blocks, 128, 0, lc.stream>>>(fc.scene, wb);
-    else k_trace_shadow<false><<<lc.blocks, 128, 0, lc.stream>>>(fc.scene, wb);
+    if (fc.scene.tuneSimple) { ShadowIO io{wb}; k_trace_simple<true><<<lc.blocks, YRT_TRACE_THREADS, 0, lc.stream>>>(fc.scene, io, &wb.counters[2], 0u); return; }
+    if (fc.countStats) k_trace_shadow<true><<<lc.blocks, YRT_TRACE_THREADS, 0, lc.stream>>>(fc.scene, wb);
+    else k_trace_shadow<false><<<lc.blocks, YRT_TRACE_THREADS, 0, lc.stream>>>(fc.scene, wb);
 }
 
-template <bool COUNT>
-__global__ void __launch_bounds__(128) k_trace_user(SceneData sc, const float4* __restrict__ rays, float4* __restrict__ hits, size_t n, int closest, unsigned long long* stats) {
+template <bool ANY, bool COUNT>
+__global__ void __launch_bounds__(YRT_TRACE_THREADS) k_trace_user(SceneData sc, const float4* __restrict__ rays, float4* __restrict__ hits, uint32_t n,
+                                                                  uint32_t* workCounter, unsigned long long* stats) {
     TraceCounters cnt = {0, 0};
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-        const float4 o = __ldg(&rays[2 * i]), d = __ldg(&rays[2 * i + 1]);
-        HitRec h;
-        if (closest) {
-            trace_ray<false, COUNT>((const uint4*)sc.nodes, sc.tris, sc.numNodes, f4v(o), f4v(d), o.w, d.w, h, &cnt);
-            hits[2 * i] = make_float4(h.t, h.u, h.v, __int_as_float(h.geomID));
-            hits[2 * i + 1] = make_float4(__int_as_float(h.primID), h.geomID >= 0 ? h.Ng.x : 0.f, h.geomID >= 0 ? h.Ng.y : 0.f, h.geomID >= 0 ? h.Ng.z : 0.f);
-        } else {
-            const bool occ = trace_ray<true, COUNT>((const uint4*)sc.nodes, sc.tris, sc.numNodes, f4v(o), f4v(d), o.w, d.w, h, &cnt);
-            float4 a = hits[2 * i]; a.w = __int_as_float(occ ? 0 : -1); hits[2 * i] = a;
-        }
-    }
+    UserIO io{rays, hits};
+    trace_stream<ANY, COUNT>((const uint4*)sc.nodes, sc.tris, sc.numNodes, n, workCounter, io, cnt, TraceTune{sc.tuneRefillMin, sc.tuneTriNum, sc.tuneTriDen});
     if (COUNT && stats) { atomicAdd(&stats[2], (unsigned long long)cnt.nodes); atomicAdd(&stats[3], (unsigned long long)cnt.tris); }
 }
-void launch_trace_user(const SceneData& sc, const float* rays, float* hits, size_t n, int closest, int countStats, unsigned long long* stats, LaunchCfg lc) {
-    if (countStats) k_trace_user<true><<<lc.blocks, 128, 0, lc.stream>>>(sc, (const float4*)rays, (float4*)hits, n, closest, stats);
-    else k_trace_user<false><<<lc.blocks, 128, 0, lc.stream>>>(sc, (const float4*)rays, (float4*)hits, n, closest, stats);
+void launch_trace_user(const SceneData& sc, const float* rays, float* hits, size_t n, int closest, int countStats,
+                       unsigned long long* stats, uint32_t* workCounter, LaunchCfg lc) {
+    const float4* r = (const float4*)rays; float4* h = (float4*)hits; const uint32_t m = (uint32_t)n;
+    if (sc.tuneSimple) {
+        UserIO io{r, h};
+        if (closest) k_trace_simple<false><<<lc.blocks, YRT_TRACE_THREADS, 0, lc.stream>>>(sc, io, nullptr, m);
+        else k_trace_simple<true><<<lc.blocks, YRT_TRACE_THREADS, 0, lc.stream>>>(sc, io, nullptr, m);
+        return;
+    }
+    if (closest) {
+        if (countStats) k_trace_user<false, true><<<lc.blocks, YRT_TRACE_THREADS, 0, lc.stream>>>(sc, r, h, m, workCounter, stats);
+        else k_trace_user<false, false><<<lc.blocks, YRT_TRACE_THREADS, 0, lc.stream>>>(sc, r, h, m, workCounter, stats);
+    } else {
+        if (countStats) k_trace_user<true, true><<<lc.blocks, YRT_TRACE_THREADS, 0, lc.stream>>>(sc, r, h, m, workCounter, stats);
+        else k_trace_user<true, false><<<lc.blocks, YRT_TRACE_THREADS, 0, lc.stream>>>(sc, r, h, m, workCounter, stats);
+    }
 }
 
 // ---- shading -------------------------------------------------------------------------------------
@@ -390,7 +446,7 @@ __global__ void __launch_bounds__(256) k_resolve(WavefrontBuffers wb, int queueS
         wb.Lacc[pid] = make_float4(L.x, L.y, L.z, 0.f);
     }
 }
-__global__ void k_reset_counters(WavefrontBuffers wb, int queueSel) { wb.counters[queueSel] = 0; wb.counters[2] = 0; }
+__global__ void k_reset_counters(WavefrontBuffers wb, int queueSel) { wb.counters[queueSel] = 0; wb.counters[2] = 0; wb.counters[4] = 0; wb.counters[5] = 0; }
 void launch_resolve(const FrameConst& fc, const WavefrontBuffers& wb, int queueSel, LaunchCfg lc) {
     k_resolve<<<lc.blocks, 256, 0, lc.stream>>>(wb, queueSel);
     k_reset_counters<<<1, 1, 0, lc.stream>>>(wb, queueSel);
