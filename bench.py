@@ -194,26 +194,15 @@ def main():
             self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 3}
     ptr, nbytes, _ = dev.framebuffer_device(s.framebuffer)
     fb_t = torch.as_tensor(_DevView(ptr, nbytes), device="cuda")
-    rows_of = [[y for y in range(size) if ((y >> 2) - r) % world == 0] for r in range(world)]
-    my_rows = len(rows_of[rank])
-    if world > 1 and rank == 0:
-        full = torch.zeros(size * stride, dtype=torch.uint8, device="cuda")
-        row_idx = [torch.tensor(r, device="cuda", dtype=torch.long) for r in rows_of]
-        max_rows = max(len(r) for r in rows_of)
-        parts = [torch.empty(max_rows * stride, dtype=torch.uint8, device="cuda") for _ in range(world)]
-    gather_ms = []
+    from yulio_raytracer_b200 import bands
+    gatherer = bands.BandGather(size, stride, rank, world, "cuda") if world > 1 else None
 
     def gather_bands():
         if world == 1:
             return 0.0
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        send = fb_t[: max(len(r) for r in rows_of) * stride]
-        dist.gather(send, parts if rank == 0 else None, dst=0)
-        if rank == 0:
-            fv = full.view(size, stride)
-            for r in range(world):
-                fv.index_copy_(0, row_idx[r], parts[r][: len(rows_of[r]) * stride].view(-1, stride))
+        gatherer.gather(fb_t)
         e1.record(); e1.synchronize()
         return e0.elapsed_time(e1)
 

@@ -169,6 +169,10 @@ YRT_API yrt_status yrtxPrimaryRays(yrt_device*, yrt_handle renderer, yrt_handle 
  * (may be NULL to query sizes): {pixel.x, pixel.y, time, lens.x, lens.y, 1D[n1], 2D[2*n2]}. */
 YRT_API yrt_status yrtxSampleTable(yrt_device*, yrt_handle renderer, yrt_handle scene, int iteration,
                                    int* sets, int* spp, int* n1, int* n2, float* table);
+/* Same table without a device or handles (host-only code; usable on a box without a GPU): filter in {"bspline","box","none"}.
+ * With table == NULL only the sizes are returned. Record layout as yrtxSampleTable. */
+YRT_API yrt_status yrtxHostSampleTable(const char* filter, int spp, int sets, int maxDepth, int iteration,
+                                       int* outSpp, int* n1, int* n2, float* table);
 /* Device-resident copy of the current buffer of a framebuffer (what yrtRenderFrame wrote before the D2H copy):
  * row stride as in the reference (api/framebuffer.h:106,146,195). Used by bench.py to gather row bands
  * between ranks over NCCL without a host round trip. */

@@ -16,6 +16,9 @@
 #include "api/scene.h"
 #include "api/swapchain.h"
 #include "renderers/integratorrenderer.h"
+#include "samplers/sampler.h"
+#include "filters/boxfilter.h"
+#include "filters/bsplinefilter.h"
 #include "embree2/rtcore.h"
 #include "embree2/rtcore_ray.h"
 #include "../../include/yrt_device.h"
@@ -158,6 +161,32 @@ yrt_status yrtxTraceRays(yrt_device*, yrt_handle scene, size_t n, const float* r
             }
         }
         if (ms) *ms = (float)std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        return YRT_OK;
+    } catch (const std::exception& e) { g_err = e.what(); return YRT_ERROR; }
+}
+
+// The reference's own SamplerFactory, driven the way RenderJob drives it (integratorrenderer.cpp:86-88 +
+// PathTraceIntegrator::requestSamples pathtraceintegrator.cpp:35-47, no precomputed lights).
+yrt_status yrtxHostSampleTable(const char* filter, int spp, int sets, int maxDepth, int iteration, int* outSpp, int* n1, int* n2, float* table) {
+    try {
+        const std::string f(filter ? filter : "bspline");
+        embree::Ref<embree::Filter> flt;
+        if (f == "box") flt = new embree::BoxFilter; else if (f == "bspline") flt = new embree::BSplineFilter;
+        else if (f != "none") throw std::runtime_error("unknown filter type: " + f);
+        embree::Ref<embree::SamplerFactory> sf = new embree::SamplerFactory((unsigned)spp, (unsigned)sets);
+        sf->request2D(); sf->request2D(maxDepth); sf->request1D(maxDepth);
+        sf->init(iteration, flt);
+        const int a = sf->numSamples1D, b = sf->numSamples2D, rec = 5 + a + 2 * b;
+        if (outSpp) *outSpp = sf->samplesPerPixel; if (n1) *n1 = a; if (n2) *n2 = b;
+        if (table)
+            for (int set = 0; set < sf->sampleSets; set++)
+                for (int s = 0; s < sf->samplesPerPixel; s++) {
+                    const embree::PrecomputedSample& p = sf->samples[set][s];
+                    float* o = table + ((size_t)set * sf->samplesPerPixel + s) * rec;
+                    o[0] = p.pixel.x; o[1] = p.pixel.y; o[2] = p.time; o[3] = p.lens.x; o[4] = p.lens.y;
+                    for (int d = 0; d < a; d++) o[5 + d] = p.samples1D[d];
+                    for (int d = 0; d < b; d++) { o[5 + a + 2 * d] = p.samples2D[d].x; o[5 + a + 2 * d + 1] = p.samples2D[d].y; }
+                }
         return YRT_OK;
     } catch (const std::exception& e) { g_err = e.what(); return YRT_ERROR; }
 }

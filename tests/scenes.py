@@ -435,14 +435,14 @@ def soup_arrays(num_tris, seed=12345, extent=1000.0, blob_tris=1000, blob_radius
     centres = rng.uniform(0, extent, (nblob, 3))
     owner = rng.integers(0, nblob, num_tris) if num_tris % blob_tris else np.repeat(np.arange(nblob), blob_tris)
     c = centres[owner] + rng.normal(0, blob_radius / 2, (num_tris, 3))
-    v = c[:, None, :] + rng.uniform(-edge, edge, (num_tris, 3, 3)) * (extent / 1000.0) * 10.0
+    v = c[:, None, :] + rng.uniform(-edge, edge, (num_tris, 3, 3))
     pos = v.reshape(-1, 3).astype(F)
     tri = np.arange(num_tris * 3, dtype=np.int32).reshape(-1, 3)
     return pos, tri
 
 
-def soup(dev, num_tris, seed=12345, extent=1000.0, meshes=1, cull=False):
-    pos, tri = soup_arrays(num_tris, seed, extent)
+def soup(dev, num_tris, seed=12345, extent=1000.0, meshes=1, cull=False, edge=0.1, blob_radius=2.0):
+    pos, tri = soup_arrays(num_tris, seed, extent, blob_radius=blob_radius, edge=edge)
     matte = dev.rtNewMaterial("matte"); dev.rtCommit(matte)
     prims = []
     per = (num_tris + meshes - 1) // meshes

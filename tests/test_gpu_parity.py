@@ -61,8 +61,8 @@ def test_cornell_image(cuda_dev, oracle_dev):
 
 @pytest.mark.parametrize("n_tris,meshes,cull", [(1, 1, False), (7, 1, False), (1000, 3, False), (20000, 2, True), (200000, 4, False)])
 def test_soup_closest_and_anyhit(cuda_dev, oracle_dev, n_tris, meshes, cull):
-    sg = scenes.soup(cuda_dev, n_tris, seed=n_tris, extent=20.0, meshes=meshes, cull=cull)
-    so = scenes.soup(oracle_dev, n_tris, seed=n_tris, extent=20.0, meshes=meshes, cull=cull)
+    sg = scenes.soup(cuda_dev, n_tris, seed=n_tris, extent=20.0, meshes=meshes, cull=cull, edge=0.6)
+    so = scenes.soup(oracle_dev, n_tris, seed=n_tris, extent=20.0, meshes=meshes, cull=cull, edge=0.6)
     rays = scenes.random_rays(20000, seed=n_tris + 1, extent=20.0)
     hg, _ = cuda_dev.trace_rays(sg.scene, rays, closest=True)
     ho, _ = oracle_dev.trace_rays(so.scene, rays, closest=True)

@@ -1,0 +1,103 @@
+"""CPU tests (no GPU) of the product's host side: the C-ABI library loads and exports every declared symbol, the
+host-built sample tables are bit-identical to the reference's SamplerFactory (golden vectors generated from the reference),
+the library refuses to run without a CUDA device (no CPU fallback), and the N-rank band partition / gather (gloo, world 2)."""
+import ctypes
+import hashlib
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from tests.golden import make_golden as mg
+from yulio_raytracer_b200 import bands
+from yulio_raytracer_b200.devapi import CUDA_LIB, DECLARED_SYMBOLS, Device, host_sample_table
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(REPO, "tests", "golden")
+
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(REPO, "include", "yrt_device.h")).read()
+    declared = set(re.findall(r"\b(yrtx?[A-Z]\w+)\s*\(", header))
+    assert declared == set(DECLARED_SYMBOLS), declared ^ set(DECLARED_SYMBOLS)
+    lib = ctypes.CDLL(CUDA_LIB)
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{CUDA_LIB} does not export {name}"
+
+
+def test_no_cpu_fallback():
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        Device.cuda()
+
+
+def test_product_never_references_the_oracle():
+    for root, _, files in os.walk(os.path.join(REPO, "yulio_raytracer_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".hpp", ".h", ".cpp")):
+                text = open(os.path.join(root, f), errors="replace").read()
+                assert "import oracle" not in text and "from oracle" not in text and "liboracle" not in text, os.path.join(root, f)
+
+
+@pytest.mark.parametrize("case", mg.TABLE_CASES)
+def test_sample_tables_match_reference(case):
+    f, spp, depth, it = case
+    gold = np.load(os.path.join(GOLD, "sample_tables.npz"))
+    t, n1, n2 = host_sample_table(CUDA_LIB, f, spp, 64, depth, it)
+    assert np.array_equal(t.view(np.uint32), gold[f"{f}_{spp}_{depth}_{it}"].view(np.uint32))
+
+
+@pytest.mark.parametrize("case", mg.HASH_CASES)
+def test_sample_table_hashes_match_reference(case):
+    f, spp, depth, it = case
+    gold = np.load(os.path.join(GOLD, "sample_tables.npz"))
+    t, _, _ = host_sample_table(CUDA_LIB, f, spp, 64, depth, it)
+    assert hashlib.sha256(t.tobytes()).digest() == gold[f"sha256_{f}_{spp}_{depth}_{it}"].tobytes()
+
+
+def test_sample_table_properties():
+    t, n1, n2 = host_sample_table(CUDA_LIB, "none", 16, 64, 4, 0)
+    assert t.shape == (64, 16, 5 + 4 + 2 * 5)
+    assert (t >= 0).all() and (t < 1).all()
+    # multi-jittered 2-D pattern: each of the 16 samples of a set falls in its own 1/16 column and row stratum (chunk = 64 though:
+    # the set is a 16-sample slice of a 64-sample pattern, so strata are only distinct at 1/64 resolution)
+    px = np.floor(t[0, :, 0] * 64).astype(int)
+    assert len(set(px)) == 16
+    with pytest.raises(RuntimeError):
+        host_sample_table(CUDA_LIB, "gauss", 1, 64, 2, 0)
+
+
+@pytest.mark.parametrize("height,world", [(64, 2), (70, 3), (1024, 8), (5, 2)])
+def test_band_partition_covers_every_row_once(height, world):
+    rows = [bands.active_rows(height, r, world) for r in range(world)]
+    flat = sorted(y for r in rows for y in r)
+    assert flat == list(range(height))
+    for r in range(world):
+        assert [bands.buffer_row(y, world) for y in rows[r]] == list(range(len(rows[r])))   # compacted, in order
+
+
+def _gather_worker(rank, world, port, height, stride, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    g = bands.BandGather(height, stride, rank, world, "cpu")
+    local = torch.zeros(height * stride, dtype=torch.uint8)
+    for b, y in enumerate(g.rows[rank]):                       # what device `rank` would have rendered: row y -> value y % 251
+        local.view(height, stride)[b] = y % 251
+    full = g.gather(local)
+    if rank == 0:
+        torch.save(full, out)
+    dist.destroy_process_group()
+
+
+def test_band_gather_world2_gloo(tmp_path):
+    height, stride, world = 70, 52, 2
+    out = str(tmp_path / "full.pt")
+    mp.spawn(_gather_worker, args=(world, 29517, height, stride, out), nprocs=world, join=True)
+    full = torch.load(out).view(height, stride)
+    assert torch.equal(full[:, 0], torch.tensor([y % 251 for y in range(height)], dtype=torch.uint8))
+    assert (full == full[:, :1]).all()

@@ -1,0 +1,53 @@
+"""Row-band partition of a frame over N devices and the gather of the bands on rank 0.
+
+This is the reference's own distributed partition (its TCP "network device"): server `id` of `count` renders the raster
+rows y with ((y >> 2) - id) % count == 0 into the compacted buffer row 4*((y >> 2) / count) + (y & 3)
+(devices/device_singleray/api/swapchain.h:57-70) and the client re-interleaves the returned rows
+(devices/device_network/network_device.cpp:235-310). device_cuda renders exactly those rows when created with
+cfg "serverID=id,serverCount=count"; here the bands travel device to device over torch.distributed (NCCL on GPUs,
+gloo in the CPU tests) instead of TCP. No reduction is involved: the bands are disjoint.
+"""
+from __future__ import annotations
+
+from typing import List, Optional
+
+import torch
+import torch.distributed as dist
+
+
+def active_rows(height: int, rank: int, world: int) -> List[int]:
+    """Raster rows rendered by `rank`, in buffer order (api/swapchain.h:57-60)."""
+    return [y for y in range(height) if ((y >> 2) - rank) % world == 0]
+
+
+def buffer_row(y: int, world: int) -> int:
+    """raster2buffer (api/swapchain.h:68-70)."""
+    return 4 * ((y >> 2) // world) + (y & 3)
+
+
+class BandGather:
+    """Gathers the compacted row bands of every rank into the full frame on rank 0."""
+
+    def __init__(self, height: int, stride_bytes: int, rank: int, world: int, device):
+        self.height, self.stride, self.rank, self.world, self.device = height, stride_bytes, rank, world, device
+        self.rows = [active_rows(height, r, world) for r in range(world)]
+        self.max_rows = max(len(r) for r in self.rows)
+        self.full: Optional[torch.Tensor] = None
+        if rank == 0:
+            self.full = torch.zeros(height * stride_bytes, dtype=torch.uint8, device=device)
+            self.index = [torch.tensor(r, dtype=torch.long, device=device) for r in self.rows]
+            self.parts = [torch.empty(self.max_rows * stride_bytes, dtype=torch.uint8, device=device) for _ in range(world)]
+
+    def gather(self, local: torch.Tensor) -> Optional[torch.Tensor]:
+        """`local`: this rank's framebuffer bytes (compacted rows first). Returns the full frame on rank 0."""
+        send = local[: self.max_rows * self.stride]
+        if self.world == 1:
+            self.full.view(self.height, self.stride).index_copy_(0, self.index[0], send[: len(self.rows[0]) * self.stride].view(-1, self.stride))
+            return self.full
+        dist.gather(send, self.parts if self.rank == 0 else None, dst=0)
+        if self.rank != 0:
+            return None
+        fv = self.full.view(self.height, self.stride)
+        for r in range(self.world):
+            fv.index_copy_(0, self.index[r], self.parts[r][: len(self.rows[r]) * self.stride].view(-1, self.stride))
+        return self.full

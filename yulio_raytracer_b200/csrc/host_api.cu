@@ -694,6 +694,20 @@ yrt_status yrtxSampleTable(yrt_device* dev, yrt_handle renderer, yrt_handle scen
     GUARD_S(sample_table(dev, cast<RendererHandle>(renderer, HK_RENDERER, "renderer"), scene ? cast<SceneHandle>(scene, HK_SCENE, "scene") : nullptr,
                          iteration, sets, spp, n1, n2, table))
 }
+yrt_status yrtxHostSampleTable(const char* filter, int spp, int sets, int maxDepth, int iteration, int* outSpp, int* n1, int* n2, float* table) {
+    try {
+        const std::string f(filter ? filter : "bspline");
+        const int kind = f == "none" ? FILTER_NONE : f == "box" ? FILTER_BOX : f == "bspline" ? FILTER_BSPLINE : -1;
+        if (kind < 0) throw std::runtime_error("unknown filter type: " + f);
+        if (spp < 1 || sets < 1 || maxDepth < 0) throw std::runtime_error("invalid sample table request");
+        PixelFilter pf; if (kind != FILTER_NONE) pf.init((FilterKind)kind);
+        const int a = maxDepth, b = 1 + maxDepth;                       // pathtraceintegrator.cpp:39-46
+        const SampleTable t = buildSampleTable(spp, sets, a, b, iteration, kind == FILTER_NONE ? nullptr : &pf);
+        if (outSpp) *outSpp = t.spp; if (n1) *n1 = a; if (n2) *n2 = b;
+        if (table) memcpy(table, t.rec.data(), t.rec.size() * sizeof(float));
+        return YRT_OK;
+    } catch (const std::exception& e) { g_lastError = e.what(); return YRT_ERROR; }
+}
 yrt_status yrtxFrameBufferDevice(yrt_device* dev, yrt_handle fb, void** devPtr, size_t* bytes, size_t* strideBytes) {
     GUARD_S(auto* f = cast<FrameBufferHandle>(fb, HK_FRAMEBUFFER, "framebuffer");
             if (devPtr) *devPtr = f->devPacked; if (bytes) *bytes = f->bytes(); if (strideBytes) *strideBytes = f->strideBytes)

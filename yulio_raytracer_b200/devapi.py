@@ -81,8 +81,26 @@ _OPTIONAL = {
     "yrtxSetReadback": (C.c_int, [C.c_int]),
 }
 
+_NODEV = {"yrtxHostSampleTable": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int] + [C.POINTER(C.c_int)] * 3 + [C.c_void_p])}
+
+
+def host_sample_table(libpath: str, filter: str, spp: int, sets: int, max_depth: int, iteration: int = 0):
+    """yrtxHostSampleTable of `libpath` (works without a GPU): returns (table[sets, spp_rounded, rec], n1, n2)."""
+    lib = C.CDLL(libpath, mode=C.RTLD_LOCAL)
+    fn = lib.yrtxHostSampleTable
+    fn.restype, fn.argtypes = _NODEV["yrtxHostSampleTable"]
+    lib.yrtGetLastError.restype = _P
+    o, a, b = C.c_int(0), C.c_int(0), C.c_int(0)
+    if fn(_b(filter), spp, sets, max_depth, iteration, C.byref(o), C.byref(a), C.byref(b), None) != 0:
+        raise RuntimeError(lib.yrtGetLastError().decode())
+    tab = np.zeros((sets, o.value, 5 + a.value + 2 * b.value), np.float32)
+    if fn(_b(filter), spp, sets, max_depth, iteration, C.byref(o), C.byref(a), C.byref(b), tab.ctypes.data) != 0:
+        raise RuntimeError(lib.yrtGetLastError().decode())
+    return tab, a.value, b.value
+
+
 #: every symbol include/yrt_device.h declares (checked by tests/test_cabi_exports.py)
-DECLARED_SYMBOLS = ["yrtCreateDevice", "yrtDestroyDevice", "yrtGetLastError"] + list(_SIGS) + list(_OPTIONAL)
+DECLARED_SYMBOLS = ["yrtCreateDevice", "yrtDestroyDevice", "yrtGetLastError"] + list(_SIGS) + list(_OPTIONAL) + list(_NODEV)
 
 
 def _b(s) -> Optional[bytes]:
