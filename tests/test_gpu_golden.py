@@ -260,3 +260,24 @@ def test_debug_renderer_id_image(cuda_dev, oracle_dev):
         d.rtRenderFrame(r, s.camera, s.scene, s.tonemapper, s.framebuffer, 0)
         imgs.append(d.read_framebuffer(s.framebuffer, "RGB8", 64, 48))
     assert np.array_equal(imgs[0], imgs[1])
+
+
+def test_plugin_boundary_with_a_reference_side_caller():
+    """lib/plugin_smoke only knows devices/device/device.h: it dlopens a back end, dlsym("create")s it as
+    Device::rtCreateDevice does (devices/device/device.cpp:24-35) and renders through the C++ virtual interface. The same
+    binary drives the CUDA plugin and the reference's CPU back end; the frames must agree."""
+    import subprocess
+    from oracle import oracle_device
+    from yulio_raytracer_b200.devapi import CUDA_LIB
+    libdir = os.path.dirname(CUDA_LIB)
+    exe, plugin = os.path.join(libdir, "plugin_smoke"), os.path.join(libdir, "libdevice_cuda.so")
+    if not (os.path.exists(exe) and os.path.exists(plugin)):
+        pytest.fail("adapter not built: run yulio_raytracer_b200/adapter/build_adapter.py where the reference is mounted")
+    means = []
+    for lib in (plugin, oracle_device.ORACLE_LIB):
+        out = subprocess.run([exe, lib, "64"], capture_output=True, text=True, timeout=120)
+        assert out.returncode == 0, out.stderr
+        line = [l for l in out.stdout.splitlines() if l.startswith("mean")][-1]
+        means.append(np.array([float(v) for v in line.split()[1:]]))
+    assert means[1].min() > 0.01
+    assert np.allclose(means[0], means[1], rtol=2e-3), means

@@ -101,3 +101,12 @@ def test_band_gather_world2_gloo(tmp_path):
     full = torch.load(out).view(height, stride)
     assert torch.equal(full[:, 0], torch.tensor([y % 251 for y in range(height)], dtype=torch.uint8))
     assert (full == full[:, :1]).all()
+
+
+def test_plugin_exports_reference_factory_symbol():
+    """libdevice_cuda.so is what Device::rtCreateDevice dlopens; it must export `create` (devices/device/device.cpp:24-35)."""
+    plugin = os.path.join(os.path.dirname(CUDA_LIB), "libdevice_cuda.so")
+    if not os.path.exists(plugin):
+        pytest.skip("adapter not built (needs the reference headers: yulio_raytracer_b200/adapter/build_adapter.py)")
+    lib = ctypes.CDLL(plugin)
+    assert hasattr(lib, "create")
