@@ -415,6 +415,10 @@ yrt_device* yrtCreateDevice(const char* parms, size_t numThreads, int threadsPri
         dev->gpu = gpu; dev->numSMs = prop.multiProcessorCount;
         YRT_CK(cudaSetDevice(gpu));
         YRT_CK(cudaStreamCreateWithFlags(&dev->stream, cudaStreamNonBlocking));
+        {   // keep freed scratch in the stream-ordered pool instead of returning it to the OS at every synchronisation
+            cudaMemPool_t pool; YRT_CK(cudaDeviceGetDefaultMemPool(&pool, gpu));
+            uint64_t keep = ~0ull; YRT_CK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+        }
         dev->chunkPaths = (uint32_t)cfg_int(cfg, "chunk", 1l << 22);
         if (dev->chunkPaths < 1024) dev->chunkPaths = 1024;
         dev->countStats = (int)cfg_int(cfg, "stats", 0);

@@ -97,7 +97,7 @@ static void image_upload(ImageObj& img, cudaStream_t s) {
 // ------------------------------------------------------------------------------------------------
 SceneHandle::~SceneHandle() { releaseDevice(); }
 void SceneHandle::releaseDevice() {
-    if (nodes) cudaFree(nodes); if (tris) cudaFree(tris);
+    if (nodes) cudaFreeAsync(nodes, nullptr); if (tris) cudaFreeAsync(tris, nullptr);   // allocated from the stream-ordered pool (bvh_build.cu)
     nodes = nullptr; tris = nullptr;
 }
 
@@ -166,6 +166,10 @@ void scene_commit(yrt_device* dev, SceneHandle* sc) {
     // depends on the slots, so an unchanged scene keeps its BVH unless cfg rebuild=1 asks for the reference's cost.
     if (sc->committed && !sc->dirty && !dev->alwaysRebuild) return;
     cudaStream_t st = dev->stream;
+    const auto tc0 = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) {
+        if (dev->verbose) printf("device_cuda: commit %-10s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tc0).count());
+    };
 
     std::vector<GeomRec> geoms; std::vector<float4> positions, normals; std::vector<float2> uvs; std::vector<int4> indices;
     std::vector<uint2> refs; std::vector<MaterialRec> materials; std::vector<LightRec> lights;
@@ -196,6 +200,11 @@ void scene_commit(yrt_device* dev, SceneHandle* sc) {
         return matIndex[m.get()] = (int)materials.size() - 1;
     };
 
+    {   // one pass to size the arrays: a rebuild per cube face must not pay for vector growth
+        size_t nv = 0, nt = 0;
+        for (const auto& p : sc->prims) if (p && p->shape) { nv += p->shape->type == MESH_TRIANGLE ? 3 : p->shape->position.size(); nt += p->shape->type == MESH_TRIANGLE ? 1 : p->shape->triangles.size(); }
+        positions.reserve(nv); normals.reserve(nv); uvs.reserve(nv); indices.reserve(nt); refs.reserve(nt); geoms.reserve(sc->prims.size());
+    }
     SceneData d{};
     d.numEnvLights = 0; d.numPrecomputed = 0;
     for (size_t slot = 0; slot < sc->prims.size(); slot++) {
@@ -262,16 +271,19 @@ void scene_commit(yrt_device* dev, SceneHandle* sc) {
         geoms.push_back(g);
     }
 
+    lap("flatten");
     sc->geoms.upload(geoms, st); sc->positions.upload(positions, st); sc->normals.upload(normals, st); sc->uvs.upload(uvs, st);
     sc->indices.upload(indices, st); sc->materials.upload(materials, st); sc->lights.upload(lights, st);
     sc->textures.upload(sc->hostTextures, st);
     DevBuf<uint2> dRefs; dRefs.upload(refs, st);
 
+    lap("upload");
     sc->releaseDevice();
     BvhBuildInput in{dRefs.p, (uint32_t)refs.size(), sc->geoms.p, sc->positions.p, sc->indices.p};
     BvhResult out{};
     build_bvh(in, out, st);
     YRT_CK(cudaStreamSynchronize(st));
+    lap("bvh");
     sc->nodes = out.nodes; sc->tris = out.tris; sc->buildMs = out.buildMs; sc->buildLaunches = out.launches; sc->rebuildCount++;
 
     d.nodes = sc->nodes; d.tris = sc->tris; d.numNodes = out.numNodes; d.numTris = out.numTris;
