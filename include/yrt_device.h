@@ -51,7 +51,7 @@ typedef int yrt_status;               /* 0 = ok */
 /* reference: Device::rtCreateDevice -> create(parms, numThreads, threadsPriority, rtcore_cfg)
  * (devices/device/device.cpp:24-48). `cfg` is the free-form "k=v,k=v" string the front end
  * passes as -rtcore (devices/renderer/renderer.cpp:922-937); keys understood:
- *   gpu=I (CUDA ordinal, default 0), chunk=P (paths per wavefront chunk, default 2^22), stats=1 (count node
+ *   gpu=I (CUDA ordinal, default 0), chunk=P (paths per wavefront chunk, default 2^26, clamped to 40 % of the free device memory), stats=1 (count node
  *   visits / triangle tests), timers=0|1 (per-stage CUDA events, default 1), rebuild=1 (rebuild the BVH on every
  *   scene commit like the reference does), serverID=I,serverCount=N (row-band interleave, see yrtSetInt1(NULL,..)),
  *   verbose=0|1.   numThreads / threadsPriority are accepted and ignored (no CPU workers). */

@@ -114,7 +114,7 @@ struct yrt_device {
     std::mutex mutex;                          // RT_COMMAND_HEADER (api/singleray_device.cpp:97)
     int gpu = 0; int numSMs = 148; cudaStream_t stream = nullptr;
     int serverID = 0, serverCount = 1;         // g_serverID / g_serverCount (api/singleray_device.cpp:109-110)
-    uint32_t chunkPaths = 1u << 22;
+    uint32_t chunkPaths = 1u << 26;      // paths per wavefront pass: whole faces where memory allows (launch tails dominate small chunks)
     int countStats = 0, verbose = 0, alwaysRebuild = 0, useTimers = 1;
     int tuneRefillMin = 8, tuneTriNum = 3, tuneTriDen = 1, tuneSimple = 0;   // cfg refill=,trinum=,triden= (bvh.cuh: TraceTune)
     bool readback = true;                      // copy the frame to the host buffer inside yrtRenderFrame (yrtxSetReadback)

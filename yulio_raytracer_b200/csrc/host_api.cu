@@ -419,7 +419,7 @@ yrt_device* yrtCreateDevice(const char* parms, size_t numThreads, int threadsPri
             cudaMemPool_t pool; YRT_CK(cudaDeviceGetDefaultMemPool(&pool, gpu));
             uint64_t keep = ~0ull; YRT_CK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
         }
-        dev->chunkPaths = (uint32_t)cfg_int(cfg, "chunk", 1l << 22);
+        dev->chunkPaths = (uint32_t)cfg_int(cfg, "chunk", 1l << 26);
         if (dev->chunkPaths < 1024) dev->chunkPaths = 1024;
         dev->countStats = (int)cfg_int(cfg, "stats", 0);
         dev->verbose = (int)cfg_int(cfg, "verbose", 0);

@@ -471,6 +471,7 @@ struct StatusRec { int state; float progress; };               // RendererStatus
 
 void render_frame(yrt_device* dev, RendererHandle* rh, CameraHandle* ch, SceneHandle* sc, ToneMapperHandle* th, FrameBufferHandle* fb, int accumulate) {
     const auto tHost0 = std::chrono::steady_clock::now();
+    auto hostLap = [&](const char* what) { if (dev->verbose >= 3) printf("  host %-10s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tHost0).count()); };
     if (!rh->inst) throw std::runtime_error("invalid renderer value");
     if (!ch->inst) throw std::runtime_error("invalid camera value");
     if (!th->inst) throw std::runtime_error("invalid tonemapper value");
@@ -508,13 +509,21 @@ void render_frame(yrt_device* dev, RendererHandle* rh, CameraHandle* ch, SceneHa
     uint64_t capacity = dev->chunkPaths;
     const uint64_t totalPaths = (uint64_t)numPixels * spp;
     if (capacity > totalPaths) capacity = totalPaths;
-    while (capacity * nl > (1ull << 28) && capacity > 65536) capacity >>= 1;
+    if (capacity > dev->wf.wb.capacity || capacity * nl > dev->wf.wb.shadowCapacity) {
+        // growing: 128 B of path state + 48 B per (path, light) shadow slot; stay within 40 % of what is free right now
+        size_t freeB = 0, totalB = 0; YRT_CK(cudaMemGetInfo(&freeB, &totalB));
+        const uint64_t have = (uint64_t)dev->wf.wb.capacity * 128ull + (uint64_t)dev->wf.wb.shadowCapacity * 48ull;   // already ours
+        const uint64_t budget = (uint64_t)(0.4 * (double)freeB) + have;
+        while (capacity * (128ull + 48ull * nl) > budget && capacity > 65536) capacity >>= 1;
+    }
+    while (capacity * nl > 0xfff00000ull && capacity > 65536) capacity >>= 1;          // 32-bit shadow-slot indices
     if (capacity < (uint64_t)spp) capacity = spp;
     const uint32_t pixelsPerChunk = (uint32_t)(capacity / spp);
     capacity = (uint64_t)pixelsPerChunk * spp;
     dev->wf.ensure((uint32_t)capacity, (uint32_t)(capacity * nl), numPixels);
     const WavefrontBuffers& wb = dev->wf.wb;
 
+    hostLap("setup");
     LaunchCfg lcTrace{dev->numSMs * 8, 128, st}, lcStream{dev->numSMs * 8, 256, st}, lcShade{dev->numSMs * 6, 128, st};
     FrameTimers& tm = dev->timers; tm.reset();
     const bool timers = dev->useTimers != 0;
@@ -568,6 +577,7 @@ void render_frame(yrt_device* dev, RendererHandle* rh, CameraHandle* ch, SceneHa
         }
     }
     YRT_CK(cudaEventRecord(evStop, st));
+    hostLap("enqueued");
     uint64_t d2h = 0;
     if (dev->readback) {
         YRT_CK(cudaMemcpyAsync(fb->host[fb->cur], fb->devPacked, fb->bytes(), cudaMemcpyDeviceToHost, st));
@@ -577,6 +587,7 @@ void render_frame(yrt_device* dev, RendererHandle* rh, CameraHandle* ch, SceneHa
     YRT_CK(cudaMemcpyAsync(hstats, wb.stats, sizeof(hstats), cudaMemcpyDeviceToHost, st));
     YRT_CK(cudaStreamSynchronize(st));
     YRT_CK(cudaGetLastError());
+    hostLap("synced");
 
     yrtx_frame_stats& S = dev->stats;
     float ms = 0.f; YRT_CK(cudaEventElapsedTime(&ms, evStart, evStop));
@@ -603,6 +614,7 @@ void render_frame(yrt_device* dev, RendererHandle* rh, CameraHandle* ch, SceneHa
     S.trace_ms = S.closest_ms + S.shadow_ms;
     S.h2d_bytes = fs.tableUploaded ? fs.tableBytes : 0; S.d2h_bytes = d2h;
     S.num_triangles = fc.scene.numTris; S.num_nodes = fc.scene.numNodes; S.build_ms = sc->buildMs; S.bvh_builds = sc->rebuildCount;
+    hostLap("stats");
     S.host_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tHost0).count();
     if (dev->verbose) {   // the reference's line (integratorrenderer.cpp:101-111), fed from CUDA events and device counters
         const double dt = ms * 1e-3;
