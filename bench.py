@@ -231,7 +231,7 @@ def main():
     for i in range(args.warmup):
         render_face(dev, s, cams[i % 12]); gather_bands()
     agg = {"rays": 0, "ms": 0.0, "closest_ms": 0.0, "shadow_ms": 0.0, "shade_ms": 0.0, "rf_ms": 0.0, "launches": 0, "closest_rays": 0,
-           "shadow_rays": 0, "closest_launches": 0, "shadow_launches": 0, "gather_ms": 0.0}
+           "shadow_rays": 0, "closest_launches": 0, "shadow_launches": 0, "gather_ms": 0.0, "sort_ms": 0.0}
     barrier()
     with ClockSampler(local_rank) as clocks:
         t_wall0 = time.perf_counter()
@@ -241,7 +241,7 @@ def main():
             st = dev.frame_stats()
             g = gather_bands()
             agg["rays"] += st.rays_closest + st.rays_shadow; agg["ms"] += st.render_ms + g; agg["gather_ms"] += g
-            agg["closest_ms"] += st.closest_ms; agg["shadow_ms"] += st.shadow_ms; agg["shade_ms"] += st.shade_ms; agg["rf_ms"] += st.raygen_film_ms
+            agg["closest_ms"] += st.closest_ms; agg["shadow_ms"] += st.shadow_ms; agg["shade_ms"] += st.shade_ms; agg["rf_ms"] += st.raygen_film_ms; agg["sort_ms"] += st.sort_ms
             agg["launches"] += st.kernel_launches; agg["closest_rays"] += st.rays_closest; agg["shadow_rays"] += st.rays_shadow
             agg["closest_launches"] += st.closest_launches; agg["shadow_launches"] += st.shadow_launches
         barrier()
@@ -304,7 +304,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": h2d // args.steps, "d2h_bytes_per_step": d2h // args.steps},
             "gpu_launches": int(launches_total), "clocks": clk, "roofline": roofline,
             "stage_ms_per_step": {"closest": agg["closest_ms"] / args.steps, "shadow": agg["shadow_ms"] / args.steps,
-                                  "shade": agg["shade_ms"] / args.steps, "raygen_film": agg["rf_ms"] / args.steps,
+                                  "shade": agg["shade_ms"] / args.steps, "raygen_film": agg["rf_ms"] / args.steps, "sort": agg["sort_ms"] / args.steps,
                                   "gather": agg["gather_ms"] / args.steps},
             "traversal": nbar, "rays_per_step": rays_total / args.steps, "wall_s_timed_region": wall_dev}
     if not args.no_cpu_baseline and world == 1:

@@ -54,6 +54,7 @@ typedef int yrt_status;               /* 0 = ok */
  *   gpu=I (CUDA ordinal, default 0), chunk=P (paths per wavefront chunk, default 2^26, clamped to 40 % of the free device memory), stats=1 (count node
  *   visits / triangle tests), timers=0|1 (per-stage CUDA events, default 1), rebuild=1 (rebuild the BVH on every
  *   scene commit like the reference does), serverID=I,serverCount=N (row-band interleave, see yrtSetInt1(NULL,..)),
+ *   sort=0|1 (re-order bounce queues by origin cell + direction octant; default 0: measured slower, profiles/README.md),
  *   verbose=0|1.   numThreads / threadsPriority are accepted and ignored (no CPU workers). */
 YRT_API yrt_device* yrtCreateDevice(const char* parms, size_t numThreads, int threadsPriority, const char* cfg);
 YRT_API void        yrtDestroyDevice(yrt_device* dev);                 /* reference: virtual ~Device, device.h:54 */
@@ -148,6 +149,7 @@ typedef struct yrtx_frame_stats {
     uint64_t shadow_launches;  /* number of any-hit traversal launches */
     uint64_t h2d_bytes;        /* host->device bytes moved by the last yrtRenderFrame (sample table, constants) */
     uint64_t d2h_bytes;        /* device->host bytes moved by the last yrtRenderFrame (the frame) */
+    double   sort_ms;          /* CUDA-event time of the ray-sort launches (key generation + radix sort) */
     uint64_t bvh_builds;       /* BVH builds since the scene handle was created (F8: commits that did not change geometry reuse it) */
 } yrtx_frame_stats;
 YRT_API yrt_status yrtxGetFrameStats(yrt_device*, yrtx_frame_stats* out);

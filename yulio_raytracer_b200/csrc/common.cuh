@@ -168,7 +168,8 @@ struct LightRec {
 };
 
 struct SceneData {
-    int tuneRefillMin, tuneTriNum, tuneTriDen, tuneSimple;   // traversal scheduling knobs (bvh.cuh: TraceTune)
+    int tuneRefillMin, tuneTriNum, tuneTriDen, tuneSimple;
+    V3 bboxLo, bboxRcpExtent;    // scene bounds (ray-sort keys): cell = (P - bboxLo) * bboxRcpExtent in [0,1]^3   // traversal scheduling knobs (bvh.cuh: TraceTune)
     // acceleration structure
     const void* nodes;           // BVH8 nodes, 80 B each (bvh.cuh)
     const float4* tris;          // 3 x float4 per triangle in leaf order (p0|geomID, p1|primID, p2|cull)

@@ -93,7 +93,7 @@ struct TableKey {                              // identity of the uploaded sampl
 };
 
 struct WavefrontStorage {
-    WavefrontBuffers wb{}; size_t pixelSetCapacity = 0;
+    WavefrontBuffers wb{}; size_t pixelSetCapacity = 0; void* sortTemp = nullptr; size_t sortTempBytes = 0;
     void ensure(uint32_t capacity, uint32_t shadowCapacity, size_t pixels);
     void release();
 };
@@ -116,7 +116,9 @@ struct yrt_device {
     int serverID = 0, serverCount = 1;         // g_serverID / g_serverCount (api/singleray_device.cpp:109-110)
     uint32_t chunkPaths = 1u << 26;      // paths per wavefront pass: whole faces where memory allows (launch tails dominate small chunks)
     int countStats = 0, verbose = 0, alwaysRebuild = 0, useTimers = 1;
-    int tuneRefillMin = 8, tuneTriNum = 3, tuneTriDen = 1, tuneSimple = 0;   // cfg refill=,trinum=,triden= (bvh.cuh: TraceTune)
+    int tuneRefillMin = 8, tuneTriNum = 3, tuneTriDen = 1, tuneSimple = 0;
+    int sortRays = 0; uint32_t sortMin = 1u << 16;   // cfg sort=0|1: re-order bounce queues of at least sortMin rays (sort.cu); measured slower, off
+    uint32_t* hostCounters = nullptr;          // pinned: queue lengths read back once per bounce   // cfg refill=,trinum=,triden= (bvh.cuh: TraceTune)
     bool readback = true;                      // copy the frame to the host buffer inside yrtRenderFrame (yrtxSetReadback)
     yrt::WavefrontStorage wf;
     yrt::FrameTimers timers;

@@ -37,6 +37,8 @@ struct WavefrontBuffers {
     uint32_t* counters;           // [0] |queueA|, [1] |queueB|, [2] shadow rays this bounce, [4]/[5]/[6] next unclaimed ray of the closest / any-hit / user traversal launch
     unsigned long long* stats;    // [0] closest rays, [1] shadow rays, [2] node visits, [3] triangle tests
     uint8_t* pixelSet;            // per pixel of the frame: sample set index
+    uint32_t* queueS;             // queue re-ordered by the ray sort (sort.cu)
+    uint32_t* sortKeys; uint32_t* sortKeysOut;   // sort keys (origin cell Morton code | direction octant)
 };
 
 struct FrameConst {               // everything a frame's kernels need, passed by value
@@ -73,6 +75,11 @@ void launch_film(const FrameConst& fc, const WavefrontBuffers& wb, const FilmPar
 // renderers/debugrenderer.cpp:66-148 (maxDepth 1): primary-hit ID image written straight into the framebuffer
 void launch_debug(const FrameConst& fc, const WavefrontBuffers& wb, const FilmParams& fp, uint32_t numPixels, LaunchCfg lc);
 void launch_export_primary(const FrameConst& fc, const WavefrontBuffers& wb, uint32_t pixelBegin, uint32_t numPixels, float* out, LaunchCfg lc);
+// ray sort (sort.cu): keys from the extension rays of queue `queueSel`, CUB radix sort of (key, path id) into wb.queueS
+void launch_sort_keys(const FrameConst& fc, const WavefrontBuffers& wb, int queueSel, uint32_t n, LaunchCfg lc);
+size_t sort_temp_bytes(uint32_t capacity);
+void sort_queue(const WavefrontBuffers& wb, int queueSel, uint32_t n, void* temp, size_t tempBytes, cudaStream_t stream);
+#define YRT_SORT_KEY_BITS 21
 // yrtxTraceRays: rays/hits on the device, 8 floats each
 void launch_trace_user(const SceneData& sc, const float* rays, float* hits, size_t n, int closest, int countStats,
                        unsigned long long* stats, uint32_t* workCounter, LaunchCfg lc);

@@ -429,6 +429,8 @@ yrt_device* yrtCreateDevice(const char* parms, size_t numThreads, int threadsPri
         dev->serverCount = (int)cfg_int(cfg, "serverCount", 1);
         dev->tuneRefillMin = (int)cfg_int(cfg, "refill", dev->tuneRefillMin);
         dev->tuneTriNum = (int)cfg_int(cfg, "trinum", dev->tuneTriNum); dev->tuneTriDen = (int)cfg_int(cfg, "triden", dev->tuneTriDen); dev->tuneSimple = cfg_int(cfg, "trav", 1) == 0;
+        dev->sortRays = (int)cfg_int(cfg, "sort", 0); dev->sortMin = (uint32_t)cfg_int(cfg, "sortmin", 1l << 16);
+        YRT_CK(cudaHostAlloc((void**)&dev->hostCounters, 16 * sizeof(uint32_t), cudaHostAllocDefault));
         if (dev->tuneRefillMin < 1) dev->tuneRefillMin = 1; if (dev->tuneRefillMin > 32) dev->tuneRefillMin = 32;
         dev->stats.num_gpus = 1;
         return dev;
@@ -440,6 +442,7 @@ void yrtDestroyDevice(yrt_device* dev) {
     cudaSetDevice(dev->gpu);
     cudaStreamSynchronize(dev->stream);
     dev->wf.release(); dev->timers.release(); dev->sampleTable.release();
+    if (dev->hostCounters) cudaFreeHost(dev->hostCounters);
     cudaStreamDestroy(dev->stream);
     delete dev;
 }

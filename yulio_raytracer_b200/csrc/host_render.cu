@@ -290,6 +290,17 @@ void scene_commit(yrt_device* dev, SceneHandle* sc) {
     d.geoms = sc->geoms.p; d.positions = sc->positions.p; d.normals = sc->normals.p; d.uvs = sc->uvs.p; d.indices = sc->indices.p;
     d.materials = sc->materials.p; d.textures = sc->textures.p; d.lights = sc->lights.p;
     d.numGeoms = (int)geoms.size(); d.numLights = (int)lights.size();
+    {   // scene bounds for the ray-sort keys
+        V3 lo(INFINITY), hi(-INFINITY);
+        for (const float4& q : positions) {
+            if (!(std::isfinite(q.x) && std::isfinite(q.y) && std::isfinite(q.z))) continue;
+            lo = V3(fminf(lo.x, q.x), fminf(lo.y, q.y), fminf(lo.z, q.z)); hi = V3(fmaxf(hi.x, q.x), fmaxf(hi.y, q.y), fmaxf(hi.z, q.z));
+        }
+        if (!(lo.x <= hi.x)) { lo = V3(0.f); hi = V3(1.f); }
+        sc->bboxLo = lo; sc->bboxHi = hi;
+        const V3 e = hi - lo;
+        d.bboxLo = lo; d.bboxRcpExtent = V3(e.x > 0.f ? 1.f / e.x : 0.f, e.y > 0.f ? 1.f / e.y : 0.f, e.z > 0.f ? 1.f / e.z : 0.f);
+    }
     sc->data = d; sc->committed = true; sc->dirty = false;
     dev->stats.build_ms = out.buildMs; dev->stats.num_triangles = out.numTris; dev->stats.num_nodes = out.numNodes;
     dev->stats.bvh_builds = sc->rebuildCount;
@@ -347,21 +358,24 @@ void WavefrontStorage::ensure(uint32_t capacity, uint32_t shadowCapacity, size_t
         dev_realloc(wb.rayO, capacity); dev_realloc(wb.rayD, capacity); dev_realloc(wb.hitA, capacity); dev_realloc(wb.hitB, capacity);
         dev_realloc(wb.thr, capacity); dev_realloc(wb.Lacc, capacity); dev_realloc(wb.medium, capacity);
         dev_realloc(wb.shadowSpan, capacity); dev_realloc(wb.queueA, capacity); dev_realloc(wb.queueB, capacity);
+        dev_realloc(wb.queueS, capacity); dev_realloc(wb.sortKeys, capacity); dev_realloc(wb.sortKeysOut, capacity);
+        if (sortTemp) cudaFree(sortTemp);
+        sortTempBytes = sort_temp_bytes(capacity); sortTemp = nullptr; YRT_CK(cudaMalloc(&sortTemp, sortTempBytes ? sortTempBytes : 1));
         wb.capacity = capacity;
     }
     if (shadowCapacity > wb.shadowCapacity) {
         dev_realloc(wb.shO, shadowCapacity); dev_realloc(wb.shD, shadowCapacity); dev_realloc(wb.shC, shadowCapacity);
         wb.shadowCapacity = shadowCapacity;
     }
-    if (!wb.counters) { dev_realloc(wb.counters, 8); YRT_CK(cudaMemset(wb.counters, 0, 8 * sizeof(uint32_t))); }
+    if (!wb.counters) { dev_realloc(wb.counters, 16); YRT_CK(cudaMemset(wb.counters, 0, 16 * sizeof(uint32_t))); }
     if (!wb.stats) { dev_realloc(wb.stats, 8); YRT_CK(cudaMemset(wb.stats, 0, 8 * sizeof(unsigned long long))); }
     if (pixels > pixelSetCapacity) { dev_realloc(wb.pixelSet, pixels); pixelSetCapacity = pixels; }
 }
 void WavefrontStorage::release() {
     void* ps[] = {wb.rayO, wb.rayD, wb.hitA, wb.hitB, wb.thr, wb.Lacc, wb.medium, wb.shadowSpan, wb.queueA, wb.queueB,
-                  wb.shO, wb.shD, wb.shC, wb.counters, wb.stats, wb.pixelSet};
+                  wb.shO, wb.shD, wb.shC, wb.counters, wb.stats, wb.pixelSet, wb.queueS, wb.sortKeys, wb.sortKeysOut, sortTemp};
     for (void* p : ps) if (p) cudaFree(p);
-    wb = WavefrontBuffers{}; pixelSetCapacity = 0;
+    wb = WavefrontBuffers{}; pixelSetCapacity = 0; sortTemp = nullptr; sortTempBytes = 0;
 }
 
 cudaEvent_t FrameTimers::get() {
@@ -372,7 +386,7 @@ void FrameTimers::begin(int kind, cudaStream_t s) { Span sp; sp.kind = kind; sp.
 void FrameTimers::end(cudaStream_t s) { Span& sp = spans.back(); sp.b = get(); YRT_CK(cudaEventRecord(sp.b, s)); }
 void FrameTimers::release() { for (auto e : pool) cudaEventDestroy(e); pool.clear(); used = 0; spans.clear(); }
 
-enum { TK_RAYGEN_FILM = 0, TK_CLOSEST = 1, TK_SHADE = 2, TK_SHADOW = 3 };
+enum { TK_RAYGEN_FILM = 0, TK_CLOSEST = 1, TK_SHADE = 2, TK_SHADOW = 3, TK_SORT = 4 };
 
 // ------------------------------------------------------------------------------------------------
 // per-frame setup shared by render_frame / primary_rays / sample_table
@@ -555,20 +569,35 @@ void render_frame(yrt_device* dev, RendererHandle* rh, CameraHandle* ch, SceneHa
             launch_raygen(fc, wb, (uint32_t)pixelBegin, np, lcStream); launches++;
             if (timers) tm.end(st);
             int q = 0;
-            for (int depth = 0; depth < fc.integ.maxDepth; depth++, q ^= 1) {
+            uint32_t alive = np * (uint32_t)spp;                 // length of the current queue, known on the host
+            for (int depth = 0; depth < fc.integ.maxDepth && alive; depth++, q ^= 1) {
+                // bounce queues are re-ordered by origin cell + direction octant (sort.cu); the sorted ids live in queueS
+                WavefrontBuffers wq = wb;
+                if (depth > 0 && dev->sortRays && alive >= dev->sortMin) {
+                    if (timers) tm.begin(TK_SORT, st);
+                    launch_sort_keys(fc, wb, q, alive, lcStream); launches++;
+                    sort_queue(wb, q, alive, dev->wf.sortTemp, dev->wf.sortTempBytes, st); launches += 4;
+                    if (timers) tm.end(st);
+                    (q ? wq.queueB : wq.queueA) = wb.queueS;
+                }
                 if (timers) tm.begin(TK_CLOSEST, st);
-                launch_trace_closest(fc, wb, q, lcTrace); launches++; closestLaunches++;
+                launch_trace_closest(fc, wq, q, lcTrace); launches++; closestLaunches++;
                 if (timers) { tm.end(st); tm.begin(TK_SHADE, st); }
-                launch_shade(fc, wb, q, (uint32_t)pixelBegin, depth, lcShade); launches++;
+                launch_shade(fc, wq, q, (uint32_t)pixelBegin, depth, lcShade); launches++;
                 if (timers) tm.end(st);
+                // queue lengths of the next bounce: one small read-back per bounce buys the early exit and the sort size
+                YRT_CK(cudaMemcpyAsync(dev->hostCounters, wb.counters, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+                cudaEvent_t evCnt = tm.get(); YRT_CK(cudaEventRecord(evCnt, st));
                 if (fc.scene.numLights > 0) {
                     if (timers) tm.begin(TK_SHADOW, st);
-                    launch_trace_shadow(fc, wb, lcTrace); launches++; shadowLaunches++;
+                    launch_trace_shadow(fc, wq, lcTrace); launches++; shadowLaunches++;
                     if (timers) { tm.end(st); tm.begin(TK_SHADE, st); }
                 }
                 else if (timers) tm.begin(TK_SHADE, st);
-                launch_resolve(fc, wb, q, lcStream); launches += 2;
+                launch_resolve(fc, wq, q, lcStream); launches += 2;
                 if (timers) tm.end(st);
+                YRT_CK(cudaEventSynchronize(evCnt));
+                alive = dev->hostCounters[q ^ 1];
             }
             if (timers) tm.begin(TK_RAYGEN_FILM, st);
             launch_film(fc, wb, fp, (uint32_t)pixelBegin, np, lcStream); launches++;
@@ -593,23 +622,21 @@ void render_frame(yrt_device* dev, RendererHandle* rh, CameraHandle* ch, SceneHa
     float ms = 0.f; YRT_CK(cudaEventElapsedTime(&ms, evStart, evStop));
     S.render_ms = ms; S.rays_closest = hstats[0]; S.rays_shadow = hstats[1]; S.node_visits = hstats[2]; S.tri_tests = hstats[3];
     S.kernel_launches = launches; S.closest_launches = closestLaunches; S.shadow_launches = shadowLaunches;
-    S.closest_ms = S.shadow_ms = S.shade_ms = S.raygen_film_ms = 0.0;
+    S.closest_ms = S.shadow_ms = S.shade_ms = S.raygen_film_ms = S.sort_ms = 0.0;
     for (const auto& sp : tm.spans) {
         if (!sp.b) continue;
         float t = 0.f; YRT_CK(cudaEventElapsedTime(&t, sp.a, sp.b));
         if (sp.kind == TK_CLOSEST) S.closest_ms += t; else if (sp.kind == TK_SHADOW) S.shadow_ms += t;
-        else if (sp.kind == TK_SHADE) S.shade_ms += t; else S.raygen_film_ms += t;
+        else if (sp.kind == TK_SHADE) S.shade_ms += t; else if (sp.kind == TK_SORT) S.sort_ms += t; else S.raygen_film_ms += t;
     }
-    if (dev->verbose >= 2) {   // stage times summed over the chunks, per position in the chunk's launch sequence
-        static const char* names[] = {"raygen/film", "closest", "shade", "shadow"};
-        const size_t perChunk = (size_t)(fc.scene.numLights > 0 ? 4 : 3) * fc.integ.maxDepth + 2;
-        std::vector<double> sum(perChunk, 0.0); std::vector<int> kind(perChunk, 0);
-        for (size_t i = 0; i < tm.spans.size(); i++) {
-            const auto& sp = tm.spans[i]; if (!sp.b) continue;
+    if (dev->verbose >= 2) {   // stage times in launch order (first 160 spans)
+        static const char* names[] = {"raygen/film", "closest", "shade", "shadow", "sort"};
+        size_t shown = 0;
+        for (const auto& sp : tm.spans) {
+            if (!sp.b || shown++ >= 160) break;
             float t = 0.f; cudaEventElapsedTime(&t, sp.a, sp.b);
-            sum[i % perChunk] += t; kind[i % perChunk] = sp.kind;
+            printf("  stage %3zu %-12s %9.3f ms\n", shown - 1, names[sp.kind], t);
         }
-        for (size_t i = 0; i < perChunk; i++) printf("  stage %2zu %-12s %9.3f ms\n", i, names[kind[i]], sum[i]);
     }
     S.trace_ms = S.closest_ms + S.shadow_ms;
     S.h2d_bytes = fs.tableUploaded ? fs.tableBytes : 0; S.d2h_bytes = d2h;

@@ -35,7 +35,7 @@ class FrameStats(C.Structure):
         ("num_gpus", C.c_uint32), ("reserved", C.c_uint32),
         ("closest_ms", C.c_double), ("shadow_ms", C.c_double), ("shade_ms", C.c_double), ("raygen_film_ms", C.c_double),
         ("closest_launches", C.c_uint64), ("shadow_launches", C.c_uint64),
-        ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("bvh_builds", C.c_uint64),
+        ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("sort_ms", C.c_double), ("bvh_builds", C.c_uint64),
     ]
 
 
