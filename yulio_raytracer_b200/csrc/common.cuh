@@ -180,6 +180,7 @@ struct SceneData {
     const MaterialRec* materials; const TextureRec* textures; const LightRec* lights;
     int numGeoms, numLights, numEnvLights, numPrecomputed;
     int envLightIdx[8];
+    int hasMedia;                // some material is a medium interface (Dielectric): path media must be tracked
 };
 
 struct IntegratorData {          // integrators/pathtraceintegrator.cpp:21-33

@@ -30,7 +30,7 @@ struct WavefrontBuffers {
     float4* thr;                  // throughput.rgb | (depth | flags << 16)
     float4* Lacc;                 // radiance accumulated along the path
     float4* medium;               // transmission.rgb | eta
-    uint2* shadowSpan;            // per path: (first shadow ray, count) of the current bounce
+    uint32_t* shadowPid;          // per group of numLights shadow slots: the path that owns it
     float4* shO; float4* shD;     // shadow ray queue
     float4* shC;                  // contribution.rgb | occluded flag (written by the any-hit kernel)
     uint32_t* queueA; uint32_t* queueB;

@@ -290,6 +290,7 @@ void scene_commit(yrt_device* dev, SceneHandle* sc) {
     d.geoms = sc->geoms.p; d.positions = sc->positions.p; d.normals = sc->normals.p; d.uvs = sc->uvs.p; d.indices = sc->indices.p;
     d.materials = sc->materials.p; d.textures = sc->textures.p; d.lights = sc->lights.p;
     d.numGeoms = (int)geoms.size(); d.numLights = (int)lights.size();
+    d.hasMedia = 0; for (const MaterialRec& m : materials) d.hasMedia |= m.isMediaInterface;
     {   // scene bounds for the ray-sort keys
         V3 lo(INFINITY), hi(-INFINITY);
         for (const float4& q : positions) {
@@ -357,7 +358,7 @@ void WavefrontStorage::ensure(uint32_t capacity, uint32_t shadowCapacity, size_t
     if (capacity > wb.capacity) {
         dev_realloc(wb.rayO, capacity); dev_realloc(wb.rayD, capacity); dev_realloc(wb.hitA, capacity); dev_realloc(wb.hitB, capacity);
         dev_realloc(wb.thr, capacity); dev_realloc(wb.Lacc, capacity); dev_realloc(wb.medium, capacity);
-        dev_realloc(wb.shadowSpan, capacity); dev_realloc(wb.queueA, capacity); dev_realloc(wb.queueB, capacity);
+        dev_realloc(wb.shadowPid, capacity); dev_realloc(wb.queueA, capacity); dev_realloc(wb.queueB, capacity);
         dev_realloc(wb.queueS, capacity); dev_realloc(wb.sortKeys, capacity); dev_realloc(wb.sortKeysOut, capacity);
         if (sortTemp) cudaFree(sortTemp);
         sortTempBytes = sort_temp_bytes(capacity); sortTemp = nullptr; YRT_CK(cudaMalloc(&sortTemp, sortTempBytes ? sortTempBytes : 1));
@@ -372,7 +373,7 @@ void WavefrontStorage::ensure(uint32_t capacity, uint32_t shadowCapacity, size_t
     if (pixels > pixelSetCapacity) { dev_realloc(wb.pixelSet, pixels); pixelSetCapacity = pixels; }
 }
 void WavefrontStorage::release() {
-    void* ps[] = {wb.rayO, wb.rayD, wb.hitA, wb.hitB, wb.thr, wb.Lacc, wb.medium, wb.shadowSpan, wb.queueA, wb.queueB,
+    void* ps[] = {wb.rayO, wb.rayD, wb.hitA, wb.hitB, wb.thr, wb.Lacc, wb.medium, wb.shadowPid, wb.queueA, wb.queueB,
                   wb.shO, wb.shD, wb.shC, wb.counters, wb.stats, wb.pixelSet, wb.queueS, wb.sortKeys, wb.sortKeysOut, sortTemp};
     for (void* p : ps) if (p) cudaFree(p);
     wb = WavefrontBuffers{}; pixelSetCapacity = 0; sortTemp = nullptr; sortTempBytes = 0;
@@ -555,6 +556,7 @@ void render_frame(yrt_device* dev, RendererHandle* rh, CameraHandle* ch, SceneHa
         launch_debug(fc, wb, fp, (uint32_t)numPixels, lcStream); launches++;
     } else if (numPixels) {
         launch_pixel_sets(fc, wb.pixelSet, fs.sets, lcStream); launches++;
+        if (fc.integ.maxDepth <= 0) YRT_CK(cudaMemsetAsync(wb.Lacc, 0, (size_t)capacity * sizeof(float4), st));   // no bounce writes the radiance
         std::vector<cudaEvent_t> chunkDone;
         size_t chunkIdx = 0;
         for (size_t pixelBegin = 0; pixelBegin < numPixels; pixelBegin += pixelsPerChunk, chunkIdx++) {

@@ -133,9 +133,7 @@ __global__ void __launch_bounds__(256) k_raygen(FrameConst fc, WavefrontBuffers 
         V3 org, dir; camera_ray(fc.camera, fx, fy, rec[3], rec[4], org, dir);
         wb.rayO[pid] = make_float4(org.x, org.y, org.z, 0.f);
         wb.rayD[pid] = make_float4(dir.x, dir.y, dir.z, INFINITY);
-        wb.thr[pid] = make_float4(1.f, 1.f, 1.f, __uint_as_float(FLAG_UNBENT << 16));
-        wb.Lacc[pid] = make_float4(0.f, 0.f, 0.f, 0.f);
-        wb.medium[pid] = make_float4(1.f, 1.f, 1.f, 1.f);
+        // throughput (1, unbent), radiance (0) and medium (vacuum) of a fresh path are implied: k_shade(depth 0) does not read them
         wb.queueA[pid] = pid;
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) { wb.counters[0] = numPaths; wb.counters[1] = 0; wb.counters[2] = 0; wb.counters[4] = 0; wb.counters[5] = 0; }
@@ -305,9 +303,14 @@ __global__ void __launch_bounds__(128) k_shade(FrameConst fc, WavefrontBuffers w
             pid = queue[i];
             const float4 o4 = wb.rayO[pid]; d4 = wb.rayD[pid];
             const float4 hA = wb.hitA[pid], hB = wb.hitB[pid];
-            const float4 t4 = wb.thr[pid]; m4 = wb.medium[pid];
-            thr = Col(t4.x, t4.y, t4.z); flags = __float_as_uint(t4.w) >> 16; hitT = hA.x;
-            const float4 L4 = wb.Lacc[pid]; Col L(L4.x, L4.y, L4.z);
+            Col L(0.f);
+            if (depth == 0) { thr = Col(1.f); flags = FLAG_UNBENT; }            // LightPath(ray): pathtraceintegrator.h:41-43
+            else {
+                const float4 t4 = wb.thr[pid]; thr = Col(t4.x, t4.y, t4.z); flags = __float_as_uint(t4.w) >> 16;
+                const float4 L4 = wb.Lacc[pid]; L = Col(L4.x, L4.y, L4.z);
+                if (sc.hasMedia) m4 = wb.medium[pid];                           // only Dielectric materials change the medium
+            }
+            hitT = hA.x;
             const PathCoord pc = path_coord(fc, pixelBegin, pid);
             rec = sample_rec(fc, wb.pixelSet, pc);
             fx = (float(pc.x) + rec[0]) * fc.rcpWidth; fy = (float(pc.y) + rec[1]) * fc.rcpHeight;
@@ -377,7 +380,7 @@ __global__ void __launch_bounds__(128) k_shade(FrameConst fc, WavefrontBuffers w
             wb.shC[slot] = make_float4(contrib.x, contrib.y, contrib.z, 1.f);
             shadowRays++;
         }
-        if (valid) wb.shadowSpan[pid] = make_uint2(base, nl);
+        if (nl) wb.shadowPid[base / nl] = pid;                // slots are claimed in groups of numLights: base is a multiple of nl
 
         // ---- path continuation (pathtraceintegrator.cpp:169-213)
         bool cont = false;
@@ -411,7 +414,7 @@ __global__ void __launch_bounds__(128) k_shade(FrameConst fc, WavefrontBuffers w
                     wb.rayO[pid] = make_float4(dg.P.x, dg.P.y, dg.P.z, dg.error * ig.epsilon);
                     wb.rayD[pid] = make_float4(smp.v.x, smp.v.y, smp.v.z, INFINITY);
                     wb.thr[pid] = make_float4(nthr.x, nthr.y, nthr.z, __uint_as_float(nflags << 16));
-                    wb.medium[pid] = m4;
+                    if (sc.hasMedia) wb.medium[pid] = m4;
                     if (reduce_max(nthr) < ig.minContribution) cont = false;     // loop-top test of the next bounce (:66)
                 }
             }
@@ -428,17 +431,15 @@ void launch_shade(const FrameConst& fc, const WavefrontBuffers& wb, int queueSel
     k_shade<<<lc.blocks, 128, 0, lc.stream>>>(fc, wb, queueSel, pixelBegin, depth);
 }
 
-// adds the unoccluded light contributions of this bounce in light order, then resets the counters
-__global__ void __launch_bounds__(256) k_resolve(WavefrontBuffers wb, int queueSel) {
-    const uint32_t* __restrict__ queue = queueSel ? wb.queueB : wb.queueA;
-    const uint32_t n = wb.counters[queueSel];
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const uint32_t pid = queue[i];
-        const uint2 span = wb.shadowSpan[pid];
-        if (!span.y) continue;
+// adds the unoccluded light contributions of this bounce in light order (one thread per path that sampled lights: its
+// numLights consecutive shadow slots), then the counters are reset
+__global__ void __launch_bounds__(256) k_resolve(WavefrontBuffers wb, uint32_t numLights) {
+    const uint32_t n = wb.counters[2] / numLights;
+    for (uint32_t g = blockIdx.x * blockDim.x + threadIdx.x; g < n; g += gridDim.x * blockDim.x) {
+        const uint32_t pid = wb.shadowPid[g];
         float4 L4 = wb.Lacc[pid]; Col L(L4.x, L4.y, L4.z);
-        for (uint32_t k = 0; k < span.y; k++) {
-            const uint32_t slot = span.x + k;
+        for (uint32_t k = 0; k < numLights; k++) {
+            const uint32_t slot = g * numLights + k;
             if (slot >= wb.shadowCapacity) break;
             const float4 c = wb.shC[slot];
             if (c.w == 0.f) L += Col(c.x, c.y, c.z);
@@ -448,7 +449,7 @@ __global__ void __launch_bounds__(256) k_resolve(WavefrontBuffers wb, int queueS
 }
 __global__ void k_reset_counters(WavefrontBuffers wb, int queueSel) { wb.counters[queueSel] = 0; wb.counters[2] = 0; wb.counters[4] = 0; wb.counters[5] = 0; }
 void launch_resolve(const FrameConst& fc, const WavefrontBuffers& wb, int queueSel, LaunchCfg lc) {
-    k_resolve<<<lc.blocks, 256, 0, lc.stream>>>(wb, queueSel);
+    if (fc.scene.numLights > 0) k_resolve<<<lc.blocks, 256, 0, lc.stream>>>(wb, (uint32_t)fc.scene.numLights);
     k_reset_counters<<<1, 1, 0, lc.stream>>>(wb, queueSel);
 }
 
