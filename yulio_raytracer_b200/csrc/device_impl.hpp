@@ -57,10 +57,16 @@ struct SceneHandle : Handle {
     std::vector<std::shared_ptr<ScenePrim>> prims;
     bool dirty = true;                         // prims changed since the last commit
     bool committed = false;
+    // Incremental commit (the per-cube-face billboard update, renderer.cpp:551-559, only moves vertices): a slot whose new
+    // primitive has the signature of the committed one is patched in place; anything else re-flattens the scene.
+    struct SlotLayout { const void* material = nullptr; int type = -1, geomID = -1, illumMask = 0, shadowMask = 0; bool hasLight = false, cull = false, allFinite = false;
+                        size_t nv = 0, nn = 0, nuv = 0, nt = 0; uint32_t vtxBase = 0, nrmBase = 0, uvBase = 0, idxBase = 0; };
+    std::vector<SlotLayout> layout; std::vector<size_t> patchSlots; bool structureDirty = true; uint32_t numRefs = 0;
+    std::vector<float4> hostPositions, hostNormals; std::vector<float2> hostUvs; std::vector<int4> hostIndices;
     // ---- committed (device) state
     SceneData data{};                          // pointers below
     DevBuf<GeomRec> geoms; DevBuf<float4> positions, normals; DevBuf<float2> uvs; DevBuf<int4> indices;
-    DevBuf<MaterialRec> materials; DevBuf<TextureRec> textures; DevBuf<LightRec> lights;
+    DevBuf<MaterialRec> materials; DevBuf<TextureRec> textures; DevBuf<LightRec> lights; DevBuf<uint2> refsBuf;
     void* nodes = nullptr; float4* tris = nullptr;
     std::vector<std::shared_ptr<ImageObj>> imagesInUse;   // keeps device pixel storage alive
     std::vector<std::shared_ptr<ImageObj>> extraImages;   // images addressable by FrameConst (backplate) appended lazily
@@ -117,6 +123,7 @@ struct yrt_device {
     uint32_t chunkPaths = 1u << 26;      // paths per wavefront pass: whole faces where memory allows (launch tails dominate small chunks)
     int countStats = 0, verbose = 0, alwaysRebuild = 0, useTimers = 1;
     int tuneRefillMin = 8, tuneTriNum = 3, tuneTriDen = 1, tuneSimple = 0;
+    int shadeCtas = 6, traceCtas = 8;
     int sortRays = 0; uint32_t sortMin = 1u << 16;   // cfg sort=0|1: re-order bounce queues of at least sortMin rays (sort.cu); measured slower, off
     uint32_t* hostCounters = nullptr;          // pinned: queue lengths read back once per bounce   // cfg refill=,trinum=,triden= (bvh.cuh: TraceTune)
     bool readback = true;                      // copy the frame to the host buffer inside yrtRenderFrame (yrtxSetReadback)

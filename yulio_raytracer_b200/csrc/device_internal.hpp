@@ -62,6 +62,9 @@ struct FilmParams {
     float gamma, rcpGamma; int vignetting;
 };
 
+#ifndef YRT_SHADE_MINBLOCKS
+#define YRT_SHADE_MINBLOCKS 6
+#endif
 struct LaunchCfg { int blocks; int threads; cudaStream_t stream; };
 
 // pixels [pixelBegin, pixelBegin+numPixels) of the *active-row* enumeration of the frame

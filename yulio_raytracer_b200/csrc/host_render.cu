@@ -138,9 +138,9 @@ static std::shared_ptr<LightObj> transform_light(const std::shared_ptr<LightObj>
 
 void scene_set_primitive(yrt_device* dev, SceneHandle* sc, size_t slot, PrimHandle* prim, const Aff3* overrideXfm) {
     (void)dev;
-    if (slot >= sc->prims.size()) sc->prims.resize(slot + 1);
+    if (slot >= sc->prims.size()) { sc->prims.resize(slot + 1); sc->structureDirty = true; }
     sc->dirty = true;
-    if (!prim) { sc->prims[slot] = nullptr; return; }
+    if (!prim) { sc->prims[slot] = nullptr; sc->structureDirty = true; return; }
     const Aff3 xfm = overrideXfm ? *overrideXfm : prim->transform;
     auto sp = std::make_shared<ScenePrim>();
     std::shared_ptr<ShapeObj> shape = prim->shape ? prim->shape->inst : nullptr;
@@ -158,6 +158,53 @@ void scene_set_primitive(yrt_device* dev, SceneHandle* sc, size_t slot, PrimHand
     sp->material = prim->material ? prim->material->inst : nullptr;
     sp->illumMask = prim->illumMask; sp->shadowMask = prim->shadowMask;
     sc->prims[slot] = sp;
+    sc->patchSlots.push_back(slot);
+}
+
+// scene bounds for the ray-sort keys (sort.cu)
+static void scene_bounds(SceneHandle* sc) {
+    V3 lo(INFINITY), hi(-INFINITY);
+    for (const float4& q : sc->hostPositions) {
+        if (!(std::isfinite(q.x) && std::isfinite(q.y) && std::isfinite(q.z))) continue;
+        lo = V3(fminf(lo.x, q.x), fminf(lo.y, q.y), fminf(lo.z, q.z)); hi = V3(fmaxf(hi.x, q.x), fmaxf(hi.y, q.y), fmaxf(hi.z, q.z));
+    }
+    if (!(lo.x <= hi.x)) { lo = V3(0.f); hi = V3(1.f); }
+    sc->bboxLo = lo; sc->bboxHi = hi;
+    const V3 e = hi - lo;
+    sc->data.bboxLo = lo; sc->data.bboxRcpExtent = V3(e.x > 0.f ? 1.f / e.x : 0.f, e.y > 0.f ? 1.f / e.y : 0.f, e.z > 0.f ? 1.f / e.z : 0.f);
+}
+
+static bool slot_matches(const SceneHandle::SlotLayout& L, const ScenePrim& p) {
+    if (!p.shape || p.light || L.hasLight || L.geomID < 0 || !L.allFinite) return false;
+    const ShapeObj& s = *p.shape;
+    if (s.type != L.type || s.type == MESH_TRIANGLE || p.material.get() != L.material || s.cullBackFaces != L.cull) return false;
+    if (p.illumMask != L.illumMask || p.shadowMask != L.shadowMask) return false;
+    if (s.position.size() != L.nv || s.normal.size() != L.nn || s.texcoord.size() != L.nuv || s.triangles.size() != L.nt) return false;
+    for (const V3& q : s.position) if (!(std::isfinite(q.x) && std::isfinite(q.y) && std::isfinite(q.z))) return false;
+    return true;
+}
+
+// Vertices of the patched slots are rewritten in the committed arrays and only the BVH is rebuilt. Returns false when a
+// slot changed more than its vertex data (then the caller re-flattens everything).
+static bool scene_patch(yrt_device* dev, SceneHandle* sc) {
+    if (!sc->committed || sc->structureDirty || sc->layout.size() != sc->prims.size()) return false;
+    for (size_t slot : sc->patchSlots) {
+        if (slot >= sc->prims.size() || !sc->prims[slot] || !slot_matches(sc->layout[slot], *sc->prims[slot])) return false;
+        const SceneHandle::SlotLayout& L = sc->layout[slot];
+        const ShapeObj& s = *sc->prims[slot]->shape;      // same index list and texture coordinates as committed?
+        if (L.nt && memcmp(s.triangles.data(), &sc->hostIndices[L.idxBase], L.nt * sizeof(int4)) != 0) return false;
+        if (L.nuv && memcmp(s.texcoord.data(), &sc->hostUvs[L.uvBase], L.nuv * sizeof(float2)) != 0) return false;
+    }
+    cudaStream_t st = dev->stream;
+    for (size_t slot : sc->patchSlots) {
+        const SceneHandle::SlotLayout& L = sc->layout[slot];
+        const ShapeObj& s = *sc->prims[slot]->shape;
+        for (size_t i = 0; i < L.nv; i++) { const V3& q = s.position[i]; sc->hostPositions[L.vtxBase + i] = make_float4(q.x, q.y, q.z, 0.f); }
+        for (size_t i = 0; i < L.nn; i++) { const V3& q = s.normal[i]; sc->hostNormals[L.nrmBase + i] = make_float4(q.x, q.y, q.z, 0.f); }
+        if (L.nv) YRT_CK(cudaMemcpyAsync(sc->positions.p + L.vtxBase, &sc->hostPositions[L.vtxBase], L.nv * sizeof(float4), cudaMemcpyHostToDevice, st));
+        if (L.nn) YRT_CK(cudaMemcpyAsync(sc->normals.p + L.nrmBase, &sc->hostNormals[L.nrmBase], L.nn * sizeof(float4), cudaMemcpyHostToDevice, st));
+    }
+    return true;
 }
 
 void scene_commit(yrt_device* dev, SceneHandle* sc) {
@@ -171,7 +218,27 @@ void scene_commit(yrt_device* dev, SceneHandle* sc) {
         if (dev->verbose) printf("device_cuda: commit %-10s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tc0).count());
     };
 
-    std::vector<GeomRec> geoms; std::vector<float4> positions, normals; std::vector<float2> uvs; std::vector<int4> indices;
+    if (scene_patch(dev, sc)) {                                // vertices of a few slots moved: rebuild the BVH over the patched arrays
+        lap("patch");
+        sc->patchSlots.clear();
+        sc->releaseDevice();
+        BvhBuildInput in{sc->refsBuf.p, sc->numRefs, sc->geoms.p, sc->positions.p, sc->indices.p};
+        BvhResult out{};
+        build_bvh(in, out, st);
+        lap("bvh");
+        sc->nodes = out.nodes; sc->tris = out.tris; sc->buildMs = out.buildMs; sc->buildLaunches = out.launches; sc->rebuildCount++;
+        sc->data.nodes = sc->nodes; sc->data.tris = sc->tris; sc->data.numNodes = out.numNodes; sc->data.numTris = out.numTris;
+        if (dev->sortRays) scene_bounds(sc);
+        sc->dirty = false;
+        dev->stats.build_ms = out.buildMs; dev->stats.num_triangles = out.numTris; dev->stats.num_nodes = out.numNodes; dev->stats.bvh_builds = sc->rebuildCount;
+        if (dev->verbose) printf("device_cuda: BVH8 rebuild (patched) %u triangles -> %u nodes, %.3f ms\n", out.numTris, out.numNodes, out.buildMs);
+        return;
+    }
+    sc->patchSlots.clear(); sc->structureDirty = false;
+    std::vector<GeomRec> geoms; std::vector<float4>& positions = sc->hostPositions; std::vector<float4>& normals = sc->hostNormals;
+    std::vector<float2>& uvs = sc->hostUvs; std::vector<int4>& indices = sc->hostIndices;
+    positions.clear(); normals.clear(); uvs.clear(); indices.clear();
+    sc->layout.assign(sc->prims.size(), SceneHandle::SlotLayout());
     std::vector<uint2> refs; std::vector<MaterialRec> materials; std::vector<LightRec> lights;
     std::map<const MaterialObj*, int> matIndex; std::map<const TextureObj*, int> texIndex;
     sc->hostTextures.clear(); sc->imagesInUse.clear(); sc->hdri.clear(); sc->geomOfSlot.assign(sc->prims.size(), -1);
@@ -243,6 +310,7 @@ void scene_commit(yrt_device* dev, SceneHandle* sc) {
         const ShapeObj& s = *p->shape;
         GeomRec g; memset(&g, 0, sizeof(g));
         const int geomID = (int)geoms.size();
+        const size_t refsBefore = refs.size();
         sc->geomOfSlot[slot] = geomID;
         g.type = s.type; g.material = material_index(p->material); g.areaLight = lightIdx;
         g.cull = s.cullBackFaces ? 1 : 0; g.illumMask = p->illumMask; g.shadowMask = p->shadowMask;
@@ -269,13 +337,19 @@ void scene_commit(yrt_device* dev, SceneHandle* sc) {
             }
         }
         geoms.push_back(g);
+        SceneHandle::SlotLayout& L = sc->layout[slot];
+        L.material = p->material.get(); L.type = s.type; L.geomID = geomID; L.illumMask = p->illumMask; L.shadowMask = p->shadowMask;
+        L.hasLight = (bool)p->light; L.cull = s.cullBackFaces; L.vtxBase = g.vtxBase; L.nrmBase = g.nrmBase; L.uvBase = g.uvBase; L.idxBase = g.idxBase;
+        if (s.type != MESH_TRIANGLE) { L.nv = s.position.size(); L.nn = s.normal.size(); L.nuv = s.texcoord.size(); L.nt = s.triangles.size(); }
+        L.allFinite = s.type != MESH_TRIANGLE && refs.size() - refsBefore == s.triangles.size();
     }
 
     lap("flatten");
     sc->geoms.upload(geoms, st); sc->positions.upload(positions, st); sc->normals.upload(normals, st); sc->uvs.upload(uvs, st);
     sc->indices.upload(indices, st); sc->materials.upload(materials, st); sc->lights.upload(lights, st);
     sc->textures.upload(sc->hostTextures, st);
-    DevBuf<uint2> dRefs; dRefs.upload(refs, st);
+    DevBuf<uint2>& dRefs = sc->refsBuf; dRefs.upload(refs, st);      // kept across commits: no cudaMalloc/cudaFree per cube face
+    sc->numRefs = (uint32_t)refs.size();
 
     lap("upload");
     sc->releaseDevice();
@@ -291,20 +365,12 @@ void scene_commit(yrt_device* dev, SceneHandle* sc) {
     d.materials = sc->materials.p; d.textures = sc->textures.p; d.lights = sc->lights.p;
     d.numGeoms = (int)geoms.size(); d.numLights = (int)lights.size();
     d.hasMedia = 0; for (const MaterialRec& m : materials) d.hasMedia |= m.isMediaInterface;
-    {   // scene bounds for the ray-sort keys
-        V3 lo(INFINITY), hi(-INFINITY);
-        for (const float4& q : positions) {
-            if (!(std::isfinite(q.x) && std::isfinite(q.y) && std::isfinite(q.z))) continue;
-            lo = V3(fminf(lo.x, q.x), fminf(lo.y, q.y), fminf(lo.z, q.z)); hi = V3(fmaxf(hi.x, q.x), fmaxf(hi.y, q.y), fmaxf(hi.z, q.z));
-        }
-        if (!(lo.x <= hi.x)) { lo = V3(0.f); hi = V3(1.f); }
-        sc->bboxLo = lo; sc->bboxHi = hi;
-        const V3 e = hi - lo;
-        d.bboxLo = lo; d.bboxRcpExtent = V3(e.x > 0.f ? 1.f / e.x : 0.f, e.y > 0.f ? 1.f / e.y : 0.f, e.z > 0.f ? 1.f / e.z : 0.f);
-    }
-    sc->data = d; sc->committed = true; sc->dirty = false;
+    sc->data = d;
+    scene_bounds(sc);
+    sc->committed = true; sc->dirty = false;
     dev->stats.build_ms = out.buildMs; dev->stats.num_triangles = out.numTris; dev->stats.num_nodes = out.numNodes;
     dev->stats.bvh_builds = sc->rebuildCount;
+    lap("done");
     if (dev->verbose) printf("device_cuda: BVH8 build %u triangles -> %u nodes, %.3f ms\n", out.numTris, out.numNodes, out.buildMs);
 }
 
@@ -539,7 +605,7 @@ void render_frame(yrt_device* dev, RendererHandle* rh, CameraHandle* ch, SceneHa
     const WavefrontBuffers& wb = dev->wf.wb;
 
     hostLap("setup");
-    LaunchCfg lcTrace{dev->numSMs * 8, 128, st}, lcStream{dev->numSMs * 8, 256, st}, lcShade{dev->numSMs * 6, 128, st};
+    LaunchCfg lcTrace{dev->numSMs * dev->traceCtas, 128, st}, lcStream{dev->numSMs * 8, 256, st}, lcShade{dev->numSMs * dev->shadeCtas, 128, st};
     FrameTimers& tm = dev->timers; tm.reset();
     const bool timers = dev->useTimers != 0;
     uint64_t launches = 0, closestLaunches = 0, shadowLaunches = 0;

@@ -88,10 +88,28 @@ YRT_D void post_intersect(const SceneData& sc, V3 org, V3 dir, float t, float u,
 
 enum LobeKind { LOBE_LAMBERTIAN, LOBE_TRANSMISSION, LOBE_SPECULAR, LOBE_REFLECTION, LOBE_DIEL_REFL, LOBE_DIEL_TRANS,
                 LOBE_THIN_DIEL_TRANS, LOBE_CONST_DIEL_TRANS, LOBE_MICROFACET_UBER };
-struct Lobe { int kind; uint32_t type; Col c; float a, b, d; };   // meaning of c,a,b,d depends on kind
-struct Lobes { Lobe l[4]; int n; };
-YRT_D void add_lobe(Lobes& L, int kind, uint32_t type, Col c, float a = 0.f, float b = 0.f, float d = 0.f) {
-    if (L.n < 4) { Lobe& o = L.l[L.n++]; o.kind = kind; o.type = type; o.c = c; o.a = a; o.b = b; o.d = d; }
+struct Lobe { int kind; uint32_t type; Col c; float a, b; };   // meaning of c,a,b depends on kind
+// The lobes of one hit and the per-lobe candidates of CompositedBRDF::sample are indexed per lane at run time. As local arrays
+// they cost uncoalesced local-memory traffic (ncu r1: 2.7 of 32 bytes used per sector); they live in shared memory instead, word
+// w of slot i of thread t at s[(i * WORDS + w) * stride + t]: bank = t, conflict-free for any per-lane i.
+#define YRT_MAX_LOBES 3
+#define YRT_LOBE_WORDS 7
+#define YRT_CAND_WORDS 9
+struct Lobes {
+    float* s; float* cand; int stride; int n;
+    YRT_D Lobe get(int i) const {
+        const float* p = s + i * YRT_LOBE_WORDS * stride; Lobe l;
+        l.kind = __float_as_int(p[0]); l.type = __float_as_uint(p[stride]); l.c = Col(p[2 * stride], p[3 * stride], p[4 * stride]); l.a = p[5 * stride]; l.b = p[6 * stride];
+        return l;
+    }
+    YRT_D uint32_t type(int i) const { return __float_as_uint(s[(i * YRT_LOBE_WORDS + 1) * stride]); }
+};
+YRT_D void add_lobe(Lobes& L, int kind, uint32_t type, Col c, float a = 0.f, float b = 0.f) {
+    if (L.n < YRT_MAX_LOBES) {
+        float* p = L.s + L.n * YRT_LOBE_WORDS * L.stride; L.n++;
+        p[0] = __int_as_float(kind); p[L.stride] = __uint_as_float(type); p[2 * L.stride] = c.x; p[3 * L.stride] = c.y; p[4 * L.stride] = c.z;
+        p[5 * L.stride] = a; p[6 * L.stride] = b;
+    }
 }
 
 struct Sample3 { V3 v; float pdf; };
@@ -124,15 +142,15 @@ YRT_D Sample3 refract_v(V3 V, V3 N, float eta, float cosi, float& cost) {
 YRT_D Sample3 cosine_sample_hemisphere(float u, float v, V3 N) {
     const float phi = YRT_TWO_PI * u;
     const float cosTheta = sqrtf(v), sinTheta = sqrtf(1.0f - v);
-    Sample3 s; s.v = xfmVector(frame(N), V3(cosf(phi) * sinTheta, sinf(phi) * sinTheta, cosTheta)); s.pdf = cosTheta * YRT_ONE_OVER_PI;
+    Sample3 s; s.v = xfmVector(frame(N), V3(YRT_COSF(phi) * sinTheta, YRT_SINF(phi) * sinTheta, cosTheta)); s.pdf = cosTheta * YRT_ONE_OVER_PI;
     return s;
 }
 YRT_D Sample3 power_cosine_sample_hemisphere(float u, float v, V3 N, float e) {
     const float phi = YRT_TWO_PI * u;
-    const float cosTheta = powf(v, rcpf(e + 1));
+    const float cosTheta = YRT_POWF(v, rcpf(e + 1));
     const float sinTheta = sqrtf(rmax(0.f, 1.f - cosTheta * cosTheta));
-    Sample3 s; s.v = xfmVector(frame(N), V3(cosf(phi) * sinTheta, sinf(phi) * sinTheta, cosTheta));
-    s.pdf = (e + 1.0f) * powf(cosTheta, e) * YRT_ONE_OVER_TWO_PI;
+    Sample3 s; s.v = xfmVector(frame(N), V3(YRT_COSF(phi) * sinTheta, YRT_SINF(phi) * sinTheta, cosTheta));
+    s.pdf = (e + 1.0f) * YRT_POWF(cosTheta, e) * YRT_ONE_OVER_TWO_PI;
     return s;
 }
 
@@ -145,7 +163,7 @@ YRT_D Col lobe_eval(const Lobe& l, V3 wo, const DG& dg, V3 wi) {
     case LOBE_SPECULAR: {
         const V3 r = reflect_v(wo, dg.Ns);
         if (dot(r, wi) < 0) return Col(0.f);
-        return l.c * (l.a + 2) * (1.0f / (2.0f * YRT_PI)) * powf(dot(r, wi), l.a) * rclamp(dot(wi, dg.Ns));
+        return l.c * (l.a + 2) * (1.0f / (2.0f * YRT_PI)) * YRT_POWF(dot(r, wi), l.a) * rclamp(dot(wi, dg.Ns));
     }
     case LOBE_REFLECTION: return l.c;
     case LOBE_MICROFACET_UBER: {
@@ -155,7 +173,7 @@ YRT_D Col lobe_eval(const Lobe& l, V3 wo, const DG& dg, V3 wi) {
         const V3 wh = normalize(wi + wo);
         const float cosThetaH = dot(wh, dg.Ns), cosTheta = dot(wi, wh);
         const Col F = Col(fresnel_diel(cosTheta, l.a));                               // l.a = etai/etat
-        const float D = ((l.b + 2) * YRT_ONE_OVER_TWO_PI) * powf(fabsf(dot(wh, dg.Ns)), l.b);   // l.b = n
+        const float D = ((l.b + 2) * YRT_ONE_OVER_TWO_PI) * YRT_POWF(fabsf(dot(wh, dg.Ns)), l.b);   // l.b = n
         const float G = rmin(rmin(1.0f, 2.0f * cosThetaH * cosThetaO * rcpf(cosTheta)), 2.0f * cosThetaH * cosThetaI * rcpf(cosTheta));
         return l.c * D * G * F * rcpf(4.0f * cosThetaO);
     }
@@ -201,11 +219,11 @@ YRT_D Col lobe_sample(const Lobe& l, V3 wo, const DG& dg, Sample3& wi, float sx,
         if (dot(wo, dg.Ns) <= 0.0f) return Col(0.f);
         // PowerCosineDistribution::sample  power_cosine_distribution.h:43-51
         const float phi = YRT_TWO_PI * sx;
-        const float cosPhi = cosf(phi), sinPhi = sinf(phi);
-        const float cosTheta = powf(sy, rcpf(l.b + 1));
+        const float cosPhi = YRT_COSF(phi), sinPhi = YRT_SINF(phi);
+        const float cosTheta = YRT_POWF(sy, rcpf(l.b + 1));
         const float sinTheta = sqrtf(rmax(0.f, 1.f - cosTheta * cosTheta));
         const V3 wh = xfmVector(frame(dg.Ns), V3(cosPhi * sinTheta, sinPhi * sinTheta, cosTheta));
-        const float whPdf = ((l.b + 1) * YRT_ONE_OVER_TWO_PI) * powf(cosTheta, l.b);
+        const float whPdf = ((l.b + 1) * YRT_ONE_OVER_TWO_PI) * YRT_POWF(cosTheta, l.b);
         wi.v = reflect_v(wo, wh); wi.pdf = whPdf * rcpf(4.0f * fabsf(dot(wo, wh)));
         if (dot(wi.v, dg.Ns) <= 0.0f) return Col(0.f);
         return lobe_eval(l, wo, dg, wi.v);
@@ -218,31 +236,40 @@ YRT_D Col lobe_sample(const Lobe& l, V3 wo, const DG& dg, Sample3& wi, float sx,
 // CompositedBRDF::eval  brdfs/compositedbrdf.h:74-80
 YRT_D Col lobes_eval(const Lobes& L, V3 wo, const DG& dg, V3 wi, uint32_t typeMask) {
     Col c(0.f);
-    for (int i = 0; i < L.n; i++) if (L.l[i].type & typeMask) c += lobe_eval(L.l[i], wo, dg, wi);
+#pragma unroll 1
+    for (int i = 0; i < L.n; i++) { const Lobe l = L.get(i); if (l.type & typeMask) c += lobe_eval(l, wo, dg, wi); }
     return c;
 }
 
 // CompositedBRDF::sample  brdfs/compositedbrdf.h:119-181
 YRT_D Col lobes_sample(const Lobes& L, V3 wo, const DG& dg, Sample3& wiOut, uint32_t& typeOut, float sx, float sy, float ss, uint32_t typeMask) {
-    float f[4]; float sum = 0.0f;
-    Col colors[4]; Sample3 samples[4]; uint32_t types[4]; int num = 0;
+    float sum = 0.0f; int num = 0;
+    const int st = L.stride;
+#pragma unroll 1
     for (int i = 0; i < L.n; i++) {
-        if (!(L.l[i].type & typeMask)) continue;
-        Sample3 wi; const Col c = lobe_sample(L.l[i], wo, dg, wi, sx, sy);
+        const Lobe l = L.get(i);
+        if (!(l.type & typeMask)) continue;
+        Sample3 wi; const Col c = lobe_sample(l, wo, dg, wi, sx, sy);
         if (c == Col(0.f) || wi.pdf <= 0.0f) continue;
-        sum += f[num] = (c.x + c.y + c.z) * rcpf(wi.pdf);
-        colors[num] = c; samples[num] = wi; types[num] = L.l[i].type; num++;
+        const float f = (c.x + c.y + c.z) * rcpf(wi.pdf);
+        sum += f;
+        float* q = L.cand + num * YRT_CAND_WORDS * st; num++;
+        q[0] = f; q[st] = c.x; q[2 * st] = c.y; q[3 * st] = c.z; q[4 * st] = wi.v.x; q[5 * st] = wi.v.y; q[6 * st] = wi.v.z; q[7 * st] = wi.pdf;
+        q[8 * st] = __uint_as_float(l.type);
     }
     if (num == 0) { wiOut.v = V3(0.f); wiOut.pdf = 0.f; typeOut = 0; return Col(0.f); }
-    for (int i = 0; i < num; i++) f[i] /= sum;
-    float d[4];
-    d[0] = f[0];
-    for (int i = 1; i < num - 1; i++) d[i] = d[i - 1] + f[i];
-    d[num - 1] = 1.0f;
-    int i = 0; while (i < num - 1 && ss > d[i]) i++;
-    wiOut.v = samples[i].v; wiOut.pdf = samples[i].pdf * f[i];
-    typeOut = types[i];
-    return colors[i];
+    // f[i] /= sum; d[0] = f[0]; d[i] = d[i-1] + f[i]; d[num-1] = 1; first i with ss <= d[i]
+    int i = 0; float d = 0.f, fi = 0.f;
+#pragma unroll 1
+    for (;; i++) {
+        fi = L.cand[i * YRT_CAND_WORDS * st] / sum;
+        d = (i == 0) ? fi : d + fi;
+        if (i >= num - 1 || !(ss > d)) break;
+    }
+    const float* q = L.cand + i * YRT_CAND_WORDS * st;
+    wiOut.v = V3(q[4 * st], q[5 * st], q[6 * st]); wiOut.pdf = q[7 * st] * fi;
+    typeOut = __float_as_uint(q[8 * st]);
+    return Col(q[st], q[2 * st], q[3 * st]);
 }
 
 // ---- materials ----------------------------------------------------------------------------------
@@ -367,10 +394,10 @@ YRT_D Col light_sample(const LightRec& l, const DG& dg, LightSampleD& ls, float 
     case LIGHT_DISTANT: {
         // uniformSampleCone(u,v,angle,N)  shapesampler.h
         const float phi = YRT_TWO_PI * sx;
-        const float cosTheta = 1.0f - sy * (1.0f - cosf(l.a));
+        const float cosTheta = 1.0f - sy * (1.0f - YRT_COSF(l.a));
         const float sinTheta = sqrtf(rmax(0.f, 1.f - cosTheta * cosTheta));
-        ls.wi = xfmVector(frame(l.v0), V3(cosf(phi) * sinTheta, sinf(phi) * sinTheta, cosTheta));
-        ls.pdf = rcpf(4.0f * YRT_PI * (sinf(0.5f * l.a) * sinf(0.5f * l.a)));
+        ls.wi = xfmVector(frame(l.v0), V3(YRT_COSF(phi) * sinTheta, YRT_SINF(phi) * sinTheta, cosTheta));
+        ls.pdf = rcpf(4.0f * YRT_PI * (YRT_SINF(0.5f * l.a) * YRT_SINF(0.5f * l.a)));
         ls.tMax = INFINITY; return l.L;
     }
     }
