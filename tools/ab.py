@@ -19,6 +19,8 @@ for spec in sys.argv[4:]:
         st = dev.frame_stats()
         if i == 0: continue
         for k in ("render_ms", "closest_ms", "shadow_ms", "shade_ms", "raygen_film_ms"): acc[k] = acc.get(k, 0.0) + getattr(st, k) / faces
+        acc["build_ms"] = st.build_ms
         acc["rays"] = acc.get("rays", 0) + (st.rays_closest + st.rays_shadow) / faces
+        if st.node_visits: acc["nodes/ray"] = st.node_visits / (st.rays_closest + st.rays_shadow); acc["tris/ray"] = st.tri_tests / (st.rays_closest + st.rays_shadow)
     print(f"{spec:28s} " + " ".join(f"{k}={v:9.3f}" for k, v in acc.items() if k != "rays") + f" Mrays/s={acc['rays'] / acc['render_ms'] / 1e3:8.1f}", flush=True)
     dev.close()

@@ -26,7 +26,9 @@ static_assert(sizeof(Node8) == 80, "Node8 must be 80 bytes");
 
 #define YRT_TRI_FLAG_CULL 1u
 #define YRT_STACK_SIZE 96
+#ifndef YRT_BOX_PAD
 #define YRT_BOX_PAD 9.5367431640625e-07f     // 2^-20
+#endif
 
 struct HitRec { float t, u, v; int geomID, primID; V3 Ng; };
 
@@ -77,6 +79,10 @@ YRT_D RayPre ray_prepare(V3 O, V3 D) {
     return r;
 }
 
+// Tried and dropped (round 1, C3 stand-in): folding the 2^23 bias into the FMA constant (fma(2^23 + q, s, o - 2^23 s)) saves the
+// 48 FADDs per node but rounds the constant at half a quantisation step; padding for it (+0.51 step) cost +16 % node visits, and
+// even the 2^15-step-bias variant (byte in mantissa bits 8..15, +1/256 step of padding) cost +7 % — bounce rays start exactly on
+// box planes of neighbouring axis-aligned geometry, so any extra dilation flips many far-plane-vs-tnear decisions. Net slower.
 YRT_D float byte_to_float(uint32_t packed, int i) {     // exact u8 -> float without I2F
     return __uint_as_float(__byte_perm(packed, 0x4B000000u, 0x7650 + i)) - 8388608.0f;
 }

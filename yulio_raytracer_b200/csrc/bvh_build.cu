@@ -5,14 +5,19 @@
 //   1. k_tri_bounds      triangle AABBs + scene bounds (warp-reduced atomics)
 //   2. k_morton          63-bit Morton code of the AABB centre (21 bits per axis)
 //   3. cub::DeviceRadixSort::SortPairs (key = Morton code, value = triangle reference index)
-//   4. k_lbvh_topology   Karras 2012: one thread per internal node, index-augmented keys
-//   5. k_lbvh_fit        bottom-up AABB fit with one atomic visit counter per internal node
+//   4. binary hierarchy over the Morton-ordered triangles, one of
+//      PLOC (default)    Meister & Bittner 2018, parallel locally-ordered clustering: every cluster looks R positions to either
+//                        side for the neighbour with the smallest merged surface area, mutual nearest neighbours merge, the
+//                        cluster array is compacted (CUB exclusive scan), repeat until one cluster is left; the last <= 1024
+//                        clusters are finished by one CTA in shared memory
+//      LBVH (cfg bvh=0)  Karras 2012 topology (k_lbvh_topology) + bottom-up AABB fit (k_lbvh_fit)
 //   6. k_collapse        level-synchronous top-down collapse of the binary tree into 8-wide nodes
 //                        (largest-surface-area child opened first, subtrees of <= 3 triangles become
 //                        leaf children), greedy octant slot assignment, conservative 8-bit plane
 //                        quantisation, triangles written in leaf order (48 B each)
 // CUB is used as a library primitive for the radix sort only (ships with the CUDA toolkit).
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
 #include <cstdio>
 #include <stdexcept>
 #include <string>
@@ -100,12 +105,25 @@ __device__ __forceinline__ int delta(const uint64_t* __restrict__ keys, int n, i
     return __clzll((long long)(a ^ b));
 }
 
-struct Lbvh {
-    uint32_t* left; uint32_t* right; uint32_t* parent;      // per internal node (parent also per leaf at [n-1 + leaf])
-    uint32_t* rangeFirst; uint32_t* rangeLast;              // per internal node: sorted range covered
+struct Lbvh {                                               // the binary tree both builders produce
+    uint32_t* left; uint32_t* right; uint32_t* count;       // per internal node: children references, triangles below
     float4* lo; float4* hi;                                 // per internal node
-    uint32_t* visit;
+    const float4* leafLo; const float4* leafHi;             // per leaf, by sorted position
+    uint32_t* parent; uint32_t* visit;                      // LBVH only (parent also per leaf at [n-1 + leaf])
 };
+
+__global__ void k_ploc_init(uint32_t n, uint32_t* __restrict__ cid) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) cid[i] = 0x80000000u | i;
+}
+
+__global__ void k_gather_leaf_boxes(const uint32_t* __restrict__ sortedIdx, uint32_t n, const float4* __restrict__ boxLo, const float4* __restrict__ boxHi,
+                                    float4* __restrict__ leafLo, float4* __restrict__ leafHi) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t s = sortedIdx[i];
+    leafLo[i] = boxLo[s]; leafHi[i] = boxHi[s];
+}
 
 __global__ void k_lbvh_topology(const uint64_t* __restrict__ keys, int n, Lbvh t) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -128,14 +146,13 @@ __global__ void k_lbvh_topology(const uint64_t* __restrict__ keys, int n, Lbvh t
     const int first = min(i, j), last = max(i, j);
     const uint32_t L = (first == gamma) ? (LEAF_FLAG | (uint32_t)gamma) : (uint32_t)gamma;
     const uint32_t R = (last == gamma + 1) ? (LEAF_FLAG | (uint32_t)(gamma + 1)) : (uint32_t)(gamma + 1);
-    t.left[i] = L; t.right[i] = R; t.rangeFirst[i] = first; t.rangeLast[i] = last;
+    t.left[i] = L; t.right[i] = R; t.count[i] = (uint32_t)(last - first + 1);
     if (L & LEAF_FLAG) t.parent[(n - 1) + gamma] = i; else t.parent[gamma] = i;
     if (R & LEAF_FLAG) t.parent[(n - 1) + gamma + 1] = i; else t.parent[gamma + 1] = i;
     if (i == 0) t.parent[0] = 0xffffffffu;
 }
 
-__global__ void k_lbvh_fit(int n, Lbvh t, const uint32_t* __restrict__ sortedIdx,
-                           const float4* __restrict__ boxLo, const float4* __restrict__ boxHi) {
+__global__ void k_lbvh_fit(int n, Lbvh t) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     uint32_t node = t.parent[(n - 1) + i];
@@ -144,9 +161,9 @@ __global__ void k_lbvh_fit(int n, Lbvh t, const uint32_t* __restrict__ sortedIdx
         __threadfence();
         const uint32_t L = t.left[node], R = t.right[node];
         float4 llo, lhi, rlo, rhi;
-        if (L & LEAF_FLAG) { const uint32_t s = sortedIdx[L & ~LEAF_FLAG]; llo = boxLo[s]; lhi = boxHi[s]; }
+        if (L & LEAF_FLAG) { llo = t.leafLo[L & ~LEAF_FLAG]; lhi = t.leafHi[L & ~LEAF_FLAG]; }
         else { llo = __ldcg(&t.lo[L]); lhi = __ldcg(&t.hi[L]); }
-        if (R & LEAF_FLAG) { const uint32_t s = sortedIdx[R & ~LEAF_FLAG]; rlo = boxLo[s]; rhi = boxHi[s]; }
+        if (R & LEAF_FLAG) { rlo = t.leafLo[R & ~LEAF_FLAG]; rhi = t.leafHi[R & ~LEAF_FLAG]; }
         else { rlo = __ldcg(&t.lo[R]); rhi = __ldcg(&t.hi[R]); }
         t.lo[node] = make_float4(fminf(llo.x, rlo.x), fminf(llo.y, rlo.y), fminf(llo.z, rlo.z), 0.f);
         t.hi[node] = make_float4(fmaxf(lhi.x, rhi.x), fmaxf(lhi.y, rhi.y), fmaxf(lhi.z, rhi.z), 0.f);
@@ -155,10 +172,137 @@ __global__ void k_lbvh_fit(int n, Lbvh t, const uint32_t* __restrict__ sortedIdx
     }
 }
 
+// ---- PLOC (parallel locally-ordered clustering) ---------------------------------------------------
+// Cluster i of an iteration = (node reference, box) at position i of a compact, Morton-ordered array.
+#define PLOC_BLOCK 256
+#define PLOC_MAX_RADIUS 32
+#define PLOC_FINAL 1024          // cluster count at which one CTA finishes the tree in shared memory
+
+__device__ __forceinline__ float union_area(const float4 alo, const float4 ahi, const float4 blo, const float4 bhi) {
+    const float dx = fmaxf(ahi.x, bhi.x) - fminf(alo.x, blo.x), dy = fmaxf(ahi.y, bhi.y) - fminf(alo.y, blo.y), dz = fmaxf(ahi.z, bhi.z) - fminf(alo.z, blo.z);
+    return dx * dy + dy * dz + dz * dx;
+}
+
+// nearest neighbour within +-radius positions: minimum merged surface area, ties to the smaller position (then the pair with the
+// globally smallest area is always mutual, so every iteration merges at least one pair)
+__global__ void __launch_bounds__(PLOC_BLOCK) k_ploc_nn(const float4* __restrict__ lo, const float4* __restrict__ hi, uint32_t m, int radius, uint32_t* __restrict__ nn) {
+    __shared__ float4 sLo[PLOC_BLOCK + 2 * PLOC_MAX_RADIUS], sHi[PLOC_BLOCK + 2 * PLOC_MAX_RADIUS];
+    const int base = (int)(blockIdx.x * PLOC_BLOCK) - radius;
+    for (int k = threadIdx.x; k < PLOC_BLOCK + 2 * radius; k += PLOC_BLOCK) {
+        const int g = base + k;
+        if (g >= 0 && g < (int)m) { sLo[k] = lo[g]; sHi[k] = hi[g]; }
+    }
+    __syncthreads();
+    const int i = (int)(blockIdx.x * PLOC_BLOCK + threadIdx.x);
+    if (i >= (int)m) return;
+    const float4 alo = sLo[threadIdx.x + radius], ahi = sHi[threadIdx.x + radius];
+    float best = INFINITY; int bj = -1;
+    for (int d = -radius; d <= radius; d++) {
+        const int j = i + d;
+        if (d == 0 || j < 0 || j >= (int)m) continue;
+        const float a = union_area(alo, ahi, sLo[threadIdx.x + radius + d], sHi[threadIdx.x + radius + d]);
+        if (a < best) { best = a; bj = j; }
+    }
+    nn[i] = (uint32_t)bj;
+}
+
+// mutual pairs merge into a new internal node that takes the lower position; flags mark surviving positions
+__global__ void __launch_bounds__(PLOC_BLOCK) k_ploc_merge(uint32_t m, const uint32_t* __restrict__ nn, const uint32_t* __restrict__ cid,
+                                                           const float4* __restrict__ lo, const float4* __restrict__ hi, Lbvh t, uint32_t* __restrict__ nodeCounter,
+                                                           uint32_t* __restrict__ cidTmp, float4* __restrict__ loTmp, float4* __restrict__ hiTmp, uint32_t* __restrict__ flags) {
+    const uint32_t i = blockIdx.x * PLOC_BLOCK + threadIdx.x;
+    if (i >= m) return;
+    const uint32_t j = nn[i];
+    uint32_t id = cid[i]; float4 l = lo[i], h = hi[i]; uint32_t keep = 1u;
+    if (j < m && nn[j] == i) {
+        if (i < j) {
+            const uint32_t other = cid[j]; const float4 ol = lo[j], oh = hi[j];
+            const uint32_t node = atomicAdd(nodeCounter, 1u);
+            t.left[node] = id; t.right[node] = other;
+            t.count[node] = ((id & LEAF_FLAG) ? 1u : t.count[id]) + ((other & LEAF_FLAG) ? 1u : t.count[other]);
+            l = make_float4(fminf(l.x, ol.x), fminf(l.y, ol.y), fminf(l.z, ol.z), 0.f);
+            h = make_float4(fmaxf(h.x, oh.x), fmaxf(h.y, oh.y), fmaxf(h.z, oh.z), 0.f);
+            t.lo[node] = l; t.hi[node] = h;
+            id = node;
+        } else keep = 0u;
+    }
+    cidTmp[i] = id; loTmp[i] = l; hiTmp[i] = h; flags[i] = keep;
+}
+
+__global__ void __launch_bounds__(PLOC_BLOCK) k_ploc_compact(uint32_t m, const uint32_t* __restrict__ flags, const uint32_t* __restrict__ offsets,
+                                                             const uint32_t* __restrict__ cidTmp, const float4* __restrict__ loTmp, const float4* __restrict__ hiTmp,
+                                                             uint32_t* __restrict__ cid, float4* __restrict__ lo, float4* __restrict__ hi, uint32_t* __restrict__ mOut) {
+    const uint32_t i = blockIdx.x * PLOC_BLOCK + threadIdx.x;
+    if (i >= m) return;
+    if (flags[i]) { const uint32_t o = offsets[i]; cid[o] = cidTmp[i]; lo[o] = loTmp[i]; hi[o] = hiTmp[i]; }
+    if (i == m - 1) *mOut = offsets[i] + flags[i];
+}
+
+// the last m <= PLOC_FINAL clusters: the same iteration, in one CTA, until the root is left (rootOut = its reference)
+__global__ void __launch_bounds__(PLOC_FINAL) k_ploc_final(uint32_t m, int radius, const uint32_t* __restrict__ cid, const float4* __restrict__ lo, const float4* __restrict__ hi,
+                                                           Lbvh t, uint32_t* __restrict__ nodeCounter, uint32_t* __restrict__ rootOut) {
+    __shared__ float4 sLo[PLOC_FINAL], sHi[PLOC_FINAL];
+    __shared__ uint32_t sId[PLOC_FINAL], sNn[PLOC_FINAL], sWarp[32], sTotal;
+    const uint32_t i = threadIdx.x, lane = i & 31u, warp = i >> 5;
+    if (i < m) { sLo[i] = lo[i]; sHi[i] = hi[i]; sId[i] = cid[i]; }
+    __syncthreads();
+    while (m > 1) {
+        if (i < m) {
+            const float4 alo = sLo[i], ahi = sHi[i];
+            float best = INFINITY; int bj = -1;
+            for (int d = -radius; d <= radius; d++) {
+                const int j = (int)i + d;
+                if (d == 0 || j < 0 || j >= (int)m) continue;
+                const float a = union_area(alo, ahi, sLo[j], sHi[j]);
+                if (a < best) { best = a; bj = j; }
+            }
+            sNn[i] = (uint32_t)bj;
+        }
+        __syncthreads();
+        uint32_t id = 0, keep = 0; float4 l = make_float4(0, 0, 0, 0), h = l;
+        if (i < m) {
+            const uint32_t j = sNn[i];
+            id = sId[i]; l = sLo[i]; h = sHi[i]; keep = 1u;
+            if (j < m && sNn[j] == i) {
+                if (i < j) {
+                    const uint32_t other = sId[j]; const float4 ol = sLo[j], oh = sHi[j];
+                    const uint32_t node = atomicAdd(nodeCounter, 1u);
+                    t.left[node] = id; t.right[node] = other;
+                    t.count[node] = ((id & LEAF_FLAG) ? 1u : t.count[id]) + ((other & LEAF_FLAG) ? 1u : t.count[other]);
+                    l = make_float4(fminf(l.x, ol.x), fminf(l.y, ol.y), fminf(l.z, ol.z), 0.f);
+                    h = make_float4(fmaxf(h.x, oh.x), fmaxf(h.y, oh.y), fmaxf(h.z, oh.z), 0.f);
+                    t.lo[node] = l; t.hi[node] = h;
+                    id = node;
+                } else keep = 0u;
+            }
+        }
+        // block-wide exclusive scan of keep
+        uint32_t incl = keep;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= (uint32_t)o) incl += v; }
+        if (lane == 31) sWarp[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            uint32_t w = sWarp[lane], wi = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, wi, o); if (lane >= (uint32_t)o) wi += v; }
+            sWarp[lane] = wi - w;
+            if (lane == 31) sTotal = wi;
+        }
+        __syncthreads();
+        const uint32_t pos = sWarp[warp] + incl - keep, total = sTotal;      // every read of this round's clusters happened before the barriers above
+        if (keep) { sId[pos] = id; sLo[pos] = l; sHi[pos] = h; }
+        __threadfence_block();
+        __syncthreads();
+        m = total;
+    }
+    if (i == 0) *rootOut = sId[0];
+}
+
 // ---- collapse to compressed BVH8 -------------------------------------------------------------
 struct CollapseArgs {
     Lbvh t; int n;
-    const uint32_t* sortedIdx; const float4* boxLo; const float4* boxHi;
+    const uint32_t* sortedIdx;
     const uint2* refs; const GeomRec* geoms; const float4* positions; const int4* indices;
     Node8* nodes; float4* tris;
     uint32_t* counters;          // [0] node counter, [1] triangle counter, [2] next-level task count
@@ -167,15 +311,21 @@ struct CollapseArgs {
 
 __device__ __forceinline__ void ref_box(const CollapseArgs& a, uint32_t ref, float lo[3], float hi[3]) {
     float4 l, h;
-    if (ref & LEAF_FLAG) { const uint32_t s = a.sortedIdx[ref & ~LEAF_FLAG]; l = a.boxLo[s]; h = a.boxHi[s]; }
+    if (ref & LEAF_FLAG) { l = a.t.leafLo[ref & ~LEAF_FLAG]; h = a.t.leafHi[ref & ~LEAF_FLAG]; }
     else { l = a.t.lo[ref]; h = a.t.hi[ref]; }
     lo[0] = l.x; lo[1] = l.y; lo[2] = l.z; hi[0] = h.x; hi[1] = h.y; hi[2] = h.z;
 }
-__device__ __forceinline__ uint32_t ref_count(const CollapseArgs& a, uint32_t ref) {
-    return (ref & LEAF_FLAG) ? 1u : (a.t.rangeLast[ref] - a.t.rangeFirst[ref] + 1u);
-}
-__device__ __forceinline__ uint32_t ref_first(const CollapseArgs& a, uint32_t ref) {
-    return (ref & LEAF_FLAG) ? (ref & ~LEAF_FLAG) : a.t.rangeFirst[ref];
+__device__ __forceinline__ uint32_t ref_count(const CollapseArgs& a, uint32_t ref) { return (ref & LEAF_FLAG) ? 1u : a.t.count[ref]; }
+// sorted positions of the (<= 3) triangles below `ref`, left to right
+__device__ __forceinline__ uint32_t ref_leaves(const CollapseArgs& a, uint32_t ref, uint32_t out[3]) {
+    uint32_t stack[3]; int sp = 0; uint32_t n = 0;
+    stack[sp++] = ref;
+    while (sp > 0 && n < 3u) {
+        const uint32_t r = stack[--sp];
+        if (r & LEAF_FLAG) out[n++] = r & ~LEAF_FLAG;
+        else { stack[sp++] = a.t.right[r]; if (sp < 3) stack[sp++] = a.t.left[r]; }
+    }
+    return n;
 }
 
 __device__ void write_triangle(const CollapseArgs& a, uint32_t sortedPos, uint32_t outIdx) {
@@ -299,8 +449,8 @@ __global__ void k_collapse(CollapseArgs a) {
         } else {
             const uint32_t unary = cnt == 1 ? 1u : (cnt == 2 ? 3u : 7u);
             nd.meta[s] = (uint8_t)((unary << 5) | triOfs);
-            const uint32_t first = ref_first(a, r);
-            for (uint32_t k = 0; k < cnt; k++) write_triangle(a, first + k, triBase + triOfs + k);
+            uint32_t leaves[3]; const uint32_t nl = ref_leaves(a, r, leaves);
+            for (uint32_t k = 0; k < nl; k++) write_triangle(a, leaves[k], triBase + triOfs + k);
             triOfs += cnt;
         }
     }
@@ -337,16 +487,52 @@ void build_bvh(const BvhBuildInput& in, BvhResult& out, cudaStream_t stream) {
     CK(cub::DeviceRadixSort::SortPairs(tmp, tmpBytes, keys, keysSorted, vals, sortedIdx, (int)n, 0, 63, stream));
     out.launches += 8;   // CUB onesweep passes (library kernels, not counted as ours elsewhere)
 
-    Lbvh t;
+    Lbvh t{};
     const uint32_t ni = n > 1 ? n - 1 : 1;
-    t.left = dalloc<uint32_t>(ni); t.right = dalloc<uint32_t>(ni); t.parent = dalloc<uint32_t>((size_t)ni + n);
-    t.rangeFirst = dalloc<uint32_t>(ni); t.rangeLast = dalloc<uint32_t>(ni);
-    t.lo = dalloc<float4>(ni); t.hi = dalloc<float4>(ni); t.visit = dalloc<uint32_t>(ni);
-    CK(cudaMemsetAsync(t.visit, 0, ni * sizeof(uint32_t), stream));
-    if (n > 1) {
+    float4* leafLo = dalloc<float4>(n); float4* leafHi = dalloc<float4>(n);
+    k_gather_leaf_boxes<<<G, B, 0, stream>>>(sortedIdx, n, boxLo, boxHi, leafLo, leafHi); out.launches++;
+    dfree(boxLo); dfree(boxHi); boxLo = boxHi = nullptr;      // stream-ordered: reusable by the allocations below
+    t.left = dalloc<uint32_t>(ni); t.right = dalloc<uint32_t>(ni); t.count = dalloc<uint32_t>(ni);
+    t.lo = dalloc<float4>(ni); t.hi = dalloc<float4>(ni); t.leafLo = leafLo; t.leafHi = leafHi;
+    uint32_t rootRef = n > 1 ? 0u : (LEAF_FLAG | 0u);
+    if (n > 1 && !in.ploc) {
+        t.parent = dalloc<uint32_t>((size_t)ni + n); t.visit = dalloc<uint32_t>(ni);
+        CK(cudaMemsetAsync(t.visit, 0, ni * sizeof(uint32_t), stream));
         k_lbvh_topology<<<(n - 1 + B - 1) / B, B, 0, stream>>>(keysSorted, (int)n, t);
-        k_lbvh_fit<<<G, B, 0, stream>>>((int)n, t, sortedIdx, boxLo, boxHi);
+        k_lbvh_fit<<<G, B, 0, stream>>>((int)n, t);
         out.launches += 2;
+    } else if (n > 1) {
+        // cluster arrays: (reference, box) by position; [0] = current, [1] = merge output before compaction
+        const int radius = in.plocRadius < 1 ? 1 : (in.plocRadius > PLOC_MAX_RADIUS ? PLOC_MAX_RADIUS : in.plocRadius);
+        uint32_t* cid[2] = {dalloc<uint32_t>(n), dalloc<uint32_t>(n)};
+        float4* clo[2] = {dalloc<float4>(n), dalloc<float4>(n)}; float4* chi[2] = {dalloc<float4>(n), dalloc<float4>(n)};
+        uint32_t* nn = dalloc<uint32_t>(n); uint32_t* flags = dalloc<uint32_t>(n); uint32_t* offsets = dalloc<uint32_t>(n);
+        uint32_t* pc = dalloc<uint32_t>(4);                        // [0] node counter, [1] cluster count, [2] root reference
+        CK(cudaMemsetAsync(pc, 0, 4 * sizeof(uint32_t), stream));
+        size_t scanBytes = 0; CK(cub::DeviceScan::ExclusiveSum(nullptr, scanBytes, flags, offsets, (int)n, stream));
+        void* scanTmp = dalloc<char>(scanBytes);
+        k_ploc_init<<<G, B, 0, stream>>>(n, cid[0]);
+        CK(cudaMemcpyAsync(clo[0], leafLo, (size_t)n * sizeof(float4), cudaMemcpyDeviceToDevice, stream));
+        CK(cudaMemcpyAsync(chi[0], leafHi, (size_t)n * sizeof(float4), cudaMemcpyDeviceToDevice, stream));
+        out.launches++;
+        uint32_t m = n; static uint32_t* hostM = nullptr;          // pinned read-back word, allocated once per process
+        if (!hostM) CK(cudaMallocHost((void**)&hostM, sizeof(uint32_t)));
+        while (m > PLOC_FINAL) {
+            const uint32_t g = (m + PLOC_BLOCK - 1) / PLOC_BLOCK;
+            k_ploc_nn<<<g, PLOC_BLOCK, 0, stream>>>(clo[0], chi[0], m, radius, nn);
+            k_ploc_merge<<<g, PLOC_BLOCK, 0, stream>>>(m, nn, cid[0], clo[0], chi[0], t, pc, cid[1], clo[1], chi[1], flags);
+            CK(cub::DeviceScan::ExclusiveSum(scanTmp, scanBytes, flags, offsets, (int)m, stream));
+            k_ploc_compact<<<g, PLOC_BLOCK, 0, stream>>>(m, flags, offsets, cid[1], clo[1], chi[1], cid[0], clo[0], chi[0], pc + 1);
+            out.launches += 5;
+            CK(cudaMemcpyAsync(hostM, pc + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+            CK(cudaStreamSynchronize(stream));
+            m = *hostM;
+        }
+        k_ploc_final<<<1, PLOC_FINAL, 0, stream>>>(m, radius, cid[0], clo[0], chi[0], t, pc, pc + 2); out.launches++;
+        CK(cudaMemcpyAsync(hostM, pc + 2, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+        CK(cudaStreamSynchronize(stream));
+        rootRef = *hostM;
+        dfree(cid[0]); dfree(cid[1]); dfree(clo[0]); dfree(clo[1]); dfree(chi[0]); dfree(chi[1]); dfree(nn); dfree(flags); dfree(offsets); dfree(pc); dfree(scanTmp);
     }
 
     // worst case one BVH8 node per BVH2 internal node; shrunk to the exact size afterwards
@@ -356,11 +542,11 @@ void build_bvh(const BvhBuildInput& in, BvhResult& out, cudaStream_t stream) {
     uint2* tasksA = dalloc<uint2>(ni + 1); uint2* tasksB = dalloc<uint2>(ni + 1);
     const uint32_t initCounters[4] = {1u, 0u, 0u, 0u};
     CK(cudaMemcpyAsync(counters, initCounters, sizeof(initCounters), cudaMemcpyHostToDevice, stream));
-    const uint2 rootTask = make_uint2(n > 1 ? 0u : (LEAF_FLAG | 0u), 0u);
+    const uint2 rootTask = make_uint2(rootRef, 0u);
     CK(cudaMemcpyAsync(tasksA, &rootTask, sizeof(rootTask), cudaMemcpyHostToDevice, stream));
 
     CollapseArgs ca;
-    ca.t = t; ca.n = (int)n; ca.sortedIdx = sortedIdx; ca.boxLo = boxLo; ca.boxHi = boxHi;
+    ca.t = t; ca.n = (int)n; ca.sortedIdx = sortedIdx;
     ca.refs = in.refs; ca.geoms = in.geoms; ca.positions = in.positions; ca.indices = in.indices;
     ca.nodes = nodesTmp; ca.tris = tris; ca.counters = counters;
     uint32_t numTasks = 1; uint2* tin = tasksA; uint2* tout = tasksB;
@@ -385,8 +571,8 @@ void build_bvh(const BvhBuildInput& in, BvhResult& out, cudaStream_t stream) {
     out.nodes = nodes; out.tris = tris;
 
     dfree(nodesTmp); dfree(counters); dfree(tasksA); dfree(tasksB);
-    dfree(t.left); dfree(t.right); dfree(t.parent); dfree(t.rangeFirst); dfree(t.rangeLast);
-    dfree(t.lo); dfree(t.hi); dfree(t.visit);
+    dfree(t.left); dfree(t.right); dfree(t.parent); dfree(t.count);
+    dfree(t.lo); dfree(t.hi); dfree(t.visit); dfree(leafLo); dfree(leafHi);
     dfree(tmp); dfree(keys); dfree(keysSorted); dfree(vals); dfree(sortedIdx);
     dfree(boxLo); dfree(boxHi); dfree(sceneBounds);
     cudaEventDestroy(e0); cudaEventDestroy(e1);

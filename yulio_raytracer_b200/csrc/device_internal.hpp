@@ -15,6 +15,8 @@ struct BvhBuildInput {
     const GeomRec* geoms;         // device
     const float4* positions;      // device
     const int4* indices;          // device
+    int ploc = 1;                 // 1: PLOC hierarchy (default), 0: Karras LBVH
+    int plocRadius = 8;           // PLOC neighbour search radius (positions to either side)
 };
 struct BvhResult {
     void* nodes; float4* tris; uint32_t numNodes, numTris; float buildMs; uint32_t launches;
