@@ -292,6 +292,12 @@ def main():
                 "frac": (achieved / peak) if achieved else None, "traffic": None, "peak_source": peak_src,
                 "bytes_per_ray": bpr, "avg_launch_ms": agg["closest_ms"] / max(1, agg["closest_launches"]),
                 "note": "BVH of this workload is L2-resident; node/triangle bytes are served by L1/L2, not HBM (DESIGN.md)"}
+    # secondary roofline: FP32 issue. flops/ray = 190*Nnode + 90*Ntri against 148 SMs x 128 lanes x 2 flop x SM clock
+    flops_per_ray = 190 * nbar["nodes_per_ray"] + 90 * nbar["tris_per_ray"]
+    fp32_peak = 148 * 128 * 2 * (clk["sm_mhz"] or 1965.0) * 1e6 / 1e12
+    fp32_ach = agg["closest_rays"] * flops_per_ray / (agg["closest_ms"] * 1e-3) / 1e12 if agg["closest_ms"] > 0 else None
+    roofline["fp32"] = {"achieved": fp32_ach, "peak": fp32_peak, "unit": "TFLOP/s", "frac": (fp32_ach / fp32_peak) if fp32_ach else None,
+                        "flops_per_ray": flops_per_ray, "peak_source": "nominal: 148 SMs x 128 FP32 lanes x 2 x sampled SM clock"}
     try:
         with open(os.path.join(REPO, "profiles", "traffic.json")) as f:
             roofline["traffic"] = json.load(f).get(args.workload)

@@ -8,8 +8,11 @@
 // resources): the control flow of StartRT/workerThreadRT (renderer.cpp:1490-1610), the ParamsRT -> renderer/light/framebuffer
 // set-up that the reference does through a synthetic command line (renderer.cpp:1557-1587 + parseCommandLine :974-1403),
 // outputMode's cube-face loop and 12W x H strip assembly (renderer.cpp:508-737), and the status tracker (:99-233).
-// Output files: <dae dir>/<dae name>_<camera name>.ppm (the reference writes .jpg through FreeImage/libjpeg-turbo, which are
-// Windows binaries in the mount; JPEG encoding is SURVEY §8f-2). The watermark resource is a Win32 resource: not available.
+// Output files: <dae dir>/<dae name>_<camera name>.jpg as in the reference when the back end is device_cuda: the 12W x H strip is
+// assembled, watermarked and JPEG-encoded on the GPU through device_cuda's optional hooks (include/yrt_device.h yrtxStrip*, SURVEY
+// §8f-2), no frame is mapped to the host. Any other back end (the CPU reference in the tests) gets the host assembly below and a
+// .ppm (the reference's FreeImage / libjpeg-turbo are Windows binaries in the mount). The watermark is a Win32 resource in the
+// reference; here it is the PNG named by YULIO_RT_WATERMARK, or watermark.png next to this library.
 #include <dlfcn.h>
 
 #include <atomic>
@@ -32,6 +35,19 @@ namespace embree {
 
 // ---- back-end selection: what devices/device/device.cpp:24-48 does, plus the "cuda" line a maintainer adds ----------------
 typedef Device* (*create_device_func)(const char* parms, size_t numThreads, int threadsPriority, const char* rtcore_cfg);
+
+// device_cuda's optional strip hooks (NULL with any other back end)
+struct StripHooks {
+    void* native = nullptr;
+    int (*setReadback)(void*, int) = nullptr;
+    int (*begin)(void*, size_t, size_t) = nullptr;
+    int (*setWatermark)(void*, const char*) = nullptr;
+    int (*addFace)(void*, void*, int, int) = nullptr;
+    int (*encode)(void*, int, int, const char*) = nullptr;
+    const char* (*lastError)() = nullptr;
+    bool ok() const { return native && begin && addFace && encode; }
+};
+static StripHooks g_hooks;
 
 static std::string ownDirectory() {
     Dl_info info;
@@ -56,6 +72,16 @@ Device* Device::rtCreateDevice(const char* type, size_t numThreads, int threadsP
     if (!f) throw std::runtime_error("invalid device library");
     Device* dev = f("", numThreads, threadsPriority, rtcore_cfg);
     if (!dev) throw std::runtime_error("device creation failed");
+    g_hooks = StripHooks();
+    if (void* (*nat)(Device*) = (void* (*)(Device*))dlsym(lib, "device_cuda_native")) {
+        g_hooks.native = nat(dev);
+        g_hooks.setReadback = (int (*)(void*, int))dlsym(lib, "yrtxSetReadback");
+        g_hooks.begin = (int (*)(void*, size_t, size_t))dlsym(lib, "yrtxStripBegin");
+        g_hooks.setWatermark = (int (*)(void*, const char*))dlsym(lib, "yrtxStripSetWatermark");
+        g_hooks.addFace = (int (*)(void*, void*, int, int))dlsym(lib, "yrtxStripAddFace");
+        g_hooks.encode = (int (*)(void*, int, int, const char*))dlsym(lib, "yrtxStripEncodeJPEG");
+        g_hooks.lastError = (const char* (*)())dlsym(lib, "yrtGetLastError");
+    }
     return dev;
 }
 
@@ -115,6 +141,15 @@ static void renderCubeMaps(Session& S) {
     std::vector<std::vector<unsigned char>> faces;
     std::vector<std::string> saved;
     const Vector3f camUp(0.f, 1.f, 0.f);                                              // g_camUp default, renderer.cpp:246
+    const bool gpuStrip = g_hooks.ok() && !getenv("YULIO_RT_HOST_STRIP");
+    if (gpuStrip) {
+        if (g_hooks.setReadback) g_hooks.setReadback(g_hooks.native, 0);             // frames stay on the GPU
+        if (S.p.waterMark && g_hooks.setWatermark) {
+            const char* wm = getenv("YULIO_RT_WATERMARK");
+            const std::string file = wm && *wm ? wm : ownDirectory() + "/watermark.png";
+            if (g_hooks.setWatermark(g_hooks.native, file.c_str()) != 0) printf("yulio_rt: no watermark (%s)\n", g_hooks.lastError ? g_hooks.lastError() : file.c_str());
+        }
+    } else if (S.p.waterMark) printf("yulio_rt: the watermark is applied by device_cuda's strip path only\n");
     for (size_t i = 0; i < S.cameras.size() && !g_stop; ++i) {
         g_status.setStage((int)i);
         const Handle<Device::RTCamera>& cam = S.cameras[i];
@@ -129,6 +164,21 @@ static void renderCubeMaps(Session& S) {
         if (S.p.toeIn) { dev->rtSetBool1(cam, "toeIn", true); dev->rtCommit(cam); }  // renderer.cpp:571-576
         dev->rtRenderFrame(S.renderer, cam, scene, S.tonemapper, S.frameBuffer, 0);
         dev->rtSwapBuffers(S.frameBuffer);
+        if (gpuStrip) {
+            // frame -> its strip segment on the device (watermark on faces 0-3), JPEG from the device: renderer.cpp:620-718
+            auto hook = [&](int rc) { if (rc != 0) throw std::runtime_error(g_hooks.lastError ? g_hooks.lastError() : "device_cuda strip hook failed"); };
+            if (face == 0) hook(g_hooks.begin(g_hooks.native, W, H));
+            hook(g_hooks.addFace(g_hooks.native, (void*)(Device::RTFrameBuffer)S.frameBuffer, (int)face, S.p.waterMark ? 1 : 0));
+            if (S.p.debug) {
+                const std::string f = base + cameraName + "_" + faceNames[face % 6] + (face < 6 ? "left" : "right") + ".jpg";
+                hook(g_hooks.encode(g_hooks.native, (int)face, S.p.jpegQuality, f.c_str())); saved.push_back(f);
+            }
+            if (face == 11) {
+                const std::string f = base + cameraName + ".jpg";
+                hook(g_hooks.encode(g_hooks.native, -1, S.p.jpegQuality, f.c_str())); saved.push_back(f);
+                printf("Generated stereoscopic cube map #%zu in file %s\n", i / 12 + 1, f.c_str());
+            }
+        } else {
         const unsigned char* px = (const unsigned char*)dev->rtMapFrameBuffer(S.frameBuffer);
         const size_t stride = (3 * W + 3) / 4 * 4;                                    // api/framebuffer.h:195
         std::vector<unsigned char> img(W * H * 3);
@@ -150,6 +200,7 @@ static void renderCubeMaps(Session& S) {
             const std::string f = base + cameraName + ".ppm";
             writePPM(f, strip.data(), 12 * W, H); saved.push_back(f);
             printf("Generated stereoscopic cube map #%zu in file %s\n", i / 12 + 1, f.c_str());
+        }
         }
         if (g_stop) {                                                                 // renderer.cpp:728-736
             if (!g_keep) for (const auto& f : saved) remove(f.c_str());
@@ -190,7 +241,6 @@ static void worker(Session* Sp) {
                 dev->rtCommit(light);
                 S.prims.push_back(dev->rtNewLightPrimitive(light, nullptr, nullptr));
             }
-            if (S.p.waterMark) printf("yulio_rt: the watermark is a Win32 resource in the reference and is not available in this re-host\n");
             renderCubeMaps(S);
         }
     } catch (const std::exception& e) {

@@ -183,6 +183,27 @@ YRT_API yrt_status yrtxFrameBufferDevice(yrt_device*, yrt_handle frameBuffer, vo
  * (default 1: the frame is in the host buffer when yrtRenderFrame returns, as in the reference). */
 YRT_API yrt_status yrtxSetReadback(yrt_device*, int readbackEachFrame);
 
+/* ---- the image readers behind yrtNewImageFromFile (common/image/image.cpp:26-58), exposed for tests -----
+ * format: 0 RGB8, 1 RGBA8, 2 RGB_FLOAT32, 3 RGBA_FLOAT32; pixels may be NULL (query the size first). File images are RGBA8 with row 0
+ * = bottom scanline of the picture, as the reference's JPEG / FreeImage loaders store them. yrtxDecodePNGFile needs no device. */
+YRT_API yrt_status yrtxReadImage(yrt_device*, yrt_handle image, int* width, int* height, int* format, void* pixels);
+YRT_API yrt_status yrtxDecodePNGFile(const char* file, int flipVertical, int flipHorizontal, int* width, int* height, void* rgba);
+
+/* ---- the stereo cube-map strip, assembled and JPEG-encoded on the device ------------------------------
+ * What the reference's front end does on the host after every rtRenderFrame of a viewpoint (devices/renderer/renderer.cpp:620-725):
+ * map the frame, blend the 100x100 watermark into the centre of faces 0-3 (:637-654), copy the 12 frames into one 12W x H image in
+ * the order Left Right Up Down Back Front, cameras 6-11 first (:665-711), store it as JPEG at jpegQuality (:713-718, common/image/
+ * jpeg.cpp:207-250). Here the frames stay on the GPU: yrtxStripAddFace copies the RGB8 frame just rendered into its segment, and
+ * yrtxStripEncodeJPEG encodes with nvJPEG. cubeFaceIndex = the camera's "cubeFaceIndex" (0..11). */
+YRT_API yrt_status yrtxStripBegin(yrt_device*, size_t faceWidth, size_t faceHeight);
+/* PNG file, loaded as the reference loads its resource (flipped vertically and horizontally, renderer.cpp:84); NULL or "" removes it */
+YRT_API yrt_status yrtxStripSetWatermark(yrt_device*, const char* pngFile);
+YRT_API yrt_status yrtxStripAddFace(yrt_device*, yrt_handle frameBuffer, int cubeFaceIndex, int watermark);
+/* copies the 12W x H x 3 strip to the host (tests, uncompressed output) */
+YRT_API yrt_status yrtxStripRead(yrt_device*, void* rgb);
+/* cubeFaceIndex < 0: the whole strip; 0..11: that face's segment (the reference's per-face debug image, :656-660) */
+YRT_API yrt_status yrtxStripEncodeJPEG(yrt_device*, int cubeFaceIndex, int quality, const char* file);
+
 #ifdef __cplusplus
 }
 #endif

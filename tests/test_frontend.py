@@ -113,12 +113,16 @@ def test_stop_discards_results(front, tmp_path):
 @pytest.mark.gpu
 def test_cube_map_cuda_matches_reference_backend(tmp_path):
     """Same .dae, same loader, same front end: device_cuda against the reference CPU device. Equal sample tables and per-path
-    decisions -> the RGB8 strips agree to quantisation except where libm/CUDA last-bit differences flip a path decision."""
+    decisions -> the RGB8 strips agree to quantisation except where libm/CUDA last-bit differences flip a path decision.
+    device_cuda's own output is the JPEG strip assembled and encoded on the GPU; YULIO_RT_HOST_STRIP=1 selects the
+    host assembly + .ppm so that the frames can also be compared exactly."""
     need_frontend()
-    d1, d2 = tmp_path / "cuda", tmp_path / "cpu"
+    from PIL import Image
+    d1, d2, d3 = tmp_path / "cuda", tmp_path / "cpu", tmp_path / "cuda_jpg"
     dae1 = dae_scene.write_scene(str(d1), "room", scene_scale=1.5)
     dae2 = dae_scene.write_scene(str(d2), "room", scene_scale=1.5)
-    r1 = run_rt_test(dae1, 64, 16, 6)
+    dae3 = dae_scene.write_scene(str(d3), "room", scene_scale=1.5)
+    r1 = run_rt_test(dae1, 64, 16, 6, extra_env={"YULIO_RT_HOST_STRIP": "1"})
     assert r1.returncode == 0, r1.stdout + r1.stderr
     r2 = run_rt_test(dae2, 64, 16, 6, device_lib=ORACLE)
     assert r2.returncode == 0, r2.stdout + r2.stderr
@@ -127,3 +131,10 @@ def test_cube_map_cuda_matches_reference_backend(tmp_path):
     assert a.shape == b.shape == (64, 12 * 64, 3)
     diff = np.abs(a - b)
     assert diff.mean() <= 0.05 and (diff > 2).mean() <= 0.005, (diff.mean(), (diff > 2).mean(), diff.max())
+    r3 = run_rt_test(dae3, 64, 16, 6)                                               # strip + JPEG on the device
+    assert r3.returncode == 0, r3.stdout + r3.stderr
+    assert not os.path.exists(str(d3 / "room_A.ppm"))
+    j = np.asarray(Image.open(str(d3 / "room_A.jpg")).convert("RGB")).astype(np.float64)
+    assert j.shape == a.shape
+    from tests.test_formats import _libjpeg_psnr, _psnr
+    assert _psnr(j, a) >= _libjpeg_psnr(a, 90, str(tmp_path / "ref.jpg")) - 1.5     # jpegQuality 90, 4:2:0: as good as libjpeg on this image

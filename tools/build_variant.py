@@ -20,7 +20,7 @@ def cc(src):
             prev2 = globals().get("prev"); globals()["prev2"] = prev2; globals()["prev"] = l
     return o
 prev = prev2 = None
-with ThreadPoolExecutor(5) as ex: objs = list(ex.map(cc, g.CU_SOURCES))
+with ThreadPoolExecutor(6) as ex: objs = list(ex.map(cc, g.CU_SOURCES))
 lib = os.path.join(out, f"libyrt_{name}.so")
-subprocess.check_call(["nvcc", "-shared", "-o", lib] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler", "-fPIC"])
+subprocess.check_call(["nvcc", "-shared", "-o", lib] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler", "-fPIC", "-lz", "-ldl"])
 print("built", lib)

@@ -23,6 +23,7 @@ class CudaDevice : public Device {
 
 public:
     explicit CudaDevice(yrt_device* dev) : d(dev) {}
+    yrt_device* native() const { return d; }
     ~CudaDevice() override { yrtDestroyDevice(d); }
 
     RTCamera rtNewCamera(const char* type) override { return (RTCamera)ok(yrtNewCamera(d, type), "rtNewCamera"); }
@@ -95,6 +96,13 @@ extern "C" __attribute__((visibility("default"))) Device* create(const char* par
     yrt_device* dev = yrtCreateDevice(parms, numThreads, threadsPriority, rtcore_cfg);
     if (!dev) throw std::runtime_error(std::string("device_cuda: ") + yrtGetLastError());
     return new CudaDevice(dev);
+}
+
+// Optional hook for callers that know device_cuda's extensions (include/yrt_device.h, yrtx*): the C handle behind a Device created by
+// this plugin, or NULL for any other Device. Object handles (RTFrameBuffer, ...) returned by this plugin ARE the C-ABI handles.
+extern "C" __attribute__((visibility("default"))) yrt_device* device_cuda_native(Device* device) {
+    CudaDevice* c = dynamic_cast<CudaDevice*>(device);
+    return c ? c->native() : nullptr;
 }
 
 }  // namespace embree

@@ -116,6 +116,10 @@ struct FrameTimers {                           // CUDA-event pairs collected dur
 
 }  // namespace yrt
 
+namespace yrt {
+// the stereo cube-map strip being assembled on the device (image_codecs.cu; devices/renderer/renderer.cpp:665-725)
+struct CubeStrip { unsigned char* dev = nullptr; size_t w = 0, h = 0; uchar4* wm = nullptr; int wmW = 0, wmH = 0; int facesAdded = 0; };
+}
 struct yrt_device {
     std::mutex mutex;                          // RT_COMMAND_HEADER (api/singleray_device.cpp:97)
     int gpu = 0; int numSMs = 148; cudaStream_t stream = nullptr;
@@ -133,5 +137,6 @@ struct yrt_device {
     yrt::DevBuf<float> sampleTable; yrt::TableKey tableKey; int tableSpp = 1, tableN1 = 0, tableN2 = 0, tableRec = 0;
     yrt::PixelFilter filters[3]; bool filterReady[3] = {false, false, false};
     yrtx_frame_stats stats{};
+    yrt::CubeStrip strip;
     void bind() const;
 };

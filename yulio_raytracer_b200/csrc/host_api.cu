@@ -31,6 +31,14 @@ void trace_rays(yrt_device* dev, SceneHandle* sc, size_t n, const float* rays, v
 void primary_rays(yrt_device* dev, RendererHandle* r, CameraHandle* c, FrameBufferHandle* f, float* rays, int* sets);
 void sample_table(yrt_device* dev, RendererHandle* r, SceneHandle* s, int iteration, int* sets, int* spp, int* n1, int* n2, float* table);
 std::shared_ptr<ImageObj> load_image_file(const char* file);
+// implemented in image_codecs.cu
+void strip_begin(yrt_device* dev, size_t faceW, size_t faceH);
+void strip_set_watermark(yrt_device* dev, const char* pngFile);
+void strip_add_face(yrt_device* dev, FrameBufferHandle* fb, int cubeFaceIndex, int watermark);
+void strip_read(yrt_device* dev, void* rgb);
+void strip_encode_jpeg(yrt_device* dev, int cubeFaceIndex, int quality, const char* file);
+void strip_release(yrt_device* dev);
+std::shared_ptr<ImageObj> decode_png_file(const char* file, bool flipVertical, bool flipHorizontal);
 
 ImageObj::~ImageObj() { if (devPixels) cudaFree(devPixels); }
 PrimHandle::~PrimHandle() {
@@ -443,7 +451,7 @@ void yrtDestroyDevice(yrt_device* dev) {
     if (!dev) return;
     cudaSetDevice(dev->gpu);
     cudaStreamSynchronize(dev->stream);
-    dev->wf.release(); dev->timers.release(); dev->sampleTable.release();
+    dev->wf.release(); dev->timers.release(); dev->sampleTable.release(); strip_release(dev);
     if (dev->hostCounters) cudaFreeHost(dev->hostCounters);
     cudaStreamDestroy(dev->stream);
     delete dev;
@@ -722,5 +730,33 @@ yrt_status yrtxFrameBufferDevice(yrt_device* dev, yrt_handle fb, void** devPtr, 
             if (devPtr) *devPtr = f->devPacked; if (bytes) *bytes = f->bytes(); if (strideBytes) *strideBytes = f->strideBytes)
 }
 yrt_status yrtxSetReadback(yrt_device* dev, int readbackEachFrame) { GUARD_S(dev->readback = readbackEachFrame != 0) }
+
+// ---- decoded images (tests of the format readers) ----------------------------------------------------
+yrt_status yrtxReadImage(yrt_device* dev, yrt_handle image, int* width, int* height, int* format, void* pixels) {
+    GUARD_S(auto* h = cast<ImageHandle>(image, HK_IMAGE, "image");
+            if (!h->inst) throw std::runtime_error("invalid image value");
+            if (width) *width = h->inst->width; if (height) *height = h->inst->height; if (format) *format = h->inst->format;
+            if (pixels && h->inst->pixels) memcpy(pixels, h->inst->pixels, h->inst->bytes());)
+}
+yrt_status yrtxDecodePNGFile(const char* file, int flipVertical, int flipHorizontal, int* width, int* height, void* rgba) {
+    try {
+        auto img = decode_png_file(file ? file : "", flipVertical != 0, flipHorizontal != 0);
+        if (!img) throw std::runtime_error(std::string("cannot decode ") + (file ? file : "(null)"));
+        if (width) *width = img->width; if (height) *height = img->height;
+        if (rgba) memcpy(rgba, img->storage.data(), img->storage.size());
+        return YRT_OK;
+    } catch (const std::exception& e) { g_lastError = e.what(); return YRT_ERROR; }
+}
+
+// ---- stereo cube-map strip on the device (image_codecs.cu) -------------------------------------------
+yrt_status yrtxStripBegin(yrt_device* dev, size_t faceWidth, size_t faceHeight) { GUARD_S(strip_begin(dev, faceWidth, faceHeight)) }
+yrt_status yrtxStripSetWatermark(yrt_device* dev, const char* pngFile) { GUARD_S(strip_set_watermark(dev, pngFile)) }
+yrt_status yrtxStripAddFace(yrt_device* dev, yrt_handle fb, int cubeFaceIndex, int watermark) {
+    GUARD_S(strip_add_face(dev, cast<FrameBufferHandle>(fb, HK_FRAMEBUFFER, "framebuffer"), cubeFaceIndex, watermark))
+}
+yrt_status yrtxStripRead(yrt_device* dev, void* rgb) { GUARD_S(if (!rgb) throw std::runtime_error("invalid buffer"); strip_read(dev, rgb)) }
+yrt_status yrtxStripEncodeJPEG(yrt_device* dev, int cubeFaceIndex, int quality, const char* file) {
+    GUARD_S(if (!file) throw std::runtime_error("invalid file name"); strip_encode_jpeg(dev, cubeFaceIndex, quality, file))
+}
 
 }  // extern "C"

@@ -36,12 +36,16 @@ static unsigned char quant8(float v) {              // Color4::set(Col4c&): clam
     const float c = rclamp(v, 0.f, 1.f) * 255.0f;
     return (unsigned char)(int)c;
 }
+std::shared_ptr<ImageObj> decode_jpeg_file(const char* file);                     // image_codecs.cu
+std::shared_ptr<ImageObj> decode_png_file(const char* file, bool flipVertical, bool flipHorizontal);
 std::shared_ptr<ImageObj> load_image_file(const char* file) {
     if (!file) return nullptr;
     const std::string name(file);
     const size_t dot = name.rfind('.');
     std::string ext = dot == std::string::npos ? "" : name.substr(dot + 1);
     for (auto& c : ext) c = (char)tolower((unsigned char)c);
+    if (ext == "jpg" || ext == "jpeg") return decode_jpeg_file(file);             // common/image/image.cpp:41-45 (libjpeg-turbo in the reference)
+    if (ext == "png") return decode_png_file(file, false, false);                 // common/image/image.cpp:50 (FreeImage in the reference)
     if (ext != "ppm" && ext != "pfm") { printf("cannot read file %s: image format %s not supported\n", file, ext.c_str()); return nullptr; }
     FILE* f = fopen(file, "rb");
     if (!f) { printf("cannot read file %s: cannot open\n", file); return nullptr; }

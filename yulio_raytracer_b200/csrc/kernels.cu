@@ -288,7 +288,8 @@ __device__ __forceinline__ uint32_t warp_alloc(uint32_t* counter, uint32_t count
 #define YRT_SHADE_THREADS 128
 #endif
 // The shading kernel is bound by instruction fetch; barriers keep the warps of a CTA in the same code region so that they share
-// fetched lines (measured: -7.5 % on the C3 stand-in). Every thread executes every iteration, so the barriers are uniform.
+// fetched lines (measured at 1024^2: -4 % shade time on the C3 stand-in, +4 % on C2; one barrier per iteration is the
+// default, YRT_SHADE_SYNC=2 adds two more inside the iteration). Every thread executes every iteration, so the barriers are uniform.
 #ifndef YRT_SHADE_SYNC
 #define YRT_SHADE_SYNC 1
 #endif
@@ -296,6 +297,11 @@ __device__ __forceinline__ uint32_t warp_alloc(uint32_t* counter, uint32_t count
 #define SHADE_BARRIER() __syncthreads()
 #else
 #define SHADE_BARRIER()
+#endif
+#if YRT_SHADE_SYNC >= 2
+#define SHADE_BARRIER2() __syncthreads()
+#else
+#define SHADE_BARRIER2()
 #endif
 __global__ void __launch_bounds__(YRT_SHADE_THREADS, YRT_SHADE_MINBLOCKS) k_shade(FrameConst fc, WavefrontBuffers wb, int queueSel, uint32_t pixelBegin, int depth) {
     __shared__ float smLobes[YRT_MAX_LOBES * YRT_LOBE_WORDS * YRT_SHADE_THREADS], smCand[YRT_MAX_LOBES * YRT_CAND_WORDS * YRT_SHADE_THREADS];
@@ -318,11 +324,13 @@ __global__ void __launch_bounds__(YRT_SHADE_THREADS, YRT_SHADE_MINBLOCKS) k_shad
             pid = queue[i];
             const float4 o4 = wb.rayO[pid]; d4 = wb.rayD[pid];
             const float4 hA = wb.hitA[pid], hB = wb.hitB[pid];
-            Col L(0.f);
+            // radiance so far: read (and written back) only by the vertices that add to it — misses that see the environment and hits
+            // on visible emitters; k_resolve adds the light samples. Bounce 0 initialises it.
+            Col L(0.f); bool Ltouched = depth == 0;
+            auto loadL = [&]() { if (!Ltouched) { const float4 L4 = wb.Lacc[pid]; L = Col(L4.x, L4.y, L4.z); Ltouched = true; } };
             if (depth == 0) { thr = Col(1.f); flags = FLAG_UNBENT; }            // LightPath(ray): pathtraceintegrator.h:41-43
             else {
                 const float4 t4 = wb.thr[pid]; thr = Col(t4.x, t4.y, t4.z); flags = __float_as_uint(t4.w) >> 16;
-                const float4 L4 = wb.Lacc[pid]; L = Col(L4.x, L4.y, L4.z);
                 if (sc.hasMedia) m4 = wb.medium[pid];                           // only Dielectric materials change the medium
             }
             hitT = hA.x;
@@ -338,8 +346,9 @@ __global__ void __launch_bounds__(YRT_SHADE_THREADS, YRT_SHADE_MINBLOCKS) k_shad
                     const TextureRec& bp = sc.textures[ig.backplateTex];
                     const int x = iclamp(int(fx * bp.width), 0, bp.width - 1), y = iclamp(int(fy * bp.height), 0, bp.height - 1);
                     const Col4 c = texel(bp, x, y);
-                    L += thr * Col(c.r, c.g, c.b);
-                } else if (!(flags & FLAG_IGNORE_VISIBLE_LIGHTS)) {
+                    loadL(); L += thr * Col(c.r, c.g, c.b);
+                } else if (!(flags & FLAG_IGNORE_VISIBLE_LIGHTS) && sc.numEnvLights > 0) {
+                    loadL();
                     for (int e = 0; e < sc.numEnvLights; e++) L += thr * env_Le(sc, sc.lights[sc.envLightIdx[e]], wo);
                 }
             } else {
@@ -347,16 +356,16 @@ __global__ void __launch_bounds__(YRT_SHADE_THREADS, YRT_SHADE_MINBLOCKS) k_shad
                 bool backfacing = false;
                 if (dot(dg.Ng, dir) > 0.f) { backfacing = true; dg.Ng = -dg.Ng; dg.Ns = -dg.Ns; }   // :95-98
                 if (dg.material >= 0) material_shade(sc, sc.materials[dg.material], dg, Col(m4.x, m4.y, m4.z), m4.w, lobes);
-                if (!(flags & FLAG_IGNORE_VISIBLE_LIGHTS) && dg.areaLight >= 0 && !backfacing) L += thr * sc.lights[dg.areaLight].L;  // :114-115
+                if (!(flags & FLAG_IGNORE_VISIBLE_LIGHTS) && dg.areaLight >= 0 && !backfacing) { loadL(); L += thr * sc.lights[dg.areaLight].L; }  // :114-115
                 for (int k = 0; k < lobes.n; k++) needLights |= (lobes.type(k) & BR_DIFFUSE) != 0;
                 alive = true;
             }
-            wb.Lacc[pid] = make_float4(L.x, L.y, L.z, 0.f);
+            if (Ltouched) wb.Lacc[pid] = make_float4(L.x, L.y, L.z, 0.f);
         }
         // ---- direct lighting: one slot per light, in light order (pathtraceintegrator.cpp:124-166).
         // Skipped lights leave an invalid ray (tfar < tnear) so the per-path span stays contiguous and the
         // resolve kernel can add the contributions in the reference's order.
-        SHADE_BARRIER();
+        SHADE_BARRIER2();
         const uint32_t nl = (valid && alive && needLights) ? (uint32_t)sc.numLights : 0u;
         const uint32_t base = warp_alloc(&wb.counters[2], nl);
         for (uint32_t li = 0; li < nl; li++) {
@@ -399,7 +408,7 @@ __global__ void __launch_bounds__(YRT_SHADE_THREADS, YRT_SHADE_MINBLOCKS) k_shad
         if (nl) wb.shadowPid[base / nl] = pid;                // slots are claimed in groups of numLights: base is a multiple of nl
 
         // ---- path continuation (pathtraceintegrator.cpp:169-213)
-        SHADE_BARRIER();
+        SHADE_BARRIER2();
         bool cont = false;
         if (valid && alive) {
             cont = depth < ig.maxDepth - 1;

@@ -79,9 +79,29 @@ _OPTIONAL = {
     "yrtxSampleTable": (C.c_int, [H, H, C.c_int] + [C.POINTER(C.c_int)] * 4 + [C.c_void_p]),
     "yrtxFrameBufferDevice": (C.c_int, [H, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
     "yrtxSetReadback": (C.c_int, [C.c_int]),
+    "yrtxReadImage": (C.c_int, [H] + [C.POINTER(C.c_int)] * 3 + [C.c_void_p]),
+    "yrtxStripBegin": (C.c_int, [C.c_size_t, C.c_size_t]), "yrtxStripSetWatermark": (C.c_int, [_P]),
+    "yrtxStripAddFace": (C.c_int, [H, C.c_int, C.c_int]), "yrtxStripRead": (C.c_int, [C.c_void_p]),
+    "yrtxStripEncodeJPEG": (C.c_int, [C.c_int, C.c_int, _P]),
 }
 
-_NODEV = {"yrtxHostSampleTable": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int] + [C.POINTER(C.c_int)] * 3 + [C.c_void_p])}
+_NODEV = {"yrtxHostSampleTable": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int] + [C.POINTER(C.c_int)] * 3 + [C.c_void_p]),
+          "yrtxDecodePNGFile": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_void_p])}
+
+
+def decode_png_file(libpath: str, file: str, flip_vertical: bool = False, flip_horizontal: bool = False) -> np.ndarray:
+    """yrtxDecodePNGFile of `libpath` (works without a GPU): RGBA8 array [h, w, 4] in the reference's row order."""
+    lib = C.CDLL(libpath, mode=C.RTLD_LOCAL)
+    fn = lib.yrtxDecodePNGFile
+    fn.restype, fn.argtypes = _NODEV["yrtxDecodePNGFile"]
+    lib.yrtGetLastError.restype = _P
+    w, h = C.c_int(0), C.c_int(0)
+    if fn(_b(file), int(flip_vertical), int(flip_horizontal), C.byref(w), C.byref(h), None) != 0:
+        raise RuntimeError(lib.yrtGetLastError().decode())
+    out = np.zeros((h.value, w.value, 4), np.uint8)
+    if fn(_b(file), int(flip_vertical), int(flip_horizontal), C.byref(w), C.byref(h), out.ctypes.data) != 0:
+        raise RuntimeError(lib.yrtGetLastError().decode())
+    return out
 
 
 def host_sample_table(libpath: str, filter: str, spp: int, sets: int, max_depth: int, iteration: int = 0):
@@ -323,6 +343,25 @@ class Device:
 
     def set_readback(self, each_frame: bool):
         self._s("yrtxSetReadback", int(each_frame))
+
+    def read_image(self, image) -> np.ndarray:
+        """Pixels of an image handle as stored (yrtxReadImage): [h, w, channels] uint8 or float32."""
+        w, h, f = C.c_int(0), C.c_int(0), C.c_int(0)
+        self._s("yrtxReadImage", image, C.byref(w), C.byref(h), C.byref(f), None)
+        ch, dt = {0: (3, np.uint8), 1: (4, np.uint8), 2: (3, np.float32), 3: (4, np.float32)}[f.value]
+        out = np.zeros((h.value, w.value, ch), dt)
+        self._s("yrtxReadImage", image, C.byref(w), C.byref(h), C.byref(f), out.ctypes.data)
+        return out
+
+    # ---- stereo cube-map strip on the device (include/yrt_device.h; renderer.cpp:620-725) ----
+    def strip_begin(self, face_w: int, face_h: int): self._s("yrtxStripBegin", face_w, face_h)
+    def strip_set_watermark(self, png_file): self._s("yrtxStripSetWatermark", _b(png_file) if png_file else None)
+    def strip_add_face(self, fb, cube_face_index: int, watermark: bool = False): self._s("yrtxStripAddFace", fb, int(cube_face_index), int(watermark))
+    def strip_read(self, face_w: int, face_h: int) -> np.ndarray:
+        out = np.zeros((face_h, 12 * face_w, 3), np.uint8)
+        self._s("yrtxStripRead", out.ctypes.data)
+        return out
+    def strip_encode_jpeg(self, file: str, quality: int = 90, cube_face_index: int = -1): self._s("yrtxStripEncodeJPEG", int(cube_face_index), int(quality), _b(file))
 
     def trace_rays_device(self, scene, rays_ptr: int, hits_ptr: int, n: int, closest: bool = True) -> float:
         """Device-resident rays/hits (8 floats each); returns the CUDA-event time of the traversal kernel in ms."""
