@@ -71,3 +71,28 @@ def test_soup_closest_and_anyhit(cuda_dev, oracle_dev, n_tris, meshes, cull):
     og, _ = cuda_dev.trace_rays(sg.scene, seg, closest=False)
     oo, _ = oracle_dev.trace_rays(so.scene, seg, closest=False)
     assert np.array_equal(ids(og)[:, 0], ids(oo)[:, 0]), "occlusion bits differ"
+
+
+def psnr(a, b, peak=1.0):
+    mse = float(((np.asarray(a, np.float64) - np.asarray(b, np.float64)) ** 2).mean())
+    return 10 * np.log10(peak * peak / max(mse, 1e-30))
+
+
+@pytest.mark.parametrize("name,size,spp,depth", [("cornell", 40, 4096, 5), ("glass", 32, 1024, 8), ("atrium", 32, 1024, 6)])
+def test_converged_images_psnr(cuda_dev, oracle_mt, name, size, spp, depth):
+    """converged images at fixed high spp (4096 for C1; 1024 for the costlier scenes) on linear float frames.
+    Stated bar: PSNR >= 40 dB against the reference CPU path at the same spp (peak = 1.0, the clamp point of the RGB8 output)."""
+    imgs = []
+    for d in (cuda_dev, oracle_mt):
+        if name == "cornell":
+            s = scenes.cornell(d, size, size, spp, depth)
+        elif name == "glass":
+            s = scenes.spheres(d, "glass", size, size, spp, depth, face=3)
+        else:
+            s = scenes.atrium(d, size, size, spp, depth, face=1, detail=6, tex_size=64)
+        d.rtRenderFrame(s.renderer, s.camera, s.scene, s.tonemapper, s.framebuffer, 0)
+        imgs.append(d.read_framebuffer(s.framebuffer, "RGB_FLOAT32", size, size))
+    assert imgs[1].mean() > 0.02
+    p = psnr(np.minimum(imgs[0], 4.0), np.minimum(imgs[1], 4.0))
+    print(f"{name}: PSNR {p:.1f} dB at {spp} spp")
+    assert p >= 40.0, p

@@ -34,20 +34,24 @@ class BandGather:
         self.max_rows = max(len(r) for r in self.rows)
         self.full: Optional[torch.Tensor] = None
         if rank == 0:
-            self.full = torch.zeros(height * stride_bytes, dtype=torch.uint8, device=device)
-            self.index = [torch.tensor(r, dtype=torch.long, device=device) for r in self.rows]
-            self.parts = [torch.empty(self.max_rows * stride_bytes, dtype=torch.uint8, device=device) for _ in range(world)]
+            # one extra (dummy) row takes the padding rows of ranks that own fewer than max_rows rows, so that the re-interleave is
+            # a single index_copy over the gathered block instead of one launch per rank
+            self.full = torch.zeros((height + 1) * stride_bytes, dtype=torch.uint8, device=device)
+            idx = []
+            for r in self.rows:
+                idx += r + [height] * (self.max_rows - len(r))
+            self.index = torch.tensor(idx, dtype=torch.long, device=device)
+            self.block = torch.empty(world * self.max_rows * stride_bytes, dtype=torch.uint8, device=device)
+            self.parts = [self.block[r * self.max_rows * stride_bytes:(r + 1) * self.max_rows * stride_bytes] for r in range(world)]
 
     def gather(self, local: torch.Tensor) -> Optional[torch.Tensor]:
         """`local`: this rank's framebuffer bytes (compacted rows first). Returns the full frame on rank 0."""
         send = local[: self.max_rows * self.stride]
         if self.world == 1:
-            self.full.view(self.height, self.stride).index_copy_(0, self.index[0], send[: len(self.rows[0]) * self.stride].view(-1, self.stride))
-            return self.full
-        dist.gather(send, self.parts if self.rank == 0 else None, dst=0)
-        if self.rank != 0:
-            return None
-        fv = self.full.view(self.height, self.stride)
-        for r in range(self.world):
-            fv.index_copy_(0, self.index[r], self.parts[r][: len(self.rows[r]) * self.stride].view(-1, self.stride))
-        return self.full
+            self.block.copy_(send)
+        else:
+            dist.gather(send, self.parts if self.rank == 0 else None, dst=0)
+            if self.rank != 0:
+                return None
+        self.full.view(self.height + 1, self.stride).index_copy_(0, self.index, self.block.view(-1, self.stride))
+        return self.full[: self.height * self.stride]

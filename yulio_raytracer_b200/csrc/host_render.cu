@@ -657,9 +657,15 @@ void render_frame(yrt_device* dev, RendererHandle* rh, CameraHandle* ch, SceneHa
                 if (timers) { tm.end(st); tm.begin(TK_SHADE, st); }
                 launch_shade(fc, wq, q, (uint32_t)pixelBegin, depth, lcShade); launches++;
                 if (timers) tm.end(st);
-                // queue lengths of the next bounce: one small read-back per bounce buys the early exit and the sort size
-                YRT_CK(cudaMemcpyAsync(dev->hostCounters, wb.counters, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-                cudaEvent_t evCnt = tm.get(); YRT_CK(cudaEventRecord(evCnt, st));
+                // queue lengths of the next bounce: one small read-back per bounce buys the early exit and the sort size. Below
+                // syncMinPaths the round trip costs more than the (short, self-terminating) launches it could save: `alive` then
+                // stays an upper bound and the remaining bounces are enqueued without waiting.
+                const bool readCounters = alive >= dev->syncMinPaths || (dev->sortRays && alive >= dev->sortMin);
+                cudaEvent_t evCnt = nullptr;
+                if (readCounters) {
+                    YRT_CK(cudaMemcpyAsync(dev->hostCounters, wb.counters, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+                    evCnt = tm.get(); YRT_CK(cudaEventRecord(evCnt, st));
+                }
                 if (fc.scene.numLights > 0) {
                     if (timers) tm.begin(TK_SHADOW, st);
                     launch_trace_shadow(fc, wq, lcTrace); launches++; shadowLaunches++;
@@ -668,8 +674,7 @@ void render_frame(yrt_device* dev, RendererHandle* rh, CameraHandle* ch, SceneHa
                 else if (timers) tm.begin(TK_SHADE, st);
                 launch_resolve(fc, wq, q, lcStream); launches += 2;
                 if (timers) tm.end(st);
-                YRT_CK(cudaEventSynchronize(evCnt));
-                alive = dev->hostCounters[q ^ 1];
+                if (readCounters) { YRT_CK(cudaEventSynchronize(evCnt)); alive = dev->hostCounters[q ^ 1]; }
             }
             if (timers) tm.begin(TK_RAYGEN_FILM, st);
             launch_film(fc, wb, fp, (uint32_t)pixelBegin, np, lcStream); launches++;
