@@ -3,7 +3,7 @@
 cube map, driven through the C-ABI (include/yrt_device.h) exactly as the reference's outputMode loop drives a device
 (devices/renderer/renderer.cpp:543-632).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c3|c1] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c3|c4|c1] [--impl reference]
 
 A "step" is one rtRenderFrame of one stereo cube face of the workload (BASELINE.json configs[1] by default: the
 sphere_glass scene, 1024x1024 per face, 64 spp, depth 8, 12 stereo cube cameras); K steps walk the faces 0..11
@@ -38,6 +38,7 @@ WORKLOADS = {
     # name: (builder, description, face size, spp, depth)
     "c2": ("spheres", "C2 sphere_glass.xml + sphere_view.ecs: stereo cube face 1024x1024, 64 spp, depth 8 (procedural lines texture stands in for lines.ppm)", 1024, 64, 8),
     "c3": ("atrium", "C3 stand-in (Sponza.DAE stripped): procedural atrium ~276k tris, Uber+alpha+dome light, stereo cube face 1024x1024, 64 spp, depth 10, tMaxShadowRay 120", 1024, 64, 10),
+    "c4": ("atrium4", "C4 stand-in (22 Frederick St .dae stripped): procedural atrium ~1.1M tris, Uber+alpha+thin glass+billboard+dome light, stereo cube face 2048x2048, 16 spp (rt_test_dll.cpp:17), depth 10, tMaxShadowRay 120", 2048, 16, 10),
     "c1": ("cornell", "C1 cornell_box.ecs: pinhole 512x512, 16 spp, depth 2", 512, 16, 2),
 }
 
@@ -49,6 +50,8 @@ def build_workload(dev, name, size, spp, depth, fmt):
         return scenes.spheres(dev, "glass", size, size, spp, depth, face=0, fmt=fmt)
     if kind == "atrium":
         return scenes.atrium(dev, size, size, spp, depth, face=0, detail=56, fmt=fmt)
+    if kind == "atrium4":
+        return scenes.atrium(dev, size, size, spp, depth, face=0, detail=112, fmt=fmt, tex_size=512)
     s = scenes.cornell(dev, size, size, spp, depth, fmt=fmt)
     s.view = None
     return s
