@@ -306,7 +306,7 @@ struct CollapseArgs {
     const uint2* refs; const GeomRec* geoms; const float4* positions; const int4* indices;
     Node8* nodes; float4* tris;
     uint32_t* counters;          // [0] node counter, [1] triangle counter, [2] next-level task count
-    const uint2* tasksIn; uint2* tasksOut; uint32_t numTasks;
+    const uint2* tasksIn; uint2* tasksOut; uint32_t numTasks; int splitLeaves;
 };
 
 __device__ __forceinline__ void ref_box(const CollapseArgs& a, uint32_t ref, float lo[3], float hi[3]) {
@@ -349,10 +349,14 @@ __global__ void k_collapse(CollapseArgs a) {
     if (task.x & LEAF_FLAG) { cand[0] = task.x; count = 1; }    // single-triangle scene
     else {
         cand[0] = a.t.left[task.x]; cand[1] = a.t.right[task.x]; count = 2;
+        // pass 0 opens subtrees of more than 3 triangles, largest surface area first; pass 1 uses slots that are still free to split
+        // the small ones too (a leaf child of 3 triangles becomes 2 + 1 or 1 + 1 + 1 with tighter boxes): the node test costs the
+        // same for 3 or 8 occupied slots, every triangle test avoided is a gain
+        for (int pass = 0; pass < (a.splitLeaves ? 2 : 1); pass++)
         while (count < 8) {
             int best = -1; float bestArea = -1.f;
             for (int c = 0; c < count; c++) {
-                if ((cand[c] & LEAF_FLAG) || ref_count(a, cand[c]) <= 3u) continue;
+                if ((cand[c] & LEAF_FLAG) || (pass == 0 && ref_count(a, cand[c]) <= 3u)) continue;
                 float lo[3], hi[3]; ref_box(a, cand[c], lo, hi);
                 const float dx = hi[0] - lo[0], dy = hi[1] - lo[1], dz = hi[2] - lo[2];
                 const float area = dx * dy + dy * dz + dz * dx;
@@ -548,7 +552,7 @@ void build_bvh(const BvhBuildInput& in, BvhResult& out, cudaStream_t stream) {
     CollapseArgs ca;
     ca.t = t; ca.n = (int)n; ca.sortedIdx = sortedIdx;
     ca.refs = in.refs; ca.geoms = in.geoms; ca.positions = in.positions; ca.indices = in.indices;
-    ca.nodes = nodesTmp; ca.tris = tris; ca.counters = counters;
+    ca.nodes = nodesTmp; ca.tris = tris; ca.counters = counters; ca.splitLeaves = in.splitLeaves;
     uint32_t numTasks = 1; uint2* tin = tasksA; uint2* tout = tasksB;
     uint32_t hostCounters[4];
     while (numTasks) {

@@ -128,7 +128,7 @@ struct yrt_device {
     int countStats = 0, verbose = 0, alwaysRebuild = 0, useTimers = 1;
     int tuneRefillMin = 8, tuneTriNum = 3, tuneTriDen = 1, tuneSimple = 0;
     int shadeCtas = 6, traceCtas = 8;
-    int bvhPloc = 1, plocRadius = 8;           // cfg bvh=0 selects the Karras LBVH hierarchy (A/B), plocr the PLOC search radius
+    int bvhPloc = 1, plocRadius = 8, splitLeaves = 1;           // cfg bvh=0 selects the Karras LBVH hierarchy (A/B), plocr the PLOC search radius
     uint32_t syncMinPaths = 1u << 20;          // cfg syncmin=: per-bounce queue-length read-back only while at least this many paths are alive
     int sortRays = 0; uint32_t sortMin = 1u << 16;   // cfg sort=0|1: re-order bounce queues of at least sortMin rays (sort.cu); measured slower, off
     uint32_t* hostCounters = nullptr;          // pinned: queue lengths read back once per bounce   // cfg refill=,trinum=,triden= (bvh.cuh: TraceTune)

@@ -16,6 +16,7 @@ struct BvhBuildInput {
     const float4* positions;      // device
     const int4* indices;          // device
     int ploc = 1;                 // 1: PLOC hierarchy (default), 0: Karras LBVH
+    int splitLeaves = 1;          // BVH8 collapse: use free child slots to split leaf children of 2-3 triangles
     int plocRadius = 8;           // PLOC neighbour search radius (positions to either side)
 };
 struct BvhResult {

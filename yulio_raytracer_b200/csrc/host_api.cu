@@ -439,7 +439,7 @@ yrt_device* yrtCreateDevice(const char* parms, size_t numThreads, int threadsPri
         dev->tuneTriNum = (int)cfg_int(cfg, "trinum", dev->tuneTriNum); dev->tuneTriDen = (int)cfg_int(cfg, "triden", dev->tuneTriDen); dev->tuneSimple = cfg_int(cfg, "trav", 1) == 0;
         dev->shadeCtas = (int)cfg_int(cfg, "shadectas", YRT_SHADE_MINBLOCKS); dev->traceCtas = (int)cfg_int(cfg, "tracectas", 8);
         dev->syncMinPaths = (uint32_t)cfg_int(cfg, "syncmin", dev->syncMinPaths);
-        dev->bvhPloc = (int)cfg_int(cfg, "bvh", 1); dev->plocRadius = (int)cfg_int(cfg, "plocr", dev->plocRadius);
+        dev->bvhPloc = (int)cfg_int(cfg, "bvh", 1); dev->plocRadius = (int)cfg_int(cfg, "plocr", dev->plocRadius); dev->splitLeaves = (int)cfg_int(cfg, "splitleaves", 1);
         dev->sortRays = (int)cfg_int(cfg, "sort", 0); dev->sortMin = (uint32_t)cfg_int(cfg, "sortmin", 1l << 16);
         YRT_CK(cudaHostAlloc((void**)&dev->hostCounters, 16 * sizeof(uint32_t), cudaHostAllocDefault));
         if (dev->tuneRefillMin < 1) dev->tuneRefillMin = 1; if (dev->tuneRefillMin > 32) dev->tuneRefillMin = 32;
