@@ -465,3 +465,45 @@ def random_rays(n, seed=67890, extent=1000.0, tfar=math.inf, tfar_uniform=None):
     rays[:, 4:7] = d
     rays[:, 7] = tfar if tfar_uniform is None else rng.uniform(0, tfar_uniform, n)
     return rays
+
+
+# ------------------------------------------------------------------------------------------------
+# The materials reachable only through .xml scenes / the regression driver: a Cornell box whose blocks, floor and
+# back wall carry Plastic, Metal (rough + polished), BrushedMetal, MetallicPaint and Velvet, lit by the quad light and a dome light.
+# Meshes carry normals and texture coordinates so that both tangent constructions are exercised (trianglemesh_full.cpp:252-270,
+# trianglemesh_normals.cpp:154-155).
+# ------------------------------------------------------------------------------------------------
+def material(dev, kind, **params):
+    m = dev.rtNewMaterial(kind)
+    for k, v in params.items():
+        if isinstance(v, (tuple, list)):
+            dev.rtSetFloat3(m, k, *v)
+        else:
+            dev.rtSetFloat1(m, k, float(v))
+    dev.rtCommit(m)
+    return m
+
+
+def showroom(dev, width=64, height=64, spp=16, depth=5, fmt="RGB_FLOAT32", **kw):
+    mats = {
+        "white": material(dev, "Velvet", reflectance=(.6, .3, .35), backScattering=.7, horizonScatteringColor=(.4, .4, .5), horizonScatteringFallOff=6.0),
+        "red": material(dev, "Plastic", pigmentColor=(.8, .1, .1), eta=1.5, roughness=.05),
+        "green": material(dev, "MetallicPaint", shadeColor=(.1, .5, .2), glitterColor=(.8, .8, .6), glitterSpread=.3, eta=1.45),
+        "blue": material(dev, "Metal", reflectance=(.9, .8, .5), eta=(.2, .9, 1.1), k=(3.9, 2.4, 2.2), roughness=.08),
+    }
+    extra = [material(dev, "BrushedMetal", reflectance=(.8, .8, .9), eta=(1.4, 1.2, 1.1), k=(5.0, 4.6, 4.2), roughnessX=.02, roughnessY=.3),
+             material(dev, "Metal", reflectance=(1, 1, 1), eta=(.6, .6, .6), k=(4.8, 4.8, 4.8), roughness=0.0),
+             material(dev, "Plastic", pigmentColor=(.2, .3, .9), roughness=0.0)]
+    prims = []
+    for gi, (mat, quads) in enumerate(_CORNELL_GROUPS):
+        for qi, q in enumerate(quads):
+            p = np.asarray(q, np.float64)
+            n = np.cross(p[1] - p[0], p[3] - p[0]); n /= np.linalg.norm(n)
+            uv = np.array([[0, 0], [1, 0], [1, 1], [0, 1]], np.float64) * (1 + qi)
+            m = mats[mat] if not (mat == "white" and gi > 0) else extra[(gi + qi) % len(extra)]
+            with_uv = (qi % 2 == 0)
+            mesh = add_mesh(dev, p, [(0, 1, 2), (0, 2, 3)], normals=np.tile(n, (4, 1)), uvs=uv if with_uv else None)
+            prims.append(dev.rtNewShapePrimitive(mesh, m, None))
+    prims += quad_light(dev, (213, 548.77, 227), (130, 0, 0), (0, 0, 105), (40, 40, 40)) + [ambient_light(dev, (.3, .35, .4))]
+    cam = pinhole(dev, (278, 273, -800), (278, 273, 0), (0, 1, 0), 37.0, width / height)
+    return _bundle(dev, prims, cam, pathtracer(dev, spp, depth, **kw), width, height, fmt)

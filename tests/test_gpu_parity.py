@@ -96,3 +96,19 @@ def test_converged_images_psnr(cuda_dev, tmp_path, name, size, spp, depth):
     p = psnr(np.minimum(img, 4.0), np.minimum(ref, 4.0))
     print(f"{name}: PSNR {p:.1f} dB at {spp} spp")
     assert p >= 40.0, p
+
+
+def test_showroom_materials(cuda_dev, oracle_dev):
+    """Plastic, Metal (rough and polished), BrushedMetal (anisotropic, both tangent constructions), MetallicPaint and Velvet
+    (materials/*.h, brdfs/{conductor,dielectriclayer,minnaert,velvety}.h, microfacet/anisotropic_power_cosine_distribution.h) — the
+    EXT instantiation of the shading kernel — at equal spp against the reference."""
+    w = h = 48; spp = 16
+    imgs = []
+    for d in (cuda_dev, oracle_dev):
+        s = scenes.showroom(d, w, h, spp, 5)
+        d.rtRenderFrame(s.renderer, s.camera, s.scene, s.tonemapper, s.framebuffer, 0)
+        imgs.append(d.read_framebuffer(s.framebuffer, "RGB_FLOAT32", w, h))
+    assert imgs[1].mean() > 0.05
+    image_close(imgs[0], imgs[1])
+    sg, so = cuda_dev.frame_stats(), oracle_dev.frame_stats()
+    assert sg.rays_closest + sg.rays_shadow == so.rays_closest

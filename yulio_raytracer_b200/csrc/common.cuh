@@ -160,12 +160,13 @@ struct GeomRec {                 // one per geomID (= one committed shape primit
     int pad;
 };
 
-enum MaterialType { MAT_NONE = 0, MAT_MATTE, MAT_OBJ, MAT_UBER, MAT_MATTE_TEXTURED, MAT_DIELECTRIC, MAT_THIN_DIELECTRIC, MAT_MIRROR };
+enum MaterialType { MAT_NONE = 0, MAT_MATTE, MAT_OBJ, MAT_UBER, MAT_MATTE_TEXTURED, MAT_DIELECTRIC, MAT_THIN_DIELECTRIC, MAT_MIRROR,
+                    MAT_PLASTIC, MAT_METAL, MAT_BRUSHED_METAL, MAT_METALLIC_PAINT, MAT_VELVET };   // from MAT_PLASTIC on: the EXT shading kernel
 struct MaterialRec {
     int type;
     int tex[5];                  // texture table indices or -1 (Obj: map_d, map_Kd, map_Ks, map_Ns, map_Bump; others: [0] = Kd)
     float s0x, s0y, dsx, dsy;
-    Col c0, c1;                  // Matte/Mirror: reflectance; Obj: Kd, Ks; Uber: diffuse; ThinDielectric: transmission
+    Col c0, c1, c2;              // Matte/Mirror: reflectance; Obj: Kd, Ks; Uber: diffuse; ThinDielectric: transmission; Metal: reflectance, eta, k
     float f[6];                  // Obj: d, Ns; Uber: eta, roughness, reflectivity, rcpRoughness; Thin: eta, thickness, transparency
     // Dielectric media (materials/dielectric.h:31-45)
     Col tOutside, tInside; float etaOutside, etaInside;
@@ -202,6 +203,7 @@ struct SceneData {
     int numGeoms, numLights, numEnvLights, numPrecomputed;
     int envLightIdx[8];
     int hasMedia;                // some material is a medium interface (Dielectric): path media must be tracked
+    int hasExtMaterials;         // some material needs the EXT shading kernel (MAT_PLASTIC and later)
 };
 
 struct IntegratorData {          // integrators/pathtraceintegrator.cpp:21-33

@@ -266,8 +266,21 @@ static std::shared_ptr<MaterialObj> make_material(const std::string& type, const
         m->textures[3] = p.getTexture("map_Ns"); r.f[1] = p.getFloat("Ns", 10.0f);
         m->textures[4] = p.getTexture("map_Bump");
         if (m->textures[4]) throw std::runtime_error("device_cuda: Obj material with map_Bump is not supported");
-    } else throw std::runtime_error("device_cuda: material type '" + type + "' is outside the supported hot path "
-                                    "(Matte, Mirror, MatteTextured, Uber, Dielectric/Glass, ThinDielectric/ThinGlass, Obj)");
+    } else if (type == "plastic") {                                                                        // plastic.h:31-36
+        r.type = MAT_PLASTIC; r.c0 = p.getV3("pigmentColor", V3(1.f)); r.f[0] = p.getFloat("eta", 1.4f); r.f[1] = p.getFloat("roughness", 0.01f); r.f[3] = rcpf(r.f[1]);
+    } else if (type == "metal") {                                                                          // metal.h:35-41
+        r.type = MAT_METAL; r.c0 = p.getV3("reflectance", V3(1.f)); r.c1 = p.getV3("eta", V3(1.4f)); r.c2 = p.getV3("k", V3(0.f));
+        r.f[1] = p.getFloat("roughness", 0.01f); r.f[3] = rcpf(r.f[1]);
+    } else if (type == "brushedmetal") {                                                                   // brushedmetal.h:36-44
+        r.type = MAT_BRUSHED_METAL; r.c0 = p.getV3("reflectance", V3(1.f)); r.c1 = p.getV3("eta", V3(1.4f)); r.c2 = p.getV3("k", V3(0.f));
+        r.f[1] = p.getFloat("roughnessX", 0.01f); r.f[2] = p.getFloat("roughnessY", 0.01f); r.f[3] = rcpf(r.f[1]); r.f[4] = rcpf(r.f[2]);
+    } else if (type == "metallicpaint") {                                                                  // metallicpaint.h:35-44
+        r.type = MAT_METALLIC_PAINT; r.c0 = p.getV3("shadeColor", V3(1.f)); r.c1 = p.getV3("glitterColor", V3(0.f));
+        r.f[1] = p.getFloat("glitterSpread", 1.0f); r.f[0] = p.getFloat("eta", 1.4f);
+    } else if (type == "velvet") {                                                                         // velvet.h:31-36
+        r.type = MAT_VELVET; r.c0 = p.getV3("reflectance", V3(1.f)); r.f[0] = p.getFloat("backScattering", 0.f);
+        r.c1 = p.getV3("horizonScatteringColor", V3(1.f)); r.f[1] = p.getFloat("horizonScatteringFallOff", 0.f);
+    } else throw std::runtime_error("unknown material type: " + type);                                    // singleray_device.cpp:280
     return m;
 }
 

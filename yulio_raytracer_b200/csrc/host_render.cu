@@ -369,6 +369,7 @@ void scene_commit(yrt_device* dev, SceneHandle* sc) {
     d.materials = sc->materials.p; d.textures = sc->textures.p; d.lights = sc->lights.p;
     d.numGeoms = (int)geoms.size(); d.numLights = (int)lights.size();
     d.hasMedia = 0; for (const MaterialRec& m : materials) d.hasMedia |= m.isMediaInterface;
+    d.hasExtMaterials = 0; for (const MaterialRec& m : materials) d.hasExtMaterials |= m.type >= MAT_PLASTIC ? 1 : 0;
     sc->data = d;
     scene_bounds(sc);
     sc->committed = true; sc->dirty = false;

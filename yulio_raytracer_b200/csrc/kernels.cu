@@ -303,8 +303,9 @@ __device__ __forceinline__ uint32_t warp_alloc(uint32_t* counter, uint32_t count
 #else
 #define SHADE_BARRIER2()
 #endif
-__global__ void __launch_bounds__(YRT_SHADE_THREADS, YRT_SHADE_MINBLOCKS) k_shade(FrameConst fc, WavefrontBuffers wb, int queueSel, uint32_t pixelBegin, int depth) {
-    __shared__ float smLobes[YRT_MAX_LOBES * YRT_LOBE_WORDS * YRT_SHADE_THREADS], smCand[YRT_MAX_LOBES * YRT_CAND_WORDS * YRT_SHADE_THREADS];
+template <bool EXT>
+__global__ void __launch_bounds__(YRT_SHADE_THREADS, EXT ? 4 : YRT_SHADE_MINBLOCKS) k_shade(FrameConst fc, WavefrontBuffers wb, int queueSel, uint32_t pixelBegin, int depth) {
+    __shared__ float smLobes[YRT_MAX_LOBES * LobesT<EXT>::WORDS * YRT_SHADE_THREADS], smCand[YRT_MAX_LOBES * YRT_CAND_WORDS * YRT_SHADE_THREADS];
     const uint32_t* __restrict__ queue = queueSel ? wb.queueB : wb.queueA;
     uint32_t* __restrict__ nextQueue = queueSel ? wb.queueA : wb.queueB;
     const uint32_t n = wb.counters[queueSel];
@@ -318,7 +319,7 @@ __global__ void __launch_bounds__(YRT_SHADE_THREADS, YRT_SHADE_MINBLOCKS) k_shad
         SHADE_BARRIER();
         bool alive = false, needLights = false;
         uint32_t pid = 0, flags = 0;
-        DG dg; Lobes lobes; lobes.s = &smLobes[threadIdx.x]; lobes.cand = &smCand[threadIdx.x]; lobes.stride = YRT_SHADE_THREADS; lobes.n = 0; V3 wo(0.f); Col thr(0.f); const float* rec = nullptr; float fx = 0, fy = 0;
+        DG dg; LobesT<EXT> lobes; lobes.s = &smLobes[threadIdx.x]; lobes.cand = &smCand[threadIdx.x]; lobes.stride = YRT_SHADE_THREADS; lobes.n = 0; V3 wo(0.f); Col thr(0.f); const float* rec = nullptr; float fx = 0, fy = 0;
         float4 d4 = make_float4(0, 0, 0, 0), m4 = make_float4(1, 1, 1, 1); float hitT = 0.f;
         if (valid) {
             pid = queue[i];
@@ -352,10 +353,10 @@ __global__ void __launch_bounds__(YRT_SHADE_THREADS, YRT_SHADE_MINBLOCKS) k_shad
                     for (int e = 0; e < sc.numEnvLights; e++) L += thr * env_Le(sc, sc.lights[sc.envLightIdx[e]], wo);
                 }
             } else {
-                post_intersect(sc, org, dir, hA.x, hA.y, hA.z, geomID, __float_as_int(hB.w), f4v(hB), dg);
+                post_intersect<EXT>(sc, org, dir, hA.x, hA.y, hA.z, geomID, __float_as_int(hB.w), f4v(hB), dg);
                 bool backfacing = false;
                 if (dot(dg.Ng, dir) > 0.f) { backfacing = true; dg.Ng = -dg.Ng; dg.Ns = -dg.Ns; }   // :95-98
-                if (dg.material >= 0) material_shade(sc, sc.materials[dg.material], dg, Col(m4.x, m4.y, m4.z), m4.w, lobes);
+                if (dg.material >= 0) material_shade<EXT>(sc, sc.materials[dg.material], dg, Col(m4.x, m4.y, m4.z), m4.w, lobes);
                 if (!(flags & FLAG_IGNORE_VISIBLE_LIGHTS) && dg.areaLight >= 0 && !backfacing) { loadL(); L += thr * sc.lights[dg.areaLight].L; }  // :114-115
                 for (int k = 0; k < lobes.n; k++) needLights |= (lobes.type(k) & BR_DIFFUSE) != 0;
                 alive = true;
@@ -454,7 +455,9 @@ __global__ void __launch_bounds__(YRT_SHADE_THREADS, YRT_SHADE_MINBLOCKS) k_shad
     if ((threadIdx.x & 31) == 0 && shadowRays) atomicAdd(&wb.stats[1], (unsigned long long)shadowRays);
 }
 void launch_shade(const FrameConst& fc, const WavefrontBuffers& wb, int queueSel, uint32_t pixelBegin, int depth, LaunchCfg lc) {
-    k_shade<<<lc.blocks, YRT_SHADE_THREADS, 0, lc.stream>>>(fc, wb, queueSel, pixelBegin, depth);
+    // scenes with Plastic / Metal / BrushedMetal / MetallicPaint / Velvet take the EXT instantiation (wider lobe records, tangents)
+    if (fc.scene.hasExtMaterials) k_shade<true><<<lc.blocks, YRT_SHADE_THREADS, 0, lc.stream>>>(fc, wb, queueSel, pixelBegin, depth);
+    else k_shade<false><<<lc.blocks, YRT_SHADE_THREADS, 0, lc.stream>>>(fc, wb, queueSel, pixelBegin, depth);
 }
 
 // adds the unoccluded light contributions of this bounce in light order (one thread per path that sampled lights: its

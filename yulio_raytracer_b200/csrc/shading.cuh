@@ -45,16 +45,19 @@ YRT_D Col4 tex_get(const TextureRec& t, float px, float py) {
 }
 
 // ---- differential geometry -----------------------------------------------------------------
-struct DG { V3 P, Ng, Ns; float s, t, error; int material, areaLight, illumMask, shadowMask; };
+struct DG { V3 P, Ng, Ns; float s, t, error; int material, areaLight, illumMask, shadowMask; V3 Tx, Ty; };   // Tx, Ty: only the EXT instantiation
 
 // TriangleMeshFull::postIntersect      shapes/trianglemesh_full.cpp:207-275
 // TriangleMeshWithNormals::postIntersect shapes/trianglemesh_normals.cpp:140-162
 // Triangle::postIntersect              shapes/triangle.h:84-93
-// (Tx/Ty are not produced: no material on the hot path reads them — Obj bump maps are rejected at commit.)
+// Tx/Ty (trianglemesh_full.cpp:252-270, trianglemesh_normals.cpp:154-155) are produced by the EXT instantiation only: BrushedMetal is
+// the one material that reads them. Meshes with tangent arrays are not supported (the arrays are ignored).
+template <bool EXT>
 YRT_D void post_intersect(const SceneData& sc, V3 org, V3 dir, float t, float u, float v, int geomID, int primID, V3 rayNg, DG& dg) {
     const GeomRec g = sc.geoms[geomID];
     dg.material = g.material; dg.areaLight = g.areaLight; dg.illumMask = g.illumMask; dg.shadowMask = g.shadowMask;
     dg.P = org + t * dir;
+    if (EXT) { dg.Tx = V3(0.f); dg.Ty = V3(0.f); }
     if (g.type == MESH_TRIANGLE) { dg.Ng = g.triNg; dg.Ns = g.triNg; dg.s = u; dg.t = v; }
     else {
         dg.Ng = normalize(rayNg);
@@ -72,6 +75,22 @@ YRT_D void post_intersect(const SceneData& sc, V3 org, V3 dir, float t, float u,
             if (dot(Ns, dg.Ng) < 0) Ns = -Ns;
             dg.Ns = Ns;
         } else dg.Ns = dg.Ng;
+        if (EXT) {
+            const float4 q0 = sc.positions[g.vtxBase + tri.x], q1 = sc.positions[g.vtxBase + tri.y], q2 = sc.positions[g.vtxBase + tri.z];
+            const V3 p0(q0.x, q0.y, q0.z), dPdu = V3(q1.x, q1.y, q1.z) - p0, dPdv = V3(q2.x, q2.y, q2.z) - p0;
+            if (g.type == MESH_NORMALS) { dg.Tx = dPdu; dg.Ty = dPdv; }
+            else {
+                float dsdu = 1.f, dtdu = 0.f, dsdv = 0.f, dtdv = 1.f;
+                if (g.uvBase != YRT_NO_ATTR) {
+                    const float2 st0 = sc.uvs[g.uvBase + tri.x], st1 = sc.uvs[g.uvBase + tri.y], st2 = sc.uvs[g.uvBase + tri.z];
+                    dsdu = st1.x - st0.x; dtdu = st1.y - st0.y; dsdv = st2.x - st0.x; dtdv = st2.y - st0.y;
+                }
+                const V3 dPds = normalize(dPdu * dtdv - dPdv * dtdu);
+                dg.Tx = normalize(dPds - dot(dPds, dg.Ns) * dg.Ns);
+                const V3 dPdt = normalize(dPdv * dsdu - dPdu * dsdv);
+                dg.Ty = normalize(dPdt - dot(dPdt, dg.Ns) * dg.Ns);
+            }
+        }
     }
     dg.error = rmax(fabsf(t), reduce_max(vabs(dg.P)));
 }
@@ -87,28 +106,36 @@ YRT_D void post_intersect(const SceneData& sc, V3 org, V3 dir, float t, float u,
 #define BR_ALL 0xFFFFFFFFu
 
 enum LobeKind { LOBE_LAMBERTIAN, LOBE_TRANSMISSION, LOBE_SPECULAR, LOBE_REFLECTION, LOBE_DIEL_REFL, LOBE_DIEL_TRANS,
-                LOBE_THIN_DIEL_TRANS, LOBE_CONST_DIEL_TRANS, LOBE_MICROFACET_UBER };
-struct Lobe { int kind; uint32_t type; Col c; float a, b; };   // meaning of c,a,b depends on kind
+                LOBE_THIN_DIEL_TRANS, LOBE_CONST_DIEL_TRANS, LOBE_MICROFACET_UBER,
+                // EXT instantiation only (Plastic, Metal, BrushedMetal, MetallicPaint, Velvet):
+                LOBE_CONDUCTOR, LOBE_MICROFACET_METAL, LOBE_MICROFACET_ANISO, LOBE_LAYER_LAMBERT, LOBE_LAYER_GLITTER, LOBE_MINNAERT, LOBE_VELVETY };
+struct Lobe { int kind; uint32_t type; Col c; float a, b; Col e, k; float x; };   // meaning of c,a,b depends on kind; e,k,x: EXT kinds
 // The lobes of one hit and the per-lobe candidates of CompositedBRDF::sample are indexed per lane at run time. As local arrays
 // they cost uncoalesced local-memory traffic (ncu r1: 2.7 of 32 bytes used per sector); they live in shared memory instead, word
 // w of slot i of thread t at s[(i * WORDS + w) * stride + t]: bank = t, conflict-free for any per-lane i.
 #define YRT_MAX_LOBES 3
 #define YRT_LOBE_WORDS 7
+#define YRT_LOBE_WORDS_EXT 14
 #define YRT_CAND_WORDS 9
-struct Lobes {
+template <bool EXT> struct LobesT {
+    static constexpr int WORDS = EXT ? YRT_LOBE_WORDS_EXT : YRT_LOBE_WORDS;
     float* s; float* cand; int stride; int n;
     YRT_D Lobe get(int i) const {
-        const float* p = s + i * YRT_LOBE_WORDS * stride; Lobe l;
+        const float* p = s + i * WORDS * stride; Lobe l;
         l.kind = __float_as_int(p[0]); l.type = __float_as_uint(p[stride]); l.c = Col(p[2 * stride], p[3 * stride], p[4 * stride]); l.a = p[5 * stride]; l.b = p[6 * stride];
+        if (EXT) { l.e = Col(p[7 * stride], p[8 * stride], p[9 * stride]); l.k = Col(p[10 * stride], p[11 * stride], p[12 * stride]); l.x = p[13 * stride]; }
+        else { l.e = Col(0.f); l.k = Col(0.f); l.x = 0.f; }
         return l;
     }
-    YRT_D uint32_t type(int i) const { return __float_as_uint(s[(i * YRT_LOBE_WORDS + 1) * stride]); }
+    YRT_D uint32_t type(int i) const { return __float_as_uint(s[(i * WORDS + 1) * stride]); }
 };
-YRT_D void add_lobe(Lobes& L, int kind, uint32_t type, Col c, float a = 0.f, float b = 0.f) {
+template <bool EXT>
+YRT_D void add_lobe(LobesT<EXT>& L, int kind, uint32_t type, Col c, float a = 0.f, float b = 0.f, Col e = Col(0.f), Col k = Col(0.f), float x = 0.f) {
     if (L.n < YRT_MAX_LOBES) {
-        float* p = L.s + L.n * YRT_LOBE_WORDS * L.stride; L.n++;
+        float* p = L.s + L.n * LobesT<EXT>::WORDS * L.stride; L.n++;
         p[0] = __int_as_float(kind); p[L.stride] = __uint_as_float(type); p[2 * L.stride] = c.x; p[3 * L.stride] = c.y; p[4 * L.stride] = c.z;
         p[5 * L.stride] = a; p[6 * L.stride] = b;
+        if (EXT) { p[7 * L.stride] = e.x; p[8 * L.stride] = e.y; p[9 * L.stride] = e.z; p[10 * L.stride] = k.x; p[11 * L.stride] = k.y; p[12 * L.stride] = k.z; p[13 * L.stride] = x; }
     }
 }
 
@@ -154,9 +181,59 @@ YRT_D Sample3 power_cosine_sample_hemisphere(float u, float v, V3 N, float e) {
     return s;
 }
 
+// fresnelConductor  brdfs/optics.h:121-130
+YRT_D Col fresnel_conductor(float cosi, Col eta, Col k) {
+    const Col tmp = eta * eta + k * k;
+    const Col dpar = tmp * cosi * cosi + 2.0f * eta * cosi + Col(1.f);
+    const Col Rpar = (tmp * cosi * cosi - 2.0f * eta * cosi + Col(1.f)) * Col(rcpf(dpar.x), rcpf(dpar.y), rcpf(dpar.z));
+    const Col dper = tmp + 2.0f * eta * cosi + Col(cosi * cosi);
+    const Col Rper = (tmp - 2.0f * eta * cosi + Col(cosi * cosi)) * Col(rcpf(dper.x), rcpf(dper.y), rcpf(dper.z));
+    return 0.5f * (Rpar + Rper);
+}
+
+// AnisotropicPowerCosineDistribution  brdfs/microfacet/anisotropic_power_cosine_distribution.h:28-76 (dx = dg.Tx, dy = dg.Ty, dz = dg.Ns)
+YRT_D float aniso_eval(const DG& dg, float nx, float ny, V3 wh) {
+    const float norm2 = sqrtf((nx + 2) * (ny + 2)) * YRT_ONE_OVER_TWO_PI;
+    const float cosPhiH = dot(wh, dg.Tx), sinPhiH = dot(wh, dg.Ty), cosThetaH = dot(wh, dg.Ns);
+    const float R = cosPhiH * cosPhiH + sinPhiH * sinPhiH;
+    if (R == 0.0f) return norm2;
+    const float n = (nx * (cosPhiH * cosPhiH) + ny * (sinPhiH * sinPhiH)) * rcpf(R);
+    return norm2 * YRT_POWF(fabsf(cosThetaH), n);
+}
+YRT_D Sample3 aniso_sample(const DG& dg, float nx, float ny, float sx, float sy) {
+    const float norm1 = sqrtf((nx + 1) * (ny + 1)) * YRT_ONE_OVER_TWO_PI;
+    const float phi = YRT_TWO_PI * sx;
+    const float sinPhi0 = sqrtf(nx + 1) * YRT_SINF(phi), cosPhi0 = sqrtf(ny + 1) * YRT_COSF(phi);
+    const float norm = rsqrtf_exact(sinPhi0 * sinPhi0 + cosPhi0 * cosPhi0);
+    const float sinPhi = sinPhi0 * norm, cosPhi = cosPhi0 * norm;
+    const float n = nx * (cosPhi * cosPhi) + ny * (sinPhi * sinPhi);
+    const float cosTheta = YRT_POWF(sy, rcpf(n + 1));
+    const float sinTheta = sqrtf(rmax(0.f, 1.f - cosTheta * cosTheta));
+    Sample3 s; s.pdf = norm1 * YRT_POWF(cosTheta, n);
+    const V3 h(cosPhi * sinTheta, sinPhi * sinTheta, cosTheta);
+    s.v = h.x * dg.Tx + h.y * dg.Ty + h.z * dg.Ns;
+    return s;
+}
+
+// Microfacet<Fresnel, Distribution>::eval  brdfs/microfacet.h:43-58 with F and D supplied by the caller's lobe kind
+template <bool EXT> YRT_D Col lobe_eval(const Lobe& l, V3 wo, const DG& dg, V3 wi);
+YRT_D Col microfacet_eval(const Lobe& l, V3 wo, const DG& dg, V3 wi, int fresnelKind /*0 dielectric l.a, 1 conductor l.e,l.k*/, int distKind /*0 power cosine n, 1 anisotropic*/, float n, float ny) {
+    if (dot(wi, dg.Ng) <= 0) return Col(0.f);
+    const float cosThetaO = dot(wo, dg.Ns), cosThetaI = dot(wi, dg.Ns);
+    if (cosThetaI <= 0.0f || cosThetaO <= 0.0f) return Col(0.f);
+    const V3 wh = normalize(wi + wo);
+    const float cosThetaH = dot(wh, dg.Ns), cosTheta = dot(wi, wh);
+    const Col F = fresnelKind == 0 ? Col(fresnel_diel(cosTheta, l.a)) : fresnel_conductor(cosTheta, l.e, l.k);
+    const float D = distKind == 0 ? ((n + 2) * YRT_ONE_OVER_TWO_PI) * YRT_POWF(fabsf(dot(wh, dg.Ns)), n) : aniso_eval(dg, n, ny, wh);
+    const float G = rmin(rmin(1.0f, 2.0f * cosThetaH * cosThetaO * rcpf(cosTheta)), 2.0f * cosThetaH * cosThetaI * rcpf(cosTheta));
+    return l.c * D * G * F * rcpf(4.0f * cosThetaO);
+}
+
 // Lambertian::eval lambertian.h:35-37; Specular::eval specular.h:34-38; Microfacet::eval microfacet.h:43-58
 // (+ PowerCosineDistribution::eval power_cosine_distribution.h:35-39, FresnelDielectric::eval fresnel.h:80-82);
+// EXT: DielectricLayer::eval dielectriclayer.h:44-56, Minnaert::eval minnaert.h:33-37, Velvety::eval velvety.h:33-39;
 // all specular lobes evaluate to zero.
+template <bool EXT>
 YRT_D Col lobe_eval(const Lobe& l, V3 wo, const DG& dg, V3 wi) {
     switch (l.kind) {
     case LOBE_LAMBERTIAN: return l.c * YRT_ONE_OVER_PI * rclamp(dot(wi, dg.Ns));
@@ -166,28 +243,65 @@ YRT_D Col lobe_eval(const Lobe& l, V3 wo, const DG& dg, V3 wi) {
         return l.c * (l.a + 2) * (1.0f / (2.0f * YRT_PI)) * YRT_POWF(dot(r, wi), l.a) * rclamp(dot(wi, dg.Ns));
     }
     case LOBE_REFLECTION: return l.c;
-    case LOBE_MICROFACET_UBER: {
-        if (dot(wi, dg.Ng) <= 0) return Col(0.f);
+    case LOBE_MICROFACET_UBER: return microfacet_eval(l, wo, dg, wi, 0, 0, l.b, 0.f);      // l.a = etai/etat, l.b = n
+    default: break;
+    }
+    if (EXT) switch (l.kind) {
+    case LOBE_MICROFACET_METAL: return microfacet_eval(l, wo, dg, wi, 1, 0, l.a, 0.f);    // l.a = n
+    case LOBE_MICROFACET_ANISO: return microfacet_eval(l, wo, dg, wi, 1, 1, l.a, l.b);    // l.a = nx, l.b = ny
+    case LOBE_MINNAERT: {
+        const float cosThetaI = rclamp(dot(wi, dg.Ns));
+        const float backScatter = YRT_POWF(rclamp(dot(wo, wi)), l.a);
+        return l.c * backScatter * cosThetaI * rcpf(YRT_PI);                             // Color / float = a * rcp(b)  (color_sse.h:162)
+    }
+    case LOBE_VELVETY: {
+        const float cosThetaO = rclamp(dot(wo, dg.Ns)), cosThetaI = rclamp(dot(wi, dg.Ns));
+        const float sinThetaO = sqrtf(1.0f - cosThetaO * cosThetaO);
+        const float horizonScatter = YRT_POWF(sinThetaO, l.a);
+        return l.c * horizonScatter * cosThetaI * rcpf(YRT_PI);
+    }
+    case LOBE_LAYER_LAMBERT: case LOBE_LAYER_GLITTER: {                                    // l.a = etait, l.b = etati, T = one
         const float cosThetaO = dot(wo, dg.Ns), cosThetaI = dot(wi, dg.Ns);
         if (cosThetaI <= 0.0f || cosThetaO <= 0.0f) return Col(0.f);
-        const V3 wh = normalize(wi + wo);
-        const float cosThetaH = dot(wh, dg.Ns), cosTheta = dot(wi, wh);
-        const Col F = Col(fresnel_diel(cosTheta, l.a));                               // l.a = etai/etat
-        const float D = ((l.b + 2) * YRT_ONE_OVER_TWO_PI) * YRT_POWF(fabsf(dot(wh, dg.Ns)), l.b);   // l.b = n
-        const float G = rmin(rmin(1.0f, 2.0f * cosThetaH * cosThetaO * rcpf(cosTheta)), 2.0f * cosThetaH * cosThetaI * rcpf(cosTheta));
-        return l.c * D * G * F * rcpf(4.0f * cosThetaO);
+        float cosThetaO1, cosThetaI1;
+        const V3 wo1 = refract_v(wo, dg.Ns, l.a, cosThetaO, cosThetaO1).v, wi1 = refract_v(wi, dg.Ns, l.a, cosThetaI, cosThetaI1).v;
+        const float Fi = 1.0f - fresnel_diel3(cosThetaI, cosThetaI1, l.a);
+        Col Fg;
+        if (l.kind == LOBE_LAYER_LAMBERT) Fg = l.c * YRT_ONE_OVER_PI * rclamp(dot(-wi1, dg.Ns));
+        else Fg = microfacet_eval(l, -wo1, dg, -wi1, 1, 0, l.x, 0.f);                      // glitter: Microfacet<FresnelConductor, PowerCosine(l.x)>
+        const float Fo = 1.0f - fresnel_diel3(cosThetaO, cosThetaO1, l.a);
+        return Col(Fo) * Fg * Fi;
     }
-    default: return Col(0.f);
+    default: break;
     }
+    return Col(0.f);
 }
 
 // The per-lobe sample() methods: lambertian.h:39-41, specular.h:40-42, transmission.h:38-40, reflection.h:40-43,
 // dielectric.h:39-45 (DielectricReflection), :80-87 (DielectricTransmission), :122-132 (ThinDielectricTransmission),
 // :185-189 (ConstDielectricTransmission), microfacet.h:60-67.
+// Microfacet::sample  microfacet.h:60-67 around a sampled half vector
+YRT_D Col microfacet_finish(const Lobe& l, V3 wo, const DG& dg, Sample3& wi, Sample3 wh, int fresnelKind, int distKind, float n, float ny) {
+    wi.v = reflect_v(wo, wh.v); wi.pdf = wh.pdf * rcpf(4.0f * fabsf(dot(wo, wh.v)));
+    if (dot(wi.v, dg.Ns) <= 0.0f) return Col(0.f);
+    return microfacet_eval(l, wo, dg, wi.v, fresnelKind, distKind, n, ny);
+}
+// PowerCosineDistribution::sample  power_cosine_distribution.h:43-51
+YRT_D Sample3 power_cosine_half_vector(const DG& dg, float n, float sx, float sy) {
+    const float phi = YRT_TWO_PI * sx;
+    const float cosPhi = YRT_COSF(phi), sinPhi = YRT_SINF(phi);
+    const float cosTheta = YRT_POWF(sy, rcpf(n + 1));
+    const float sinTheta = sqrtf(rmax(0.f, 1.f - cosTheta * cosTheta));
+    Sample3 wh; wh.v = xfmVector(frame(dg.Ns), V3(cosPhi * sinTheta, sinPhi * sinTheta, cosTheta));
+    wh.pdf = ((n + 1) * YRT_ONE_OVER_TWO_PI) * YRT_POWF(cosTheta, n);
+    return wh;
+}
+
+template <bool EXT>
 YRT_D Col lobe_sample(const Lobe& l, V3 wo, const DG& dg, Sample3& wi, float sx, float sy) {
     switch (l.kind) {
-    case LOBE_LAMBERTIAN: wi = cosine_sample_hemisphere(sx, sy, dg.Ns); return lobe_eval(l, wo, dg, wi.v);
-    case LOBE_SPECULAR: wi = power_cosine_sample_hemisphere(sx, sy, reflect_v(wo, dg.Ns), l.a); return lobe_eval(l, wo, dg, wi.v);
+    case LOBE_LAMBERTIAN: wi = cosine_sample_hemisphere(sx, sy, dg.Ns); return lobe_eval<EXT>(l, wo, dg, wi.v);
+    case LOBE_SPECULAR: wi = power_cosine_sample_hemisphere(sx, sy, reflect_v(wo, dg.Ns), l.a); return lobe_eval<EXT>(l, wo, dg, wi.v);
     case LOBE_TRANSMISSION: wi.v = -wo; wi.pdf = 1.0f; return l.c;
     case LOBE_REFLECTION: wi.v = reflect_v(wo, dg.Ns); wi.pdf = 1.0f; return l.c;
     case LOBE_DIEL_REFL: {
@@ -217,39 +331,62 @@ YRT_D Col lobe_sample(const Lobe& l, V3 wo, const DG& dg, Sample3& wi, float sx,
     case LOBE_MICROFACET_UBER: {
         wi.v = V3(0.f); wi.pdf = 0.f;
         if (dot(wo, dg.Ns) <= 0.0f) return Col(0.f);
-        // PowerCosineDistribution::sample  power_cosine_distribution.h:43-51
-        const float phi = YRT_TWO_PI * sx;
-        const float cosPhi = YRT_COSF(phi), sinPhi = YRT_SINF(phi);
-        const float cosTheta = YRT_POWF(sy, rcpf(l.b + 1));
-        const float sinTheta = sqrtf(rmax(0.f, 1.f - cosTheta * cosTheta));
-        const V3 wh = xfmVector(frame(dg.Ns), V3(cosPhi * sinTheta, sinPhi * sinTheta, cosTheta));
-        const float whPdf = ((l.b + 1) * YRT_ONE_OVER_TWO_PI) * YRT_POWF(cosTheta, l.b);
-        wi.v = reflect_v(wo, wh); wi.pdf = whPdf * rcpf(4.0f * fabsf(dot(wo, wh)));
-        if (dot(wi.v, dg.Ns) <= 0.0f) return Col(0.f);
-        return lobe_eval(l, wo, dg, wi.v);
+        return microfacet_finish(l, wo, dg, wi, power_cosine_half_vector(dg, l.b, sx, sy), 0, 0, l.b, 0.f);
     }
+    default: break;
     }
     wi.v = V3(0.f); wi.pdf = 0.f;
+    if (EXT) switch (l.kind) {
+    case LOBE_CONDUCTOR: wi.v = reflect_v(wo, dg.Ns); wi.pdf = 1.0f; return l.c * fresnel_conductor(dot(wo, dg.Ns), l.e, l.k);   // conductor.h:41-44
+    case LOBE_MICROFACET_METAL:
+        if (dot(wo, dg.Ns) <= 0.0f) return Col(0.f);
+        return microfacet_finish(l, wo, dg, wi, power_cosine_half_vector(dg, l.a, sx, sy), 1, 0, l.a, 0.f);
+    case LOBE_MICROFACET_ANISO:
+        if (dot(wo, dg.Ns) <= 0.0f) return Col(0.f);
+        return microfacet_finish(l, wo, dg, wi, aniso_sample(dg, l.a, l.b, sx, sy), 1, 1, l.a, l.b);
+    case LOBE_MINNAERT: case LOBE_VELVETY: wi = cosine_sample_hemisphere(sx, sy, dg.Ns); return lobe_eval<EXT>(l, wo, dg, wi.v);
+    case LOBE_LAYER_LAMBERT: case LOBE_LAYER_GLITTER: {                                    // DielectricLayer::sample  dielectriclayer.h:58-80
+        const float cosThetaO = dot(wo, dg.Ns);
+        if (cosThetaO <= 0.0f) return Col(0.f);
+        float cosThetaO1; const Sample3 wo1 = refract_v(wo, dg.Ns, l.a, cosThetaO, cosThetaO1);
+        Sample3 wi1; wi1.v = V3(0.f); wi1.pdf = 0.f; Col Fg;
+        const V3 wg = -wo1.v;
+        if (l.kind == LOBE_LAYER_LAMBERT) { wi1 = cosine_sample_hemisphere(sx, sy, dg.Ns); Fg = l.c * YRT_ONE_OVER_PI * rclamp(dot(wi1.v, dg.Ns)); }
+        else if (dot(wg, dg.Ns) <= 0.0f) Fg = Col(0.f);
+        else Fg = microfacet_finish(l, wg, dg, wi1, power_cosine_half_vector(dg, l.x, sx, sy), 1, 0, l.x, 0.f);
+        const float cosThetaI1 = dot(wi1.v, dg.Ns);
+        if (cosThetaI1 <= 0.0f) return Col(0.f);
+        float cosThetaI; const Sample3 wi0 = refract_v(-wi1.v, -dg.Ns, l.b, cosThetaI1, cosThetaI);
+        if (wi0.pdf == 0.0f) return Col(0.f);
+        wi.v = wi0.v; wi.pdf = wi1.pdf;
+        const float Fi = 1.0f - fresnel_diel3(cosThetaI, cosThetaI1, l.a);
+        const float Fo = 1.0f - fresnel_diel3(cosThetaO, cosThetaO1, l.a);
+        return Col(Fo) * Fg * Fi;
+    }
+    default: break;
+    }
     return Col(0.f);
 }
 
 // CompositedBRDF::eval  brdfs/compositedbrdf.h:74-80
-YRT_D Col lobes_eval(const Lobes& L, V3 wo, const DG& dg, V3 wi, uint32_t typeMask) {
+template <bool EXT>
+YRT_D Col lobes_eval(const LobesT<EXT>& L, V3 wo, const DG& dg, V3 wi, uint32_t typeMask) {
     Col c(0.f);
 #pragma unroll 1
-    for (int i = 0; i < L.n; i++) { const Lobe l = L.get(i); if (l.type & typeMask) c += lobe_eval(l, wo, dg, wi); }
+    for (int i = 0; i < L.n; i++) { const Lobe l = L.get(i); if (l.type & typeMask) c += lobe_eval<EXT>(l, wo, dg, wi); }
     return c;
 }
 
 // CompositedBRDF::sample  brdfs/compositedbrdf.h:119-181
-YRT_D Col lobes_sample(const Lobes& L, V3 wo, const DG& dg, Sample3& wiOut, uint32_t& typeOut, float sx, float sy, float ss, uint32_t typeMask) {
+template <bool EXT>
+YRT_D Col lobes_sample(const LobesT<EXT>& L, V3 wo, const DG& dg, Sample3& wiOut, uint32_t& typeOut, float sx, float sy, float ss, uint32_t typeMask) {
     float sum = 0.0f; int num = 0;
     const int st = L.stride;
 #pragma unroll 1
     for (int i = 0; i < L.n; i++) {
         const Lobe l = L.get(i);
         if (!(l.type & typeMask)) continue;
-        Sample3 wi; const Col c = lobe_sample(l, wo, dg, wi, sx, sy);
+        Sample3 wi; const Col c = lobe_sample<EXT>(l, wo, dg, wi, sx, sy);
         if (c == Col(0.f) || wi.pdf <= 0.0f) continue;
         const float f = (c.x + c.y + c.z) * rcpf(wi.pdf);
         sum += f;
@@ -275,7 +412,8 @@ YRT_D Col lobes_sample(const Lobes& L, V3 wo, const DG& dg, Sample3& wiOut, uint
 // ---- materials ----------------------------------------------------------------------------------
 // Matte matte.h:35-37; Obj obj.h:50-69; Uber Uber.h:34-69; MatteTextured matte_textured.h:39-41;
 // Dielectric dielectric.h:57-69; ThinDielectric thindielectric.h:44-60; Mirror mirror.h:36-38
-YRT_D void material_shade(const SceneData& sc, const MaterialRec& m, const DG& dg, Col mediumT, float mediumEta, Lobes& L) {
+template <bool EXT>
+YRT_D void material_shade(const SceneData& sc, const MaterialRec& m, const DG& dg, Col mediumT, float mediumEta, LobesT<EXT>& L) {
     L.n = 0;
     switch (m.type) {
     case MAT_MATTE: add_lobe(L, LOBE_LAMBERTIAN, BR_DIFFUSE_REFLECTION, m.c0); break;
@@ -322,6 +460,36 @@ YRT_D void material_shade(const SceneData& sc, const MaterialRec& m, const DG& d
         add_lobe(L, LOBE_THIN_DIEL_TRANS, BR_SPECULAR_TRANSMISSION, Col(logf(T.x), logf(T.y), logf(T.z)), 1.f * rcpf(eta), thickness);
         break;
     }
+    default: break;
+    }
+    if (EXT) switch (m.type) {
+    case MAT_PLASTIC: {                                                               // plastic.h:38-47
+        const float eta = m.f[0], roughness = m.f[1], rcpRoughness = m.f[3];
+        add_lobe(L, LOBE_LAYER_LAMBERT, BR_DIFFUSE_REFLECTION, m.c0, 1.0f * rcpf(eta), eta * rcpf(1.0f));
+        if (roughness == 0.0f) add_lobe(L, LOBE_DIEL_REFL, BR_SPECULAR_REFLECTION, Col(0.f), 1.0f * rcpf(eta), 1.f);
+        else add_lobe(L, LOBE_MICROFACET_UBER, BR_GLOSSY_REFLECTION, Col(1.f), 1.0f * rcpf(eta), rcpRoughness);
+        break;
+    }
+    case MAT_METAL:                                                                   // metal.h:43-50
+        if (m.f[1] == 0.0f) add_lobe(L, LOBE_CONDUCTOR, BR_SPECULAR_REFLECTION, m.c0, 0.f, 0.f, m.c1, m.c2);
+        else add_lobe(L, LOBE_MICROFACET_METAL, BR_GLOSSY_REFLECTION, m.c0, m.f[3], 0.f, m.c1, m.c2);
+        break;
+    case MAT_BRUSHED_METAL:                                                           // brushedmetal.h:46-55
+        if (m.f[1] == 0.0f || m.f[2] == 0.0f) add_lobe(L, LOBE_CONDUCTOR, BR_SPECULAR_REFLECTION, m.c0, 0.f, 0.f, m.c1, m.c2);
+        else add_lobe(L, LOBE_MICROFACET_ANISO, BR_GLOSSY_REFLECTION, m.c0, m.f[3], m.f[4], m.c1, m.c2);
+        break;
+    case MAT_METALLIC_PAINT: {                                                        // metallicpaint.h:35-62
+        const float eta = m.f[0], glitterSpread = m.f[1];
+        add_lobe(L, LOBE_DIEL_REFL, BR_SPECULAR_REFLECTION, Col(0.f), 1.0f * rcpf(eta), 1.f);
+        add_lobe(L, LOBE_LAYER_LAMBERT, BR_DIFFUSE_REFLECTION, m.c0, 1.0f * rcpf(eta), eta * rcpf(1.0f));
+        if (glitterSpread != 0 && m.c1 != Col(0.f))
+            add_lobe(L, LOBE_LAYER_GLITTER, BR_GLOSSY_REFLECTION, m.c1, 1.0f * rcpf(eta), eta * rcpf(1.0f), Col(0.62f), Col(4.8f), rcpf(glitterSpread));
+        break;
+    }
+    case MAT_VELVET:                                                                  // velvet.h:38-41
+        add_lobe(L, LOBE_MINNAERT, BR_DIFFUSE_REFLECTION, m.c0, m.f[0]);
+        add_lobe(L, LOBE_VELVETY, BR_DIFFUSE_REFLECTION, m.c1, m.f[1]);
+        break;
     default: break;
     }
 }
