@@ -169,14 +169,16 @@ YRT_D Sample3 refract_v(V3 V, V3 N, float eta, float cosi, float& cost) {
 YRT_D Sample3 cosine_sample_hemisphere(float u, float v, V3 N) {
     const float phi = YRT_TWO_PI * u;
     const float cosTheta = sqrtf(v), sinTheta = sqrtf(1.0f - v);
-    Sample3 s; s.v = xfmVector(frame(N), V3(YRT_COSF(phi) * sinTheta, YRT_SINF(phi) * sinTheta, cosTheta)); s.pdf = cosTheta * YRT_ONE_OVER_PI;
+    float sinPhi, cosPhi; YRT_SINCOS(phi, sinPhi, cosPhi);
+    Sample3 s; s.v = xfmVector(frame(N), V3(cosPhi * sinTheta, sinPhi * sinTheta, cosTheta)); s.pdf = cosTheta * YRT_ONE_OVER_PI;
     return s;
 }
 YRT_D Sample3 power_cosine_sample_hemisphere(float u, float v, V3 N, float e) {
     const float phi = YRT_TWO_PI * u;
     const float cosTheta = YRT_POWF(v, rcpf(e + 1));
     const float sinTheta = sqrtf(rmax(0.f, 1.f - cosTheta * cosTheta));
-    Sample3 s; s.v = xfmVector(frame(N), V3(YRT_COSF(phi) * sinTheta, YRT_SINF(phi) * sinTheta, cosTheta));
+    float sinPhi, cosPhi; YRT_SINCOS(phi, sinPhi, cosPhi);
+    Sample3 s; s.v = xfmVector(frame(N), V3(cosPhi * sinTheta, sinPhi * sinTheta, cosTheta));
     s.pdf = (e + 1.0f) * YRT_POWF(cosTheta, e) * YRT_ONE_OVER_TWO_PI;
     return s;
 }
@@ -203,7 +205,8 @@ YRT_D float aniso_eval(const DG& dg, float nx, float ny, V3 wh) {
 YRT_D Sample3 aniso_sample(const DG& dg, float nx, float ny, float sx, float sy) {
     const float norm1 = sqrtf((nx + 1) * (ny + 1)) * YRT_ONE_OVER_TWO_PI;
     const float phi = YRT_TWO_PI * sx;
-    const float sinPhi0 = sqrtf(nx + 1) * YRT_SINF(phi), cosPhi0 = sqrtf(ny + 1) * YRT_COSF(phi);
+    float sinP, cosP; YRT_SINCOS(phi, sinP, cosP);
+    const float sinPhi0 = sqrtf(nx + 1) * sinP, cosPhi0 = sqrtf(ny + 1) * cosP;
     const float norm = rsqrtf_exact(sinPhi0 * sinPhi0 + cosPhi0 * cosPhi0);
     const float sinPhi = sinPhi0 * norm, cosPhi = cosPhi0 * norm;
     const float n = nx * (cosPhi * cosPhi) + ny * (sinPhi * sinPhi);
@@ -289,7 +292,7 @@ YRT_D Col microfacet_finish(const Lobe& l, V3 wo, const DG& dg, Sample3& wi, Sam
 // PowerCosineDistribution::sample  power_cosine_distribution.h:43-51
 YRT_D Sample3 power_cosine_half_vector(const DG& dg, float n, float sx, float sy) {
     const float phi = YRT_TWO_PI * sx;
-    const float cosPhi = YRT_COSF(phi), sinPhi = YRT_SINF(phi);
+    float sinPhi, cosPhi; YRT_SINCOS(phi, sinPhi, cosPhi);
     const float cosTheta = YRT_POWF(sy, rcpf(n + 1));
     const float sinTheta = sqrtf(rmax(0.f, 1.f - cosTheta * cosTheta));
     Sample3 wh; wh.v = xfmVector(frame(dg.Ns), V3(cosPhi * sinTheta, sinPhi * sinTheta, cosTheta));
@@ -564,7 +567,8 @@ YRT_D Col light_sample(const LightRec& l, const DG& dg, LightSampleD& ls, float 
         const float phi = YRT_TWO_PI * sx;
         const float cosTheta = 1.0f - sy * (1.0f - YRT_COSF(l.a));
         const float sinTheta = sqrtf(rmax(0.f, 1.f - cosTheta * cosTheta));
-        ls.wi = xfmVector(frame(l.v0), V3(YRT_COSF(phi) * sinTheta, YRT_SINF(phi) * sinTheta, cosTheta));
+        float sinPhi, cosPhi; YRT_SINCOS(phi, sinPhi, cosPhi);
+        ls.wi = xfmVector(frame(l.v0), V3(cosPhi * sinTheta, sinPhi * sinTheta, cosTheta));
         ls.pdf = rcpf(4.0f * YRT_PI * (YRT_SINF(0.5f * l.a) * YRT_SINF(0.5f * l.a)));
         ls.tMax = INFINITY; return l.L;
     }
