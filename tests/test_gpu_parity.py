@@ -112,3 +112,16 @@ def test_showroom_materials(cuda_dev, oracle_dev):
     image_close(imgs[0], imgs[1])
     sg, so = cuda_dev.frame_stats(), oracle_dev.frame_stats()
     assert sg.rays_closest + sg.rays_shadow == so.rays_closest
+
+
+def test_pick_all_camera_models(cuda_dev, oracle_dev):
+    """rtPick (api/singleray_device.cpp:692-708): Camera::ray(Vec2f(x, y), Vec2f(.5, .5)) + rtcIntersect, for the pinhole and the
+    stereo cube cameras; picked points agree with the reference to the primary-ray tolerance."""
+    for make in (lambda d: scenes.cornell(d, 32, 32, 1, 2), lambda d: scenes.atrium(d, 32, 32, 1, 2, face=7, detail=4, tex_size=16)):
+        sg, so = make(cuda_dev), make(oracle_dev)
+        for x, y in ((.5, .5), (.2, .7), (.93, .11), (.01, .99)):
+            hg, pg = cuda_dev.rtPick(sg.camera, x, y, sg.scene)
+            ho, po = oracle_dev.rtPick(so.camera, x, y, so.scene)
+            assert hg == ho
+            if ho:
+                assert np.allclose(pg, po, rtol=2e-5, atol=2e-3), (pg, po)

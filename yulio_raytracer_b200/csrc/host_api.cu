@@ -13,6 +13,7 @@
 
 #include "../../include/yrt_device.h"
 #include "device_impl.hpp"
+#include "camera.cuh"
 #include "host_math.hpp"
 
 using namespace yrt;
@@ -699,10 +700,9 @@ int yrtPick(yrt_device* dev, yrt_handle camera, float x, float y, yrt_handle sce
         std::lock_guard<std::mutex> lock(dev->mutex); dev->bind();
         auto* c = cast<CameraHandle>(camera, HK_CAMERA, "camera"); auto* s = cast<SceneHandle>(scene, HK_SCENE, "scene");
         if (!c->inst) throw std::runtime_error("invalid camera value");
-        // Camera::ray(Vec2f(x,y), Vec2f(0.5,0.5)) for the pinhole model on the host; other cameras through the ray-gen kernel are not needed by rtPick callers
-        if (c->inst->type != CAM_PINHOLE) throw std::runtime_error("device_cuda: rtPick supports the pinhole camera only");
-        const Aff3& m = c->inst->p2w[0];
-        const V3 dir = normalize(x * m.l.vx + (1.0f - y) * m.l.vy + m.l.vz);
+        // Camera::ray(Vec2f(x,y), Vec2f(0.5,0.5))  (singleray_device.cpp:692-708), any camera model, evaluated on the host
+        V3 org, dir; camera_ray(*c->inst, x, y, 0.5f, 0.5f, org, dir);
+        Aff3 m; m.p = org;
         float ray[8] = {m.p.x, m.p.y, m.p.z, 0.f, dir.x, dir.y, dir.z, INFINITY};
         float hit[8]; int32_t* hi = (int32_t*)hit; hi[3] = -1;
         trace_rays(dev, s, 1, ray, hit, 1, 0, nullptr);

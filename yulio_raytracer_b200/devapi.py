@@ -291,6 +291,14 @@ class Device:
     def rtRenderFrame(self, renderer, camera, scene, tonemapper, framebuffer, accumulate=0):
         self._s("yrtRenderFrame", renderer, camera, scene, tonemapper, framebuffer, int(accumulate))
 
+    def rtPick(self, camera, x: float, y: float, scene):
+        """(hit, (px, py, pz)) — device.h:329."""
+        a, b, c = C.c_float(0), C.c_float(0), C.c_float(0)
+        r = self.lib.yrtPick(self.dev, camera, C.c_float(x), C.c_float(y), scene, C.byref(a), C.byref(b), C.byref(c))
+        if r < 0:
+            raise RuntimeError(f"rtPick: {self.last_error()}")
+        return r == 1, (a.value, b.value, c.value)
+
     # ---- convenience ---------------------------------------------------------------
     def read_framebuffer(self, fb, fmt: str, width: int, height: int) -> np.ndarray:
         """Map, copy out (honouring the reference's row strides, api/framebuffer.h:106,146,195), unmap."""
