@@ -83,8 +83,20 @@ YRT_D RayPre ray_prepare(V3 O, V3 D) {
 // 48 FADDs per node but rounds the constant at half a quantisation step; padding for it (+0.51 step) cost +16 % node visits, and
 // even the 2^15-step-bias variant (byte in mantissa bits 8..15, +1/256 step of padding) cost +7 % — bounce rays start exactly on
 // box planes of neighbouring axis-aligned geometry, so any extra dilation flips many far-plane-vs-tnear decisions. Net slower.
-YRT_D float byte_to_float(uint32_t packed, int i) {     // exact u8 -> float without I2F
-    return __uint_as_float(__byte_perm(packed, 0x4B000000u, 0x7650 + i)) - 8388608.0f;
+static __constant__ uint32_t yrt_c_magic = 0x4B000000u;   // a constant-bank operand: ptxas cannot fold it back into an immediate
+
+// exact u8 -> float without I2F: PRMT builds the float 2^23 + byte, one FADD removes the bias. `magic` is 0x4B000000 held in a register
+// (node_test reads it from the constant bank): PRMT takes one immediate, and with the constant as the immediate ptxas kept
+// re-materialising the four byte selectors into registers — ~45 extra MOV/IMAD per node test in the r1 SASS.
+YRT_D float byte_to_float(uint32_t packed, uint32_t magic, int i) {
+    uint32_t r;
+    switch (i) {       // i is a compile-time constant after unrolling: the selector is an immediate
+    case 0: asm("prmt.b32 %0, %1, %2, 0x7650;" : "=r"(r) : "r"(packed), "r"(magic)); break;
+    case 1: asm("prmt.b32 %0, %1, %2, 0x7651;" : "=r"(r) : "r"(packed), "r"(magic)); break;
+    case 2: asm("prmt.b32 %0, %1, %2, 0x7652;" : "=r"(r) : "r"(packed), "r"(magic)); break;
+    default: asm("prmt.b32 %0, %1, %2, 0x7653;" : "=r"(r) : "r"(packed), "r"(magic)); break;
+    }
+    return __uint_as_float(r) - 8388608.0f;
 }
 
 // Intersects the 8 quantised child boxes of one node; returns the CWBVH hit mask:
@@ -102,6 +114,7 @@ YRT_D uint32_t node_test(const uint4 n0, const uint4 n1, const uint4 n2, const u
     const bool nx = r.idir.x < 0.f, ny = r.idir.y < 0.f, nz = r.idir.z < 0.f;
     const uint32_t octinv4 = r.octinv * 0x01010101u;
     const float tfarPadded = tbest * (1.0f + YRT_BOX_PAD);
+    const uint32_t magic = yrt_c_magic;
     uint32_t hitmask = 0;
 #pragma unroll
     for (int half = 0; half < 2; half++) {
@@ -118,12 +131,12 @@ YRT_D uint32_t node_test(const uint4 n0, const uint4 n1, const uint4 n2, const u
         const uint32_t childBits4 = (meta4 >> 5) & 0x07070707u;
 #pragma unroll
         for (int i = 0; i < 4; i++) {
-            const float tnx = __fmaf_rn(byte_to_float(nearx, i), sx, oxn);
-            const float tny = __fmaf_rn(byte_to_float(neary, i), sy, oyn);
-            const float tnz = __fmaf_rn(byte_to_float(nearz, i), sz, ozn);
-            const float tfx = __fmaf_rn(byte_to_float(farx, i), sx, oxf);
-            const float tfy = __fmaf_rn(byte_to_float(fary, i), sy, oyf);
-            const float tfz = __fmaf_rn(byte_to_float(farz, i), sz, ozf);
+            const float tnx = __fmaf_rn(byte_to_float(nearx, magic, i), sx, oxn);
+            const float tny = __fmaf_rn(byte_to_float(neary, magic, i), sy, oyn);
+            const float tnz = __fmaf_rn(byte_to_float(nearz, magic, i), sz, ozn);
+            const float tfx = __fmaf_rn(byte_to_float(farx, magic, i), sx, oxf);
+            const float tfy = __fmaf_rn(byte_to_float(fary, magic, i), sy, oyf);
+            const float tfz = __fmaf_rn(byte_to_float(farz, magic, i), sz, ozf);
             const float tmin = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, tnear));
             const float tmax = fminf(fminf(tfx, tfy), fminf(tfz, tfarPadded));
             if (tmin <= tmax) {
