@@ -507,3 +507,80 @@ def showroom(dev, width=64, height=64, spp=16, depth=5, fmt="RGB_FLOAT32", **kw)
     prims += quad_light(dev, (213, 548.77, 227), (130, 0, 0), (0, 0, 105), (40, 40, 40)) + [ambient_light(dev, (.3, .35, .4))]
     cam = pinhole(dev, (278, 273, -800), (278, 273, 0), (0, 1, 0), 37.0, width / height)
     return _bundle(dev, prims, cam, pathtracer(dev, spp, depth, **kw), width, height, fmt)
+
+
+# ------------------------------------------------------------------------------------------------
+# The reference's randomised API stress (devices/renderer/regression.cpp:32-226): one ambient light, random objects — tiny meshes with
+# random, possibly degenerate index triples (positions with stride 16, one texcoord per vertex) or tessellated spheres — with random
+# materials of its 8 kinds and 32x32 "x*y" textures (RGB8 or float). Seeded here (the reference uses unseeded rand()). The light
+# primitive is placed after the shapes: the reference's flat scene indexes its primitive list with geomIDs counted over shapes only
+# (api/scene_flat.h:99-105,140-142), so its own order (light first) dereferences the light's null shape on the first hit.
+# ------------------------------------------------------------------------------------------------
+def _regression_image(dev, rng, width=32, height=32):
+    y, x = np.mgrid[0:height, 0:width]
+    px = np.stack([(x * y), (y * x), (x + y)], -1).astype(np.int64)
+    as_char = ((px + 128) % 256 - 128).astype(np.int8)                  # char(x * y): signed on the reference's platforms
+    if rng.random() < 0.5:
+        return dev.rtNewImage("RGB8", width, height, np.ascontiguousarray(as_char.view(np.uint8)))
+    return dev.rtNewImage("RGB_FLOAT32", width, height, np.ascontiguousarray(as_char.astype(F) / F(255.0)))
+
+
+def _regression_material(dev, rng):
+    r = lambda: float(F(rng.random()))
+    k = int(rng.integers(0, 8))
+    if k == 0:
+        return material(dev, "Matte", reflectance=(r(), r(), r()))
+    if k == 1:
+        return material(dev, "Plastic", pigmentColor=(r(), r(), r()), eta=1.0 + r(), roughness=0.1 * r())
+    if k == 2:
+        return material(dev, "Dielectric", transmission=(.5 * r() + .5, .5 * r() + .5, .5 * r() + .5), etaOutside=1.0, etaInside=1.0 + r())
+    if k == 3:
+        return material(dev, "ThinDielectric", transmission=(.5 * r() + .5, .5 * r() + .5, .5 * r() + .5), eta=1.0 + r(), thickness=.5 * r())
+    if k == 4:
+        return material(dev, "Mirror", reflectance=(.5 * r() + .5, .5 * r() + .5, .5 * r() + .5))
+    if k == 5:
+        return material(dev, "Metal", reflectance=(.5 * r() + .5, .5 * r() + .5, .5 * r() + .5), eta=(1 + r(), 1 + r(), 1 + r()),
+                        k=(.3 * r(), .3 * r(), .3 * r()), roughness=.3 * r())
+    if k == 6:
+        return material(dev, "MetallicPaint", shadeColor=(.5 * r() + .5, .5 * r() + .5, .5 * r() + .5), glitterColor=(r(), r(), r()),
+                        glitterSpread=.5 + r(), eta=1.0 + r())
+    m = dev.rtNewMaterial("MatteTextured")
+    t = dev.rtNewTexture("image")
+    dev.rtSetImage(t, "image", _regression_image(dev, rng)); dev.rtCommit(t)
+    dev.rtSetTexture(m, "Kd", t)
+    dev.rtSetFloat2(m, "s0", r(), r()); dev.rtSetFloat2(m, "ds", 5 * r(), 5 * r())
+    dev.rtCommit(m)
+    return m
+
+
+def _regression_shape(dev, rng, num_triangles):
+    if num_triangles < 20:
+        n = num_triangles
+        pos = 2.0 * rng.random(3) - 1.0
+        positions = np.zeros((n, 4), F); positions[:, :3] = pos + 0.3 * rng.random((n, 3))
+        texcoords = rng.random((n, 2)).astype(F)
+        indices = rng.integers(0, max(n, 1), (n, 3)).astype(np.int32)
+        mesh = dev.rtNewShape("trianglemesh")
+        dp, dt, di = dev.rtNewData("immutable", positions), dev.rtNewData("immutable", texcoords), dev.rtNewData("immutable", indices)
+        dev.rtSetArray(mesh, "positions", "float3", dp, n, 16, 0)
+        dev.rtSetArray(mesh, "texcoords", "float2", dt, n, 8, 0)
+        dev.rtSetArray(mesh, "indices", "int3", di, n, 12, 0)
+        dev.rtCommit(mesh)
+        return mesh
+    s = dev.rtNewShape("sphere")
+    dev.rtSetFloat3(s, "P", *(float(v) for v in 2.0 * rng.random(3) - 1.0))
+    dev.rtSetFloat1(s, "r", 0.2 * float(rng.random()))
+    dev.rtSetInt1(s, "numTheta", num_triangles // 20); dev.rtSetInt1(s, "numPhi", 20)
+    dev.rtCommit(s)
+    return s
+
+
+def regression(dev, seed, num_objects=10, num_triangles=60, width=32, height=32, spp=4, depth=4, fmt="RGB_FLOAT32"):
+    rng = np.random.default_rng(seed)
+    prims = []
+    for _ in range(num_objects):
+        s = int(rng.integers(0, num_triangles)) if num_triangles else 0
+        prims.append(dev.rtNewShapePrimitive(_regression_shape(dev, rng, s), _regression_material(dev, rng), None))
+    prims.append(ambient_light(dev, (1.0, 1.0, 1.0)))
+    cam = pinhole(dev, (0.2, 0.3, -2.6), (0, 0, 0), (0, 1, 0), 50.0, width / height)
+    return _bundle(dev, prims, cam, pathtracer(dev, spp, depth), width, height, fmt)

@@ -242,6 +242,9 @@ __device__ __forceinline__ uint32_t warp_alloc(uint32_t* counter, uint32_t count
 // The shading kernel is bound by instruction fetch; barriers keep the warps of a CTA in the same code region so that they share
 // fetched lines (measured at 1024^2: -4 % shade time on the C3 stand-in, +4 % on C2; one barrier per iteration is the
 // default, YRT_SHADE_SYNC=2 adds two more inside the iteration). Every thread executes every iteration, so the barriers are uniform.
+#ifndef YRT_SHADE_PREFETCH
+#define YRT_SHADE_PREFETCH 0
+#endif
 #ifndef YRT_SHADE_SYNC
 #define YRT_SHADE_SYNC 1
 #endif
@@ -269,6 +272,19 @@ __global__ void __launch_bounds__(YRT_SHADE_THREADS, EXT ? 4 : YRT_SHADE_MINBLOC
         const uint32_t i = it * stride + blockIdx.x * blockDim.x + threadIdx.x;
         const bool valid = i < n;
         SHADE_BARRIER();
+#if YRT_SHADE_PREFETCH
+        {   // software prefetch of the next iteration's path state: the queue entry is read now, the lines are requested at the end
+            const uint32_t in = i + stride;
+            if (in < n) {
+                const uint32_t pn = queue[in];
+                asm volatile("prefetch.global.L2 [%0];" :: "l"(&wb.hitA[pn]));
+                asm volatile("prefetch.global.L2 [%0];" :: "l"(&wb.hitB[pn]));
+                asm volatile("prefetch.global.L2 [%0];" :: "l"(&wb.rayO[pn]));
+                asm volatile("prefetch.global.L2 [%0];" :: "l"(&wb.rayD[pn]));
+                if (depth > 0) asm volatile("prefetch.global.L2 [%0];" :: "l"(&wb.thr[pn]));
+            }
+        }
+#endif
         bool alive = false, needLights = false;
         uint32_t pid = 0, flags = 0;
         DG dg; LobesT<EXT> lobes; lobes.s = &smLobes[threadIdx.x]; lobes.cand = &smCand[threadIdx.x]; lobes.stride = YRT_SHADE_THREADS; lobes.n = 0; V3 wo(0.f); Col thr(0.f); const float* rec = nullptr; float fx = 0, fy = 0;
