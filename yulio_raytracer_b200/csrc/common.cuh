@@ -168,7 +168,7 @@ struct GeomRec {                 // one per geomID (= one committed shape primit
     uint32_t vtxBase, idxBase;   // into positions and the int4 index array
     uint32_t nrmBase, uvBase;    // into normals / uvs, YRT_NO_ATTR when the mesh has none
     V3 triNg;                    // MESH_TRIANGLE: normalize(cross(v2-v0, v1-v0))  (shapes/triangle.h:43)
-    int pad;
+    int shadeClass;              // 1..14: hits whose shading follows the same code path (material kind, textured or not, lobe set)
 };
 
 enum MaterialType { MAT_NONE = 0, MAT_MATTE, MAT_OBJ, MAT_UBER, MAT_MATTE_TEXTURED, MAT_DIELECTRIC, MAT_THIN_DIELECTRIC, MAT_MIRROR,

@@ -368,6 +368,22 @@ void scene_commit(yrt_device* dev, SceneHandle* sc) {
     d.geoms = sc->geoms.p; d.positions = sc->positions.p; d.normals = sc->normals.p; d.uvs = sc->uvs.p; d.indices = sc->indices.p;
     d.materials = sc->materials.p; d.textures = sc->textures.p; d.lights = sc->lights.p;
     d.numGeoms = (int)geoms.size(); d.numLights = (int)lights.size();
+    {   // shading classes for the CTA-local regrouping of k_shade: same material kind / textured-ness / lobe set -> same class
+        std::map<uint64_t, int> classOf;
+        for (GeomRec& g : geoms) {
+            uint64_t sig = 0;
+            if (g.material >= 0) {
+                const MaterialRec& m = materials[g.material];
+                sig = (uint64_t)m.type | ((uint64_t)(m.tex[0] >= 0) << 8) | ((uint64_t)(m.tex[1] >= 0) << 9);
+                if (m.type == MAT_UBER) sig |= (uint64_t)(m.f[2] > 0.f ? 1 : (m.f[1] == 0.f ? 2 : 3)) << 10;
+                if (m.type == MAT_UBER && m.tex[0] >= 0 && sc->hostTextures[m.tex[0]].format != TEX_RGBA8 && sc->hostTextures[m.tex[0]].format != TEX_RGBA_F32) sig |= 1ull << 12;  // no alpha lobe
+            }
+            sig |= (uint64_t)(g.areaLight >= 0) << 16;
+            auto it = classOf.find(sig);
+            if (it == classOf.end()) it = classOf.emplace(sig, 1 + (int)(classOf.size() % 14)).first;
+            g.shadeClass = it->second;
+        }
+    }
     d.hasMedia = 0; for (const MaterialRec& m : materials) d.hasMedia |= m.isMediaInterface;
     d.hasExtMaterials = 0; for (const MaterialRec& m : materials) d.hasExtMaterials |= m.type >= MAT_PLASTIC ? 1 : 0;
     sc->data = d;

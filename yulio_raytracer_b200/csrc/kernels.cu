@@ -242,6 +242,11 @@ __device__ __forceinline__ uint32_t warp_alloc(uint32_t* counter, uint32_t count
 // The shading kernel is bound by instruction fetch; barriers keep the warps of a CTA in the same code region so that they share
 // fetched lines (measured at 1024^2: -4 % shade time on the C3 stand-in, +4 % on C2; one barrier per iteration is the
 // default, YRT_SHADE_SYNC=2 adds two more inside the iteration). Every thread executes every iteration, so the barriers are uniform.
+// Measured and left off (round 1): regrouping the CTA's queue entries by shading class before shading (-DYRT_SHADE_REGROUP=1) costs three
+// barriers, two dependent loads and the warp-level coalescing of the path state: shade time +8 % on the C3 stand-in, +7 % on C2.
+#ifndef YRT_SHADE_REGROUP
+#define YRT_SHADE_REGROUP 0
+#endif
 #ifndef YRT_SHADE_PREFETCH
 #define YRT_SHADE_PREFETCH 0
 #endif
@@ -261,6 +266,7 @@ __device__ __forceinline__ uint32_t warp_alloc(uint32_t* counter, uint32_t count
 template <bool EXT>
 __global__ void __launch_bounds__(YRT_SHADE_THREADS, EXT ? 4 : YRT_SHADE_MINBLOCKS) k_shade(FrameConst fc, WavefrontBuffers wb, int queueSel, uint32_t pixelBegin, int depth) {
     __shared__ float smLobes[YRT_MAX_LOBES * LobesT<EXT>::WORDS * YRT_SHADE_THREADS], smCand[YRT_MAX_LOBES * YRT_CAND_WORDS * YRT_SHADE_THREADS];
+    __shared__ uint32_t smHist[16], smPerm[YRT_SHADE_THREADS];
     const uint32_t* __restrict__ queue = queueSel ? wb.queueB : wb.queueA;
     uint32_t* __restrict__ nextQueue = queueSel ? wb.queueA : wb.queueB;
     const uint32_t n = wb.counters[queueSel];
@@ -269,28 +275,42 @@ __global__ void __launch_bounds__(YRT_SHADE_THREADS, EXT ? 4 : YRT_SHADE_MINBLOC
     const uint32_t nIter = (n + stride - 1) / stride;
     uint32_t shadowRays = 0;
     for (uint32_t it = 0; it < nIter; it++) {
-        const uint32_t i = it * stride + blockIdx.x * blockDim.x + threadIdx.x;
-        const bool valid = i < n;
+        uint32_t i = it * stride + blockIdx.x * blockDim.x + threadIdx.x;
+        bool valid = i < n;
         SHADE_BARRIER();
-#if YRT_SHADE_PREFETCH
-        {   // software prefetch of the next iteration's path state: the queue entry is read now, the lines are requested at the end
-            const uint32_t in = i + stride;
-            if (in < n) {
-                const uint32_t pn = queue[in];
-                asm volatile("prefetch.global.L2 [%0];" :: "l"(&wb.hitA[pn]));
-                asm volatile("prefetch.global.L2 [%0];" :: "l"(&wb.hitB[pn]));
-                asm volatile("prefetch.global.L2 [%0];" :: "l"(&wb.rayO[pn]));
-                asm volatile("prefetch.global.L2 [%0];" :: "l"(&wb.rayD[pn]));
-                if (depth > 0) asm volatile("prefetch.global.L2 [%0];" :: "l"(&wb.thr[pn]));
-            }
+        uint32_t pid = 0;
+        if (valid) pid = queue[i];
+#if YRT_SHADE_REGROUP
+        // Regroup the CTA's entries by shading class (counting sort over <= 16 classes in shared memory) so that the lanes of a warp
+        // run the same material code: bounce rays hit unrelated surfaces, and the heaviest paths (glossy lobes, texture fetches) ran
+        // with ~10 of 32 lanes active. The permutation stays inside the CTA's window of the queue, so the path-state accesses keep
+        // their cache-line locality. Primary hits (bounce 0) are coherent already.
+        if (depth > 0) {
+            uint32_t cls = 15u;                                  // entries past the end of the queue sort last
+            if (valid) { const int g = __float_as_int(wb.hitA[pid].w); cls = g < 0 ? 0u : (uint32_t)sc.geoms[g].shadeClass; }
+            if (threadIdx.x < 16) smHist[threadIdx.x] = 0u;
+            __syncthreads();
+            // warp-aggregated histogram: one shared-memory atomic per (warp, class) instead of one per thread
+            const unsigned peers = __match_any_sync(0xffffffffu, cls);
+            const unsigned lane = threadIdx.x & 31u;
+            const int leader = __ffs(peers) - 1;
+            uint32_t wbase = 0;
+            if ((int)lane == leader) wbase = atomicAdd(&smHist[cls], (uint32_t)__popc(peers));
+            const uint32_t rank = __shfl_sync(0xffffffffu, wbase, leader) + (uint32_t)__popc(peers & ((1u << lane) - 1u));
+            __syncthreads();
+            uint32_t base = 0;
+            for (uint32_t c = 0; c < cls; c++) base += smHist[c];
+            smPerm[base + rank] = valid ? pid : 0xffffffffu;
+            __syncthreads();
+            pid = smPerm[threadIdx.x];
+            valid = pid != 0xffffffffu;
         }
 #endif
         bool alive = false, needLights = false;
-        uint32_t pid = 0, flags = 0;
+        uint32_t flags = 0;
         DG dg; LobesT<EXT> lobes; lobes.s = &smLobes[threadIdx.x]; lobes.cand = &smCand[threadIdx.x]; lobes.stride = YRT_SHADE_THREADS; lobes.n = 0; V3 wo(0.f); Col thr(0.f); const float* rec = nullptr; float fx = 0, fy = 0;
         float4 d4 = make_float4(0, 0, 0, 0), m4 = make_float4(1, 1, 1, 1); float hitT = 0.f;
         if (valid) {
-            pid = queue[i];
             const float4 o4 = wb.rayO[pid]; d4 = wb.rayD[pid];
             const float4 hA = wb.hitA[pid], hB = wb.hitB[pid];
             // radiance so far: read (and written back) only by the vertices that add to it — misses that see the environment and hits
