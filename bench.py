@@ -288,8 +288,9 @@ def main():
     e2e_value = e2e_rays_total / e2e_total / 1e6
     ms_per_step = ms_total / args.steps
     peak, peak_src = measured_peak()
-    # dominant kernel: closest-hit traversal. Algorithmic bytes/ray = 32 (ray) + 32 (hit) + 80*Nnode + 48*Ntri
-    bpr = 64 + 80 * nbar["nodes_per_ray"] + 48 * nbar["tris_per_ray"]
+    # dominant kernel: closest-hit traversal. Algorithmic bytes/ray = 32 (ray in) + 16 (hit out: t,u,v,triangle index — SURVEY §8d planned
+    # 32, the record shrank when the shading data moved into per-triangle records) + 80*Nnode + 48*Ntri
+    bpr = 48 + 80 * nbar["nodes_per_ray"] + 48 * nbar["tris_per_ray"]
     achieved = agg["closest_rays"] * bpr / (agg["closest_ms"] * 1e-3) / 1e9 if agg["closest_ms"] > 0 else None
     roofline = {"bound": "hbm", "kernel": "k_trace_closest", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": (achieved / peak) if achieved else None, "traffic": None, "peak_source": peak_src,

@@ -30,7 +30,7 @@ static_assert(sizeof(Node8) == 80, "Node8 must be 80 bytes");
 #define YRT_BOX_PAD 9.5367431640625e-07f     // 2^-20
 #endif
 
-struct HitRec { float t, u, v; int geomID, primID; V3 Ng; };
+struct HitRec { float t, u, v; int geomID, primID; V3 Ng; uint32_t tri; };   // tri = leaf-order triangle index
 
 #if defined(__CUDACC__)
 
@@ -156,7 +156,7 @@ struct TraceCounters { uint32_t nodes, tris; };
 template <bool ANY, bool COUNT>
 YRT_D bool trace_ray(const uint4* __restrict__ nodes, const float4* __restrict__ tris, uint32_t numNodes,
                      V3 O, V3 D, float tnear, float tfar, HitRec& hit, TraceCounters* cnt) {
-    hit.geomID = -1; hit.primID = -1; hit.t = tfar;
+    hit.geomID = -1; hit.primID = -1; hit.t = tfar; hit.tri = 0xffffffffu;
     if (numNodes == 0 || !(tnear <= tfar)) return false;   // NaN tfar: no hit
     const RayPre r = ray_prepare(O, D);
     uint2 stack[YRT_STACK_SIZE];
@@ -186,7 +186,8 @@ YRT_D bool trace_ray(const uint4* __restrict__ nodes, const float4* __restrict__
         while (T.y) {
             const uint32_t bit = 31u - __clz(T.y);
             T.y &= ~(1u << bit);
-            const float4* tp = tris + 3ull * (T.x + bit);
+            const uint32_t triIdx = T.x + bit;
+            const float4* tp = tris + 3ull * triIdx;
             const float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
             if (COUNT) cnt->tris++;
             float t, u, v, den; V3 Ng;
@@ -199,7 +200,7 @@ YRT_D bool trace_ray(const uint4* __restrict__ nodes, const float4* __restrict__
             // back-face cull filter (shapes/trianglemesh_full.cpp:101-121): reject if dot(Ng, dir) <= 0
             if ((__float_as_uint(c.w) & YRT_TRI_FLAG_CULL) && den <= 0.f) continue;
             have = true; tbest = t;
-            hit.t = t; hit.u = u; hit.v = v; hit.geomID = g; hit.primID = p; hit.Ng = Ng;
+            hit.t = t; hit.u = u; hit.v = v; hit.geomID = g; hit.primID = p; hit.Ng = Ng; hit.tri = triIdx;
             if (ANY) return true;
         }
         if ((G.y & 0xff000000u) == 0) {
@@ -352,13 +353,7 @@ YRT_D void trace_stream(const uint4* __restrict__ nodes, const float4* __restric
                 if (e.y & 0xff000000u) G = e; else T = e;
             } else {
                 if (ANY) io.store_any(tag, occluded);
-                else if (bestTri == YRT_NO_TRI) io.store_closest(tag, bt, 0.f, 0.f, -1, -1, V3(0.f));
-                else {
-                    const float4* tp = tris + 3ull * bestTri;
-                    const float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
-                    const V3 p0(a.x, a.y, a.z), p1(b.x, b.y, b.z), p2(c.x, c.y, c.z);
-                    io.store_closest(tag, bt, bu, bv, __float_as_int(a.w), __float_as_int(b.w), cross(p0 - p1, p2 - p0));
-                }
+                else io.store_hit(tag, bt, bu, bv, bestTri, tris);     // bestTri == YRT_NO_TRI: miss
                 active = false;
             }
         }

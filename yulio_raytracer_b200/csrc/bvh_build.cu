@@ -303,8 +303,8 @@ __global__ void __launch_bounds__(PLOC_FINAL) k_ploc_final(uint32_t m, int radiu
 struct CollapseArgs {
     Lbvh t; int n;
     const uint32_t* sortedIdx;
-    const uint2* refs; const GeomRec* geoms; const float4* positions; const int4* indices;
-    Node8* nodes; float4* tris;
+    const uint2* refs; const GeomRec* geoms; const float4* positions; const int4* indices; const float4* normals; const float2* uvs;
+    Node8* nodes; float4* tris; float4* triShade;
     uint32_t* counters;          // [0] node counter, [1] triangle counter, [2] next-level task count
     const uint2* tasksIn; uint2* tasksOut; uint32_t numTasks; int splitLeaves;
 };
@@ -328,6 +328,10 @@ __device__ __forceinline__ uint32_t ref_leaves(const CollapseArgs& a, uint32_t r
     return n;
 }
 
+// Leaf-order triangle (48 B, traversal) + its shading record (80 B): everything postIntersect reads, gathered once at build time so that
+// the shading kernel reaches it with ONE dependent load from the hit (triangle index) instead of geometry record -> index triple ->
+// three vertices. r0 = (Ng | geomID << 2 | hasNormals | hasUV << 1), r1..r3 = (n_k | uv pieces), r4 = (uv1.y, uv2.x, uv2.y, primID).
+// Ng = normalize(cross(p0 - p1, p2 - p0)): the arithmetic of the hit record + TriangleMeshFull::postIntersect (trianglemesh_full.cpp:221).
 __device__ void write_triangle(const CollapseArgs& a, uint32_t sortedPos, uint32_t outIdx) {
     const uint2 r = a.refs[a.sortedIdx[sortedPos]];
     const GeomRec g = a.geoms[r.x];
@@ -337,6 +341,20 @@ __device__ void write_triangle(const CollapseArgs& a, uint32_t sortedPos, uint32
     o[0] = make_float4(p0.x, p0.y, p0.z, __int_as_float((int)r.x));
     o[1] = make_float4(p1.x, p1.y, p1.z, __int_as_float((int)r.y));
     o[2] = make_float4(p2.x, p2.y, p2.z, __uint_as_float(g.cull ? YRT_TRI_FLAG_CULL : 0u));
+    const V3 q0(p0.x, p0.y, p0.z), q1(p1.x, p1.y, p1.z), q2(p2.x, p2.y, p2.z);
+    V3 Ng = g.type == MESH_TRIANGLE ? g.triNg : normalize(cross(q0 - q1, q2 - q0));
+    uint32_t flags = (uint32_t)r.x << 2;
+    float4 n0 = make_float4(0, 0, 0, 0), n1 = n0, n2 = n0; float2 s0 = make_float2(0, 0), s1 = s0, s2 = s0;
+    if (g.type != MESH_TRIANGLE) {
+        if (g.nrmBase != YRT_NO_ATTR) { flags |= 1u; n0 = a.normals[g.nrmBase + t.x]; n1 = a.normals[g.nrmBase + t.y]; n2 = a.normals[g.nrmBase + t.z]; }
+        if (g.uvBase != YRT_NO_ATTR) { flags |= 2u; s0 = a.uvs[g.uvBase + t.x]; s1 = a.uvs[g.uvBase + t.y]; s2 = a.uvs[g.uvBase + t.z]; }
+    }
+    float4* h = a.triShade + 5ull * outIdx;
+    h[0] = make_float4(Ng.x, Ng.y, Ng.z, __uint_as_float(flags));
+    h[1] = make_float4(n0.x, n0.y, n0.z, s0.x);
+    h[2] = make_float4(n1.x, n1.y, n1.z, s0.y);
+    h[3] = make_float4(n2.x, n2.y, n2.z, s1.x);
+    h[4] = make_float4(s1.y, s2.x, s2.y, __int_as_float((int)r.y));
 }
 
 __global__ void k_collapse(CollapseArgs a) {
@@ -469,7 +487,7 @@ template <typename T> static T* dalloc(size_t n) { T* p = nullptr; CK(cudaMalloc
 static void dfree(void* p) { if (p) cudaFreeAsync(p, g_allocStream); }
 
 void build_bvh(const BvhBuildInput& in, BvhResult& out, cudaStream_t stream) {
-    out.nodes = nullptr; out.tris = nullptr; out.numNodes = 0; out.numTris = 0; out.buildMs = 0.f; out.launches = 0;
+    out.nodes = nullptr; out.tris = nullptr; out.triShade = nullptr; out.numNodes = 0; out.numTris = 0; out.buildMs = 0.f; out.launches = 0;
     const uint32_t n = in.numRefs;
     if (n == 0) return;
     g_allocStream = stream;
@@ -541,7 +559,7 @@ void build_bvh(const BvhBuildInput& in, BvhResult& out, cudaStream_t stream) {
 
     // worst case one BVH8 node per BVH2 internal node; shrunk to the exact size afterwards
     Node8* nodesTmp = dalloc<Node8>((size_t)ni + 1);
-    float4* tris = dalloc<float4>(3ull * n);
+    float4* tris = dalloc<float4>(3ull * n); float4* triShade = dalloc<float4>(5ull * n);
     uint32_t* counters = dalloc<uint32_t>(4);
     uint2* tasksA = dalloc<uint2>(ni + 1); uint2* tasksB = dalloc<uint2>(ni + 1);
     const uint32_t initCounters[4] = {1u, 0u, 0u, 0u};
@@ -551,8 +569,8 @@ void build_bvh(const BvhBuildInput& in, BvhResult& out, cudaStream_t stream) {
 
     CollapseArgs ca;
     ca.t = t; ca.n = (int)n; ca.sortedIdx = sortedIdx;
-    ca.refs = in.refs; ca.geoms = in.geoms; ca.positions = in.positions; ca.indices = in.indices;
-    ca.nodes = nodesTmp; ca.tris = tris; ca.counters = counters; ca.splitLeaves = in.splitLeaves;
+    ca.refs = in.refs; ca.geoms = in.geoms; ca.positions = in.positions; ca.indices = in.indices; ca.normals = in.normals; ca.uvs = in.uvs;
+    ca.nodes = nodesTmp; ca.tris = tris; ca.triShade = triShade; ca.counters = counters; ca.splitLeaves = in.splitLeaves;
     uint32_t numTasks = 1; uint2* tin = tasksA; uint2* tout = tasksB;
     uint32_t hostCounters[4];
     while (numTasks) {
@@ -572,7 +590,7 @@ void build_bvh(const BvhBuildInput& in, BvhResult& out, cudaStream_t stream) {
     CK(cudaEventRecord(e1, stream));
     CK(cudaStreamSynchronize(stream));
     CK(cudaEventElapsedTime(&out.buildMs, e0, e1));
-    out.nodes = nodes; out.tris = tris;
+    out.nodes = nodes; out.tris = tris; out.triShade = triShade;
 
     dfree(nodesTmp); dfree(counters); dfree(tasksA); dfree(tasksB);
     dfree(t.left); dfree(t.right); dfree(t.parent); dfree(t.count);

@@ -206,6 +206,7 @@ struct SceneData {
     // acceleration structure
     const void* nodes;           // BVH8 nodes, 80 B each (bvh.cuh)
     const float4* tris;          // 3 x float4 per triangle in leaf order (p0|geomID, p1|primID, p2|cull)
+    const float4* triShade;      // 5 x float4 per triangle in leaf order: what postIntersect needs (bvh_build.cu: write_triangle)
     uint32_t numNodes, numTris;
     // shading data
     const GeomRec* geoms;

@@ -67,7 +67,7 @@ struct SceneHandle : Handle {
     SceneData data{};                          // pointers below
     DevBuf<GeomRec> geoms; DevBuf<float4> positions, normals; DevBuf<float2> uvs; DevBuf<int4> indices;
     DevBuf<MaterialRec> materials; DevBuf<TextureRec> textures; DevBuf<LightRec> lights; DevBuf<uint2> refsBuf;
-    void* nodes = nullptr; float4* tris = nullptr;
+    void* nodes = nullptr; float4* tris = nullptr; float4* triShade = nullptr;
     std::vector<std::shared_ptr<ImageObj>> imagesInUse;   // keeps device pixel storage alive
     std::vector<std::shared_ptr<ImageObj>> extraImages;   // images addressable by FrameConst (backplate) appended lazily
     std::vector<TextureRec> hostTextures;

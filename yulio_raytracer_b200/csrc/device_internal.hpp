@@ -15,12 +15,14 @@ struct BvhBuildInput {
     const GeomRec* geoms;         // device
     const float4* positions;      // device
     const int4* indices;          // device
+    const float4* normals;        // device (shading normals, GeomRec::nrmBase)
+    const float2* uvs;            // device (texture coordinates, GeomRec::uvBase)
     int ploc = 1;                 // 1: PLOC hierarchy (default), 0: Karras LBVH
     int splitLeaves = 1;          // BVH8 collapse: use free child slots to split leaf children of 2-3 triangles
     int plocRadius = 8;           // PLOC neighbour search radius (positions to either side)
 };
 struct BvhResult {
-    void* nodes; float4* tris; uint32_t numNodes, numTris; float buildMs; uint32_t launches;
+    void* nodes; float4* tris; float4* triShade; uint32_t numNodes, numTris; float buildMs; uint32_t launches;
 };
 void build_bvh(const BvhBuildInput& in, BvhResult& out, cudaStream_t stream);
 
@@ -29,7 +31,7 @@ struct WavefrontBuffers {
     uint32_t capacity;            // paths per chunk
     uint32_t shadowCapacity;      // shadow rays per chunk and bounce
     float4* rayO; float4* rayD;   // org.xyz|tnear, dir.xyz|tfar
-    float4* hitA; float4* hitB;   // t,u,v,geomID | Ng.xyz,primID
+    float4* hitA;                 // t,u,v | leaf-order triangle index (-1 = miss)
     float4* thr;                  // throughput.rgb | (depth | flags << 16)
     float4* Lacc;                 // radiance accumulated along the path
     float4* medium;               // transmission.rgb | eta

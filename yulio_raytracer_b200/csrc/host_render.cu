@@ -101,8 +101,8 @@ static void image_upload(ImageObj& img, cudaStream_t s) {
 // ------------------------------------------------------------------------------------------------
 SceneHandle::~SceneHandle() { releaseDevice(); }
 void SceneHandle::releaseDevice() {
-    if (nodes) cudaFreeAsync(nodes, nullptr); if (tris) cudaFreeAsync(tris, nullptr);   // allocated from the stream-ordered pool (bvh_build.cu)
-    nodes = nullptr; tris = nullptr;
+    if (nodes) cudaFreeAsync(nodes, nullptr); if (tris) cudaFreeAsync(tris, nullptr); if (triShade) cudaFreeAsync(triShade, nullptr);   // allocated from the stream-ordered pool (bvh_build.cu)
+    nodes = nullptr; tris = nullptr; triShade = nullptr;
 }
 
 // Shape::transform  shapes/trianglemesh_full.cpp:68-90, trianglemesh_normals.cpp:42-56, triangle.h:47-49
@@ -226,12 +226,12 @@ void scene_commit(yrt_device* dev, SceneHandle* sc) {
         lap("patch");
         sc->patchSlots.clear();
         sc->releaseDevice();
-        BvhBuildInput in{sc->refsBuf.p, sc->numRefs, sc->geoms.p, sc->positions.p, sc->indices.p, dev->bvhPloc, dev->splitLeaves, dev->plocRadius};
+        BvhBuildInput in{sc->refsBuf.p, sc->numRefs, sc->geoms.p, sc->positions.p, sc->indices.p, sc->normals.p, sc->uvs.p, dev->bvhPloc, dev->splitLeaves, dev->plocRadius};
         BvhResult out{};
         build_bvh(in, out, st);
         lap("bvh");
-        sc->nodes = out.nodes; sc->tris = out.tris; sc->buildMs = out.buildMs; sc->buildLaunches = out.launches; sc->rebuildCount++;
-        sc->data.nodes = sc->nodes; sc->data.tris = sc->tris; sc->data.numNodes = out.numNodes; sc->data.numTris = out.numTris;
+        sc->nodes = out.nodes; sc->tris = out.tris; sc->triShade = out.triShade; sc->buildMs = out.buildMs; sc->buildLaunches = out.launches; sc->rebuildCount++;
+        sc->data.nodes = sc->nodes; sc->data.tris = sc->tris; sc->data.triShade = sc->triShade; sc->data.numNodes = out.numNodes; sc->data.numTris = out.numTris;
         if (dev->sortRays) scene_bounds(sc);
         sc->dirty = false;
         dev->stats.build_ms = out.buildMs; dev->stats.num_triangles = out.numTris; dev->stats.num_nodes = out.numNodes; dev->stats.bvh_builds = sc->rebuildCount;
@@ -357,14 +357,14 @@ void scene_commit(yrt_device* dev, SceneHandle* sc) {
 
     lap("upload");
     sc->releaseDevice();
-    BvhBuildInput in{dRefs.p, (uint32_t)refs.size(), sc->geoms.p, sc->positions.p, sc->indices.p, dev->bvhPloc, dev->splitLeaves, dev->plocRadius};
+    BvhBuildInput in{dRefs.p, (uint32_t)refs.size(), sc->geoms.p, sc->positions.p, sc->indices.p, sc->normals.p, sc->uvs.p, dev->bvhPloc, dev->splitLeaves, dev->plocRadius};
     BvhResult out{};
     build_bvh(in, out, st);
     YRT_CK(cudaStreamSynchronize(st));
     lap("bvh");
-    sc->nodes = out.nodes; sc->tris = out.tris; sc->buildMs = out.buildMs; sc->buildLaunches = out.launches; sc->rebuildCount++;
+    sc->nodes = out.nodes; sc->tris = out.tris; sc->triShade = out.triShade; sc->buildMs = out.buildMs; sc->buildLaunches = out.launches; sc->rebuildCount++;
 
-    d.nodes = sc->nodes; d.tris = sc->tris; d.numNodes = out.numNodes; d.numTris = out.numTris;
+    d.nodes = sc->nodes; d.tris = sc->tris; d.triShade = sc->triShade; d.numNodes = out.numNodes; d.numTris = out.numTris;
     d.geoms = sc->geoms.p; d.positions = sc->positions.p; d.normals = sc->normals.p; d.uvs = sc->uvs.p; d.indices = sc->indices.p;
     d.materials = sc->materials.p; d.textures = sc->textures.p; d.lights = sc->lights.p;
     d.numGeoms = (int)geoms.size(); d.numLights = (int)lights.size();
@@ -443,7 +443,7 @@ template <typename T> static void dev_realloc(T*& p, size_t n) { if (p) cudaFree
 
 void WavefrontStorage::ensure(uint32_t capacity, uint32_t shadowCapacity, size_t pixels) {
     if (capacity > wb.capacity) {
-        dev_realloc(wb.rayO, capacity); dev_realloc(wb.rayD, capacity); dev_realloc(wb.hitA, capacity); dev_realloc(wb.hitB, capacity);
+        dev_realloc(wb.rayO, capacity); dev_realloc(wb.rayD, capacity); dev_realloc(wb.hitA, capacity);
         dev_realloc(wb.thr, capacity); dev_realloc(wb.Lacc, capacity); dev_realloc(wb.medium, capacity);
         dev_realloc(wb.shadowPid, capacity); dev_realloc(wb.queueA, capacity); dev_realloc(wb.queueB, capacity);
         dev_realloc(wb.queueS, capacity); dev_realloc(wb.sortKeys, capacity); dev_realloc(wb.sortKeysOut, capacity);
@@ -460,7 +460,7 @@ void WavefrontStorage::ensure(uint32_t capacity, uint32_t shadowCapacity, size_t
     if (pixels > pixelSetCapacity) { dev_realloc(wb.pixelSet, pixels); pixelSetCapacity = pixels; }
 }
 void WavefrontStorage::release() {
-    void* ps[] = {wb.rayO, wb.rayD, wb.hitA, wb.hitB, wb.thr, wb.Lacc, wb.medium, wb.shadowPid, wb.queueA, wb.queueB,
+    void* ps[] = {wb.rayO, wb.rayD, wb.hitA, wb.thr, wb.Lacc, wb.medium, wb.shadowPid, wb.queueA, wb.queueB,
                   wb.shO, wb.shD, wb.shC, wb.counters, wb.stats, wb.pixelSet, wb.queueS, wb.sortKeys, wb.sortKeysOut, sortTemp};
     for (void* p : ps) if (p) cudaFree(p);
     wb = WavefrontBuffers{}; pixelSetCapacity = 0; sortTemp = nullptr; sortTempBytes = 0;
@@ -612,11 +612,11 @@ void render_frame(yrt_device* dev, RendererHandle* rh, CameraHandle* ch, SceneHa
     const uint64_t totalPaths = (uint64_t)numPixels * spp;
     if (capacity > totalPaths) capacity = totalPaths;
     if (capacity > dev->wf.wb.capacity || capacity * nl > dev->wf.wb.shadowCapacity) {
-        // growing: 128 B of path state + 48 B per (path, light) shadow slot; stay within 40 % of what is free right now
+        // growing: 112 B of path state + 48 B per (path, light) shadow slot; stay within 40 % of what is free right now
         size_t freeB = 0, totalB = 0; YRT_CK(cudaMemGetInfo(&freeB, &totalB));
-        const uint64_t have = (uint64_t)dev->wf.wb.capacity * 128ull + (uint64_t)dev->wf.wb.shadowCapacity * 48ull;   // already ours
+        const uint64_t have = (uint64_t)dev->wf.wb.capacity * 112ull + (uint64_t)dev->wf.wb.shadowCapacity * 48ull;   // already ours
         const uint64_t budget = (uint64_t)(0.4 * (double)freeB) + have;
-        while (capacity * (128ull + 48ull * nl) > budget && capacity > 65536) capacity >>= 1;
+        while (capacity * (112ull + 48ull * nl) > budget && capacity > 65536) capacity >>= 1;
     }
     while (capacity * nl > 0xfff00000ull && capacity > 65536) capacity >>= 1;          // 32-bit shadow-slot indices
     if (capacity < (uint64_t)spp) capacity = spp;

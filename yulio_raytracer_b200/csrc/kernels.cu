@@ -113,9 +113,9 @@ struct ClosestIO {
         O = f4v(o); D = f4v(d); tnear = o.w; tfar = d.w;
         return pid;
     }
-    __device__ __forceinline__ void store_closest(uint32_t pid, float t, float u, float v, int g, int p, V3 Ng) const {
-        wb.hitA[pid] = make_float4(t, u, v, __int_as_float(g));
-        wb.hitB[pid] = make_float4(Ng.x, Ng.y, Ng.z, __int_as_float(p));
+    // the wavefront's hit record is (t, u, v, leaf-order triangle index): k_shade finds everything else in SceneData::triShade
+    __device__ __forceinline__ void store_hit(uint32_t pid, float t, float u, float v, uint32_t tri, const float4*) const {
+        wb.hitA[pid] = make_float4(t, u, v, __int_as_float(tri == YRT_NO_TRI ? -1 : (int)tri));
     }
     __device__ __forceinline__ void store_any(uint32_t, bool) const {}
 };
@@ -126,7 +126,7 @@ struct ShadowIO {
         O = f4v(o); D = f4v(d); tnear = o.w; tfar = d.w;
         return i;
     }
-    __device__ __forceinline__ void store_closest(uint32_t, float, float, float, int, int, V3) const {}
+    __device__ __forceinline__ void store_hit(uint32_t, float, float, float, uint32_t, const float4*) const {}
     __device__ __forceinline__ void store_any(uint32_t i, bool occluded) const { wb.shC[i].w = occluded ? 1.f : 0.f; }
 };
 struct UserIO {
@@ -136,9 +136,14 @@ struct UserIO {
         O = f4v(o); D = f4v(d); tnear = o.w; tfar = d.w;
         return i;
     }
-    __device__ __forceinline__ void store_closest(uint32_t i, float t, float u, float v, int g, int p, V3 Ng) const {
-        hits[2ull * i] = make_float4(t, u, v, __int_as_float(g));
-        hits[2ull * i + 1] = make_float4(__int_as_float(p), Ng.x, Ng.y, Ng.z);
+    // the API's hit record: (t, u, v, geomID | primID, Ng) with Ng = cross(p0 - p1, p2 - p0) unnormalised (RTCRay, rtcore_ray.h:28-55)
+    __device__ __forceinline__ void store_hit(uint32_t i, float t, float u, float v, uint32_t tri, const float4* __restrict__ tris) const {
+        if (tri == YRT_NO_TRI) { hits[2ull * i] = make_float4(t, 0.f, 0.f, __int_as_float(-1)); hits[2ull * i + 1] = make_float4(__int_as_float(-1), 0.f, 0.f, 0.f); return; }
+        const float4* tp = tris + 3ull * tri;
+        const float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
+        const V3 p0(a.x, a.y, a.z), p1(b.x, b.y, b.z), p2(c.x, c.y, c.z), Ng = cross(p0 - p1, p2 - p0);
+        hits[2ull * i] = make_float4(t, u, v, a.w);
+        hits[2ull * i + 1] = make_float4(b.w, Ng.x, Ng.y, Ng.z);
     }
     __device__ __forceinline__ void store_any(uint32_t i, bool occluded) const {
         float4 a = hits[2ull * i]; a.w = __int_as_float(occluded ? 0 : -1); hits[2ull * i] = a;
@@ -155,7 +160,7 @@ __global__ void __launch_bounds__(YRT_TRACE_THREADS) k_trace_simple(SceneData sc
         HitRec h; TraceCounters cnt;
         const bool hit = trace_ray<ANY, false>((const uint4*)sc.nodes, sc.tris, sc.numNodes, O, D, tnear, tfar, h, &cnt);
         if (ANY) io.store_any(tag, hit);
-        else io.store_closest(tag, h.t, hit ? h.u : 0.f, hit ? h.v : 0.f, h.geomID, h.primID, hit ? h.Ng : V3(0.f));
+        else io.store_hit(tag, h.t, hit ? h.u : 0.f, hit ? h.v : 0.f, hit ? h.tri : YRT_NO_TRI, sc.tris);
     }
 }
 
@@ -287,7 +292,7 @@ __global__ void __launch_bounds__(YRT_SHADE_THREADS, EXT ? 4 : YRT_SHADE_MINBLOC
         // their cache-line locality. Primary hits (bounce 0) are coherent already.
         if (depth > 0) {
             uint32_t cls = 15u;                                  // entries past the end of the queue sort last
-            if (valid) { const int g = __float_as_int(wb.hitA[pid].w); cls = g < 0 ? 0u : (uint32_t)sc.geoms[g].shadeClass; }
+            if (valid) { const int tr = __float_as_int(wb.hitA[pid].w); cls = tr < 0 ? 0u : (uint32_t)sc.geoms[__float_as_uint(sc.triShade[5ull * tr].w) >> 2].shadeClass; }
             if (threadIdx.x < 16) smHist[threadIdx.x] = 0u;
             __syncthreads();
             // warp-aggregated histogram: one shared-memory atomic per (warp, class) instead of one per thread
@@ -312,7 +317,7 @@ __global__ void __launch_bounds__(YRT_SHADE_THREADS, EXT ? 4 : YRT_SHADE_MINBLOC
         float4 d4 = make_float4(0, 0, 0, 0), m4 = make_float4(1, 1, 1, 1); float hitT = 0.f;
         if (valid) {
             const float4 o4 = wb.rayO[pid]; d4 = wb.rayD[pid];
-            const float4 hA = wb.hitA[pid], hB = wb.hitB[pid];
+            const float4 hA = wb.hitA[pid];
             // radiance so far: read (and written back) only by the vertices that add to it — misses that see the environment and hits
             // on visible emitters; k_resolve adds the light samples. Bounce 0 initialises it.
             Col L(0.f); bool Ltouched = depth == 0;
@@ -328,8 +333,8 @@ __global__ void __launch_bounds__(YRT_SHADE_THREADS, EXT ? 4 : YRT_SHADE_MINBLOC
             fx = (float(pc.x) + rec[0]) * fc.rcpWidth; fy = (float(pc.y) + rec[1]) * fc.rcpHeight;
             const V3 org = f4v(o4), dir = f4v(d4);
             wo = -dir;
-            const int geomID = __float_as_int(hA.w);
-            if (geomID < 0) {
+            const int triIdx = __float_as_int(hA.w);
+            if (triIdx < 0) {
                 // environment shading (pathtraceintegrator.cpp:79-92)
                 if (ig.backplateTex >= 0 && (flags & FLAG_UNBENT)) {
                     const TextureRec& bp = sc.textures[ig.backplateTex];
@@ -341,7 +346,7 @@ __global__ void __launch_bounds__(YRT_SHADE_THREADS, EXT ? 4 : YRT_SHADE_MINBLOC
                     for (int e = 0; e < sc.numEnvLights; e++) L += thr * env_Le(sc, sc.lights[sc.envLightIdx[e]], wo);
                 }
             } else {
-                post_intersect<EXT>(sc, org, dir, hA.x, hA.y, hA.z, geomID, __float_as_int(hB.w), f4v(hB), dg);
+                post_intersect<EXT>(sc, org, dir, hA.x, hA.y, hA.z, triIdx, dg);
                 bool backfacing = false;
                 if (dot(dg.Ng, dir) > 0.f) { backfacing = true; dg.Ng = -dg.Ng; dg.Ns = -dg.Ns; }   // :95-98
                 if (dg.material >= 0) material_shade<EXT>(sc, sc.materials[dg.material], dg, Col(m4.x, m4.y, m4.z), m4.w, lobes);

@@ -53,43 +53,38 @@ struct DG { V3 P, Ng, Ns; float s, t, error; int material, areaLight, illumMask,
 // Tx/Ty (trianglemesh_full.cpp:252-270, trianglemesh_normals.cpp:154-155) are produced by the EXT instantiation only: BrushedMetal is
 // the one material that reads them. Meshes with tangent arrays are not supported (the arrays are ignored).
 template <bool EXT>
-YRT_D void post_intersect(const SceneData& sc, V3 org, V3 dir, float t, float u, float v, int geomID, int primID, V3 rayNg, DG& dg) {
-    const GeomRec g = sc.geoms[geomID];
+YRT_D void post_intersect(const SceneData& sc, V3 org, V3 dir, float t, float u, float v, int triIdx, DG& dg) {
+    // one 80-byte record per leaf-order triangle (bvh_build.cu: write_triangle) replaces geometry record -> indices -> 3 vertices
+    const float4* h = sc.triShade + 5ull * (uint32_t)triIdx;
+    const float4 r0 = __ldg(h), r1 = __ldg(h + 1), r2 = __ldg(h + 2), r3 = __ldg(h + 3), r4 = __ldg(h + 4);
+    const uint32_t flags = __float_as_uint(r0.w);
+    const GeomRec& g = sc.geoms[flags >> 2];
     dg.material = g.material; dg.areaLight = g.areaLight; dg.illumMask = g.illumMask; dg.shadowMask = g.shadowMask;
     dg.P = org + t * dir;
+    dg.Ng = V3(r0.x, r0.y, r0.z);                               // normalize(ray.Ng), or Triangle::Ng for a triangle shape
     if (EXT) { dg.Tx = V3(0.f); dg.Ty = V3(0.f); }
-    if (g.type == MESH_TRIANGLE) { dg.Ng = g.triNg; dg.Ns = g.triNg; dg.s = u; dg.t = v; }
-    else {
-        dg.Ng = normalize(rayNg);
-        const int4 tri = sc.indices[g.idxBase + primID];
-        const float w = 1.0f - u - v;
-        if (g.uvBase != YRT_NO_ATTR) {
-            const float2 st0 = sc.uvs[g.uvBase + tri.x], st1 = sc.uvs[g.uvBase + tri.y], st2 = sc.uvs[g.uvBase + tri.z];
-            dg.s = st0.x * w + st1.x * u + st2.x * v; dg.t = st0.y * w + st1.y * u + st2.y * v;
-        } else { dg.s = u; dg.t = v; }
-        if (g.nrmBase != YRT_NO_ATTR) {
-            const float4 a = sc.normals[g.nrmBase + tri.x], b = sc.normals[g.nrmBase + tri.y], c = sc.normals[g.nrmBase + tri.z];
-            V3 Ns = w * V3(a.x, a.y, a.z) + u * V3(b.x, b.y, b.z) + v * V3(c.x, c.y, c.z);
-            const float len2 = dot(Ns, Ns);
-            Ns = len2 > 0 ? Ns * rsqrtf_exact(len2) : dg.Ng;
-            if (dot(Ns, dg.Ng) < 0) Ns = -Ns;
-            dg.Ns = Ns;
-        } else dg.Ns = dg.Ng;
-        if (EXT) {
-            const float4 q0 = sc.positions[g.vtxBase + tri.x], q1 = sc.positions[g.vtxBase + tri.y], q2 = sc.positions[g.vtxBase + tri.z];
-            const V3 p0(q0.x, q0.y, q0.z), dPdu = V3(q1.x, q1.y, q1.z) - p0, dPdv = V3(q2.x, q2.y, q2.z) - p0;
-            if (g.type == MESH_NORMALS) { dg.Tx = dPdu; dg.Ty = dPdv; }
-            else {
-                float dsdu = 1.f, dtdu = 0.f, dsdv = 0.f, dtdv = 1.f;
-                if (g.uvBase != YRT_NO_ATTR) {
-                    const float2 st0 = sc.uvs[g.uvBase + tri.x], st1 = sc.uvs[g.uvBase + tri.y], st2 = sc.uvs[g.uvBase + tri.z];
-                    dsdu = st1.x - st0.x; dtdu = st1.y - st0.y; dsdv = st2.x - st0.x; dtdv = st2.y - st0.y;
-                }
-                const V3 dPds = normalize(dPdu * dtdv - dPdv * dtdu);
-                dg.Tx = normalize(dPds - dot(dPds, dg.Ns) * dg.Ns);
-                const V3 dPdt = normalize(dPdv * dsdu - dPdu * dsdv);
-                dg.Ty = normalize(dPdt - dot(dPdt, dg.Ns) * dg.Ns);
-            }
+    const float w = 1.0f - u - v;
+    if (flags & 2u) { dg.s = r1.w * w + r3.w * u + r4.y * v; dg.t = r2.w * w + r4.x * u + r4.z * v; }
+    else { dg.s = u; dg.t = v; }
+    if (flags & 1u) {
+        V3 Ns = w * V3(r1.x, r1.y, r1.z) + u * V3(r2.x, r2.y, r2.z) + v * V3(r3.x, r3.y, r3.z);
+        const float len2 = dot(Ns, Ns);
+        Ns = len2 > 0 ? Ns * rsqrtf_exact(len2) : dg.Ng;
+        if (dot(Ns, dg.Ng) < 0) Ns = -Ns;
+        dg.Ns = Ns;
+    } else dg.Ns = dg.Ng;
+    if (EXT && g.type != MESH_TRIANGLE) {
+        const float4* tp = sc.tris + 3ull * (uint32_t)triIdx;
+        const float4 q0 = __ldg(tp), q1 = __ldg(tp + 1), q2 = __ldg(tp + 2);
+        const V3 p0(q0.x, q0.y, q0.z), dPdu = V3(q1.x, q1.y, q1.z) - p0, dPdv = V3(q2.x, q2.y, q2.z) - p0;
+        if (g.type == MESH_NORMALS) { dg.Tx = dPdu; dg.Ty = dPdv; }
+        else {
+            float dsdu = 1.f, dtdu = 0.f, dsdv = 0.f, dtdv = 1.f;
+            if (flags & 2u) { dsdu = r3.w - r1.w; dtdu = r4.x - r2.w; dsdv = r4.y - r1.w; dtdv = r4.z - r2.w; }
+            const V3 dPds = normalize(dPdu * dtdv - dPdv * dtdu);
+            dg.Tx = normalize(dPds - dot(dPds, dg.Ns) * dg.Ns);
+            const V3 dPdt = normalize(dPdv * dsdu - dPdu * dsdv);
+            dg.Ty = normalize(dPdt - dot(dPdt, dg.Ns) * dg.Ns);
         }
     }
     dg.error = rmax(fabsf(t), reduce_max(vabs(dg.P)));
