@@ -251,7 +251,7 @@ static std::shared_ptr<MaterialObj> make_material(const std::string& type, const
     else if (type == "uber") {                                                                             // Uber.h:20-30
         r.type = MAT_UBER; m->textures[0] = p.getTexture("Kd"); r.c0 = p.getV3("diffuse", V3(0.f)); st();
         r.f[0] = p.getFloat("eta", 1.4f); r.f[1] = p.getFloat("roughness", .9f); r.f[2] = p.getFloat("reflectivity", .0f);
-        r.f[3] = rcpf(r.f[1]);
+        r.f[3] = rcpf(r.f[1]); r.f[4] = 1.f * rcpf(r.f[0]);
     } else if (type == "dielectric" || type == "glass") {                                                  // dielectric.h:31-45
         r.type = MAT_DIELECTRIC; r.etaOutside = p.getFloat("etaOutside", 1.0f); r.etaInside = p.getFloat("etaInside", 1.4f);
         r.tOutside = p.getV3("transmissionOutside", V3(1.f)); r.tInside = p.getV3("transmission", V3(1.f)); r.isMediaInterface = 1;

@@ -164,8 +164,11 @@ __global__ void __launch_bounds__(YRT_TRACE_THREADS) k_trace_simple(SceneData sc
     }
 }
 
+#ifndef YRT_CLOSEST_MINBLOCKS
+#define YRT_CLOSEST_MINBLOCKS 8
+#endif
 template <bool COUNT>
-__global__ void __launch_bounds__(YRT_TRACE_THREADS) k_trace_closest(SceneData sc, WavefrontBuffers wb, int queueSel) {
+__global__ void __launch_bounds__(YRT_TRACE_THREADS, YRT_CLOSEST_MINBLOCKS) k_trace_closest(SceneData sc, WavefrontBuffers wb, int queueSel) {
     const uint32_t n = wb.counters[queueSel];
     TraceCounters cnt = {0, 0};
     ClosestIO io{wb, queueSel ? wb.queueB : wb.queueA};

@@ -223,7 +223,8 @@ YRT_D Col microfacet_eval(const Lobe& l, V3 wo, const DG& dg, V3 wi, int fresnel
     const float cosThetaH = dot(wh, dg.Ns), cosTheta = dot(wi, wh);
     const Col F = fresnelKind == 0 ? Col(fresnel_diel(cosTheta, l.a)) : fresnel_conductor(cosTheta, l.e, l.k);
     const float D = distKind == 0 ? ((n + 2) * YRT_ONE_OVER_TWO_PI) * YRT_POWF(fabsf(dot(wh, dg.Ns)), n) : aniso_eval(dg, n, ny, wh);
-    const float G = rmin(rmin(1.0f, 2.0f * cosThetaH * cosThetaO * rcpf(cosTheta)), 2.0f * cosThetaH * cosThetaI * rcpf(cosTheta));
+    const float rcpCosTheta = rcpf(cosTheta);            // once: the out-of-line reciprocal is opaque to common-subexpression elimination
+    const float G = rmin(rmin(1.0f, 2.0f * cosThetaH * cosThetaO * rcpCosTheta), 2.0f * cosThetaH * cosThetaI * rcpCosTheta);
     return l.c * D * G * F * rcpf(4.0f * cosThetaO);
 }
 
@@ -435,10 +436,10 @@ YRT_D void material_shade(const SceneData& sc, const MaterialRec& m, const DG& d
         if (m.tex[0] >= 0) { dc = tex_get(sc.textures[m.tex[0]], m.dsx * dg.s + m.s0x, m.dsy * dg.t + m.s0y); alpha = dc.a; opacity = 1.f - alpha; }
         add_lobe(L, LOBE_LAMBERTIAN, BR_DIFFUSE_REFLECTION, Col(dc.r * alpha, dc.g * alpha, dc.b * alpha));
         if (alpha < 1.f) add_lobe(L, LOBE_CONST_DIEL_TRANS, BR_SPECULAR_TRANSMISSION, Col(opacity));
-        const float eta = m.f[0], roughness = m.f[1], reflectivity = m.f[2], rcpRoughness = m.f[3];
-        if (reflectivity > 0.f) add_lobe(L, LOBE_DIEL_REFL, BR_SPECULAR_REFLECTION, Col(0.f), 1.f * rcpf(eta), alpha * reflectivity);
-        else if (roughness == 0.f) add_lobe(L, LOBE_DIEL_REFL, BR_SPECULAR_REFLECTION, Col(0.f), 1.f * rcpf(eta), alpha);
-        else add_lobe(L, LOBE_MICROFACET_UBER, BR_GLOSSY_REFLECTION, Col(alpha), 1.f * rcpf(eta), rcpRoughness);
+        const float roughness = m.f[1], reflectivity = m.f[2], rcpRoughness = m.f[3], etait = m.f[4];   // f[4] = 1.f * rcp(eta), computed once at commit
+        if (reflectivity > 0.f) add_lobe(L, LOBE_DIEL_REFL, BR_SPECULAR_REFLECTION, Col(0.f), etait, alpha * reflectivity);
+        else if (roughness == 0.f) add_lobe(L, LOBE_DIEL_REFL, BR_SPECULAR_REFLECTION, Col(0.f), etait, alpha);
+        else add_lobe(L, LOBE_MICROFACET_UBER, BR_GLOSSY_REFLECTION, Col(alpha), etait, rcpRoughness);
         break;
     }
     case MAT_DIELECTRIC: {
