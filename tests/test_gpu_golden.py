@@ -281,3 +281,22 @@ def test_plugin_boundary_with_a_reference_side_caller():
         means.append(np.array([float(v) for v in line.split()[1:]]))
     assert means[1].min() > 0.01
     assert np.allclose(means[0], means[1], rtol=2e-3), means
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cfg", ["chunk=4096", "bvh=0", "splitleaves=0", "syncmin=0", "syncmin=1000000000", "trav=0", "sort=1,sortmin=1",
+                                 "refill=1,trinum=1,triden=4", "shadectas=3,tracectas=2"])
+def test_frame_is_independent_of_scheduling_and_acceleration_structure(cuda_dev, cfg):
+    """Radiance is accumulated per path in the reference's order and hits are the (t, geomID, primID) minimum, so the frame must be
+    bit-identical whatever the wavefront chunking, queue order, traversal schedule, launch geometry or BVH builder."""
+    from yulio_raytracer_b200 import Device
+    ref = None
+    for d in (cuda_dev, Device.cuda(cfg=cfg)):
+        s = scenes.atrium(d, 48, 40, 8, 6, face=2, detail=4, tex_size=32)
+        for _, _ in scenes.render_cube_map(d, s, faces=[2]):
+            img = d.read_framebuffer(s.framebuffer, "RGB_FLOAT32", 48, 40)
+        if ref is None:
+            ref = img
+        else:
+            assert np.array_equal(ref.view(np.uint32), img.view(np.uint32)), cfg
+            d.close()
