@@ -482,7 +482,7 @@ __global__ void k_collapse(CollapseArgs a) {
 // ---------------------------------------------------------------------------------------------
 // Scratch comes from the stream-ordered pool (cudaMallocAsync): a rebuild per cube face must not pay
 // cudaMalloc/cudaFree round trips (measured: 30 ms ... 1.4 s of wall clock per build with the synchronous allocator).
-static cudaStream_t g_allocStream = nullptr;
+static thread_local cudaStream_t g_allocStream = nullptr;   // per host thread: a group device builds on several GPUs at once (group_api.cu)
 template <typename T> static T* dalloc(size_t n) { T* p = nullptr; CK(cudaMallocAsync((void**)&p, (n ? n : 1) * sizeof(T), g_allocStream)); return p; }
 static void dfree(void* p) { if (p) cudaFreeAsync(p, g_allocStream); }
 
@@ -537,8 +537,7 @@ void build_bvh(const BvhBuildInput& in, BvhResult& out, cudaStream_t stream) {
         CK(cudaMemcpyAsync(clo[0], leafLo, (size_t)n * sizeof(float4), cudaMemcpyDeviceToDevice, stream));
         CK(cudaMemcpyAsync(chi[0], leafHi, (size_t)n * sizeof(float4), cudaMemcpyDeviceToDevice, stream));
         out.launches++;
-        uint32_t m = n; static uint32_t* hostM = nullptr;          // pinned read-back word, allocated once per process
-        if (!hostM) CK(cudaMallocHost((void**)&hostM, sizeof(uint32_t)));
+        uint32_t m = n; uint32_t* hostM = in.hostWord;               // the device's pinned read-back word
         while (m > PLOC_FINAL) {
             const uint32_t g = (m + PLOC_BLOCK - 1) / PLOC_BLOCK;
             k_ploc_nn<<<g, PLOC_BLOCK, 0, stream>>>(clo[0], chi[0], m, radius, nn);

@@ -121,6 +121,7 @@ namespace yrt {
 struct CubeStrip { unsigned char* dev = nullptr; size_t w = 0, h = 0; uchar4* wm = nullptr; int wmW = 0, wmH = 0; int facesAdded = 0; };
 }
 struct yrt_device {
+    std::vector<yrt_device*> members;          // non-empty: a group device (cfg gpus=N, group_api.cu); nothing below is used then
     std::mutex mutex;                          // RT_COMMAND_HEADER (api/singleray_device.cpp:97)
     int gpu = 0; int numSMs = 148; cudaStream_t stream = nullptr;
     int serverID = 0, serverCount = 1;         // g_serverID / g_serverCount (api/singleray_device.cpp:109-110)

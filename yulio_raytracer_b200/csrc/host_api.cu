@@ -12,6 +12,8 @@
 #include <cstdlib>
 
 #include "../../include/yrt_device.h"
+#include "gen/core_decls.inc"
+#include "gen/core_names.inc"      // the entry points below are the single-GPU implementation: yrtX -> yrtX_core (group_api.cu owns the public names)
 #include "device_impl.hpp"
 #include "camera.cuh"
 #include "host_math.hpp"

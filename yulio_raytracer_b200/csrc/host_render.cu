@@ -226,7 +226,7 @@ void scene_commit(yrt_device* dev, SceneHandle* sc) {
         lap("patch");
         sc->patchSlots.clear();
         sc->releaseDevice();
-        BvhBuildInput in{sc->refsBuf.p, sc->numRefs, sc->geoms.p, sc->positions.p, sc->indices.p, sc->normals.p, sc->uvs.p, dev->bvhPloc, dev->splitLeaves, dev->plocRadius};
+        BvhBuildInput in{sc->refsBuf.p, sc->numRefs, sc->geoms.p, sc->positions.p, sc->indices.p, sc->normals.p, sc->uvs.p, dev->hostCounters + 8, dev->bvhPloc, dev->splitLeaves, dev->plocRadius};
         BvhResult out{};
         build_bvh(in, out, st);
         lap("bvh");
@@ -357,7 +357,7 @@ void scene_commit(yrt_device* dev, SceneHandle* sc) {
 
     lap("upload");
     sc->releaseDevice();
-    BvhBuildInput in{dRefs.p, (uint32_t)refs.size(), sc->geoms.p, sc->positions.p, sc->indices.p, sc->normals.p, sc->uvs.p, dev->bvhPloc, dev->splitLeaves, dev->plocRadius};
+    BvhBuildInput in{dRefs.p, (uint32_t)refs.size(), sc->geoms.p, sc->positions.p, sc->indices.p, sc->normals.p, sc->uvs.p, dev->hostCounters + 8, dev->bvhPloc, dev->splitLeaves, dev->plocRadius};
     BvhResult out{};
     build_bvh(in, out, st);
     YRT_CK(cudaStreamSynchronize(st));

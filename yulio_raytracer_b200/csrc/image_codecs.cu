@@ -43,11 +43,13 @@ struct NvJpeg {
     decltype(&nvjpegEncodeImage) EncodeImage; decltype(&nvjpegEncodeRetrieveBitstream) EncodeRetrieveBitstream;
 };
 
+// one library handle per CUDA device (a group device decodes the same texture on every member's GPU)
 static NvJpeg& nvjpeg() {
-    static NvJpeg nj; static std::once_flag once; static std::string err;
+    static NvJpeg base; static std::once_flag once; static std::string err; static std::mutex mtx; static NvJpeg perGpu[64]; static bool ready[64];
     std::call_once(once, [] {
-        for (const char* name : {"libnvjpeg.so.12", "libnvjpeg.so", "/usr/local/cuda/lib64/libnvjpeg.so.12"}) { nj.lib = dlopen(name, RTLD_NOW | RTLD_LOCAL); if (nj.lib) break; }
-        if (!nj.lib) { err = std::string("device_cuda: nvJPEG not available (") + dlerror() + ")"; return; }
+        for (const char* name : {"libnvjpeg.so.12", "libnvjpeg.so", "/usr/local/cuda/lib64/libnvjpeg.so.12"}) { base.lib = dlopen(name, RTLD_NOW | RTLD_LOCAL); if (base.lib) break; }
+        if (!base.lib) { err = std::string("device_cuda: nvJPEG not available (") + dlerror() + ")"; return; }
+        NvJpeg& nj = base;
 #define NJ_SYM(field, sym) nj.field = (decltype(nj.field))dlsym(nj.lib, #sym); if (!nj.field) { err = "device_cuda: nvJPEG symbol missing: " #sym; return; }
         NJ_SYM(CreateSimple, nvjpegCreateSimple) NJ_SYM(CreateEx, nvjpegCreateEx) NJ_SYM(JpegStateCreate, nvjpegJpegStateCreate) NJ_SYM(JpegStateDestroy, nvjpegJpegStateDestroy)
         NJ_SYM(GetImageInfo, nvjpegGetImageInfo) NJ_SYM(Decode, nvjpegDecode)
@@ -57,14 +59,21 @@ static NvJpeg& nvjpeg() {
         NJ_SYM(EncoderParamsSetOptimizedHuffman, nvjpegEncoderParamsSetOptimizedHuffman)
         NJ_SYM(EncodeImage, nvjpegEncodeImage) NJ_SYM(EncodeRetrieveBitstream, nvjpegEncodeRetrieveBitstream)
 #undef NJ_SYM
+    });
+    if (!err.empty() || !base.EncodeRetrieveBitstream) throw std::runtime_error(err.empty() ? "device_cuda: nvJPEG not initialised" : err);
+    int gpu = 0; cudaGetDevice(&gpu);
+    if (gpu < 0 || gpu >= 64) throw std::runtime_error("device_cuda: unexpected CUDA device index");
+    std::lock_guard<std::mutex> lock(mtx);
+    if (!ready[gpu]) {
+        NvJpeg nj = base;
         // chroma planes are up-sampled with interpolation, as libjpeg-turbo's default "fancy upsampling" does in the reference's reader
         if (nj.CreateEx(NVJPEG_BACKEND_DEFAULT, nullptr, nullptr, NVJPEG_FLAGS_UPSAMPLING_WITH_INTERPOLATION, &nj.handle) != NVJPEG_STATUS_SUCCESS) {
             nj.handle = nullptr;
-            if (nj.CreateSimple(&nj.handle) != NVJPEG_STATUS_SUCCESS) { nj.handle = nullptr; err = "device_cuda: nvjpegCreate failed"; }
+            if (nj.CreateSimple(&nj.handle) != NVJPEG_STATUS_SUCCESS) throw std::runtime_error("device_cuda: nvjpegCreate failed");
         }
-    });
-    if (!nj.handle) throw std::runtime_error(err.empty() ? "device_cuda: nvJPEG not initialised" : err);
-    return nj;
+        perGpu[gpu] = nj; ready[gpu] = true;
+    }
+    return perGpu[gpu];
 }
 #define NJ_CK(x) do { const nvjpegStatus_t s_ = (x); if (s_ != NVJPEG_STATUS_SUCCESS) throw std::runtime_error(std::string("nvJPEG error ") + std::to_string((int)s_) + " in " #x); } while (0)
 
@@ -270,6 +279,25 @@ void strip_add_face(yrt_device* dev, FrameBufferHandle* fb, int cubeFaceIndex, i
     k_strip_face<<<dim3((unsigned)((s.w + 127) / 128), (unsigned)s.h), 128, 0, dev->stream>>>((const unsigned char*)fb->devPacked, (int)fb->strideBytes, (int)s.w, (int)s.h,
                                                                                                 s.dev, (int)(12 * s.w * 3), seg * (int)s.w, wm ? s.wm : nullptr, s.wmW, s.wmH, x0, y0);
     YRT_CK(cudaGetLastError());
+    s.facesAdded++;
+}
+
+// the same for a frame that is in host memory (a group device collects its members' bands on the host, group_api.cu)
+void strip_add_face_host(yrt_device* dev, const unsigned char* rgb, size_t strideBytes, size_t w, size_t h, int cubeFaceIndex, int watermark) {
+    CubeStrip& s = dev->strip;
+    if (!s.dev) throw std::runtime_error("device_cuda: yrtxStripBegin was not called");
+    if (w != s.w || h != s.h) throw std::runtime_error("device_cuda: the strip takes RGB8 frames of the size given to yrtxStripBegin");
+    unsigned char* tmp = nullptr;
+    YRT_CK(cudaMallocAsync((void**)&tmp, strideBytes * h ? strideBytes * h : 1, dev->stream));
+    YRT_CK(cudaMemcpyAsync(tmp, rgb, strideBytes * h, cudaMemcpyHostToDevice, dev->stream));
+    const int seg = strip_segment(cubeFaceIndex);
+    const bool wm = watermark && s.wm && (((cubeFaceIndex % 12) + 12) % 6) < 4;
+    const int x0 = (int)(0 + ((float)s.w - (float)s.wmW) * .5f), y0 = (int)(0 + ((float)s.h - (float)s.wmH) * .5f);
+    k_strip_face<<<dim3((unsigned)((s.w + 127) / 128), (unsigned)s.h), 128, 0, dev->stream>>>(tmp, (int)strideBytes, (int)s.w, (int)s.h, s.dev, (int)(12 * s.w * 3),
+                                                                                                seg * (int)s.w, wm ? s.wm : nullptr, s.wmW, s.wmH, x0, y0);
+    YRT_CK(cudaGetLastError());
+    YRT_CK(cudaFreeAsync(tmp, dev->stream));
+    YRT_CK(cudaStreamSynchronize(dev->stream));                      // `rgb` belongs to the caller
     s.facesAdded++;
 }
 
