@@ -109,12 +109,21 @@ yrt_device* yrtCreateDevice(const char* parms, size_t numThreads, int threadsPri
         if (n > have) throw std::runtime_error("device_cuda: cfg gpus=" + std::to_string(n) + " but only " + std::to_string(have) + " CUDA device(s) are visible");
         const long first = cfg_int(c, "gpu", 0);
         std::unique_ptr<yrt_device> g(new yrt_device());
-        for (long i = 0; i < n; i++) {
-            const std::string mc = c + ",gpus=1,gpu=" + std::to_string(first + i) + ",serverID=" + std::to_string(i) + ",serverCount=" + std::to_string(n);
-            yrt_device* m = yrtCreateDevice_core(parms, numThreads, threadsPriority, mc.c_str());     // later keys override earlier ones
-            if (!m) { for (yrt_device* d : g->members) yrtDestroyDevice_core(d); return nullptr; }
-            g->members.push_back(m);
-        }
+        // the members' CUDA contexts are created concurrently (about 1.5 s each)
+        std::vector<yrt_device*> ms((size_t)n, nullptr); std::vector<std::string> err((size_t)n); std::vector<std::thread> th;
+        for (long i = 0; i < n; i++)
+            th.emplace_back([&, i] {
+                const std::string mc = c + ",gpus=1,gpu=" + std::to_string(first + i) + ",serverID=" + std::to_string(i) + ",serverCount=" + std::to_string(n);
+                ms[(size_t)i] = yrtCreateDevice_core(parms, numThreads, threadsPriority, mc.c_str());     // later keys override earlier ones
+                if (!ms[(size_t)i]) err[(size_t)i] = yrtGetLastError_core();
+            });
+        for (auto& t : th) t.join();
+        for (long i = 0; i < n; i++)
+            if (!ms[(size_t)i]) {
+                for (yrt_device* d : ms) if (d) yrtDestroyDevice_core(d);
+                throw std::runtime_error(err[(size_t)i]);
+            }
+        g->members = ms;
         return g.release();
     } catch (const std::exception& e) { fail(e); return nullptr; }
 }
