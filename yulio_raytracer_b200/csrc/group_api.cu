@@ -13,6 +13,7 @@
 // The public entry points (include/yrt_device.h) are generated (tools/gen_group_api.py -> gen/group_wrappers.inc): a plain device goes
 // straight to the single-GPU implementation yrtX_core (host_api.cu), a group either runs the call on every member or lands in grp:: here.
 #include <atomic>
+#include <condition_variable>
 #include <cstdlib>
 #include <cstring>
 #include <functional>
@@ -61,16 +62,55 @@ template <class F> yrt_status each(yrt_device* dev, F f) {
         return YRT_OK;
     } catch (const std::exception& e) { return fail(e); }
 }
-// the same on one host thread per member (render, scene commit, frame read-back)
+// One persistent host thread per member: render, scene commit and frame read-back run on all GPUs at once, and a cube face of a small
+// scene is only a few milliseconds of GPU work — spawning threads per call would show (3 x N thread starts per face).
+struct Workers {
+    struct Slot { std::thread th; std::mutex m; std::condition_variable cv; std::function<void()> job; bool stop = false; };
+    std::vector<std::unique_ptr<Slot>> slots; std::mutex doneM; std::condition_variable doneCv; size_t pending = 0;
+    explicit Workers(size_t n) {
+        for (size_t i = 0; i < n; i++) {
+            slots.emplace_back(new Slot());
+            Slot* s = slots.back().get();
+            s->th = std::thread([this, s] {
+                for (;;) {
+                    std::function<void()> job;
+                    { std::unique_lock<std::mutex> l(s->m); s->cv.wait(l, [s] { return s->stop || s->job; }); if (s->stop) return; job.swap(s->job); }
+                    job();
+                    { std::lock_guard<std::mutex> l(doneM); pending--; }
+                    doneCv.notify_all();
+                }
+            });
+        }
+    }
+    ~Workers() {
+        for (auto& s : slots) { { std::lock_guard<std::mutex> l(s->m); s->stop = true; } s->cv.notify_all(); }
+        for (auto& s : slots) s->th.join();
+    }
+    void run(const std::function<void(size_t)>& f) {       // f(i) on worker i for every i; returns when all are done
+        { std::lock_guard<std::mutex> l(doneM); pending = slots.size(); }
+        for (size_t i = 0; i < slots.size(); i++) { { std::lock_guard<std::mutex> l(slots[i]->m); slots[i]->job = [&f, i] { f(i); }; } slots[i]->cv.notify_all(); }
+        std::unique_lock<std::mutex> l(doneM); doneCv.wait(l, [this] { return pending == 0; });
+    }
+};
+static std::mutex g_workersM; static std::vector<std::pair<yrt_device*, std::unique_ptr<Workers>>> g_workers;
+static Workers& workers(yrt_device* dev) {
+    std::lock_guard<std::mutex> l(g_workersM);
+    for (auto& w : g_workers) if (w.first == dev) return *w.second;
+    g_workers.emplace_back(dev, std::unique_ptr<Workers>(new Workers(dev->members.size())));
+    return *g_workers.back().second;
+}
+static void drop_workers(yrt_device* dev) {
+    std::lock_guard<std::mutex> l(g_workersM);
+    for (size_t i = 0; i < g_workers.size(); i++) if (g_workers[i].first == dev) { g_workers.erase(g_workers.begin() + (long)i); return; }
+}
+
 template <class F> yrt_status each_parallel(yrt_device* dev, F f) {
     const size_t n = dev->members.size();
-    std::vector<std::string> err(n); std::vector<int> rc(n, YRT_OK); std::vector<std::thread> th;
-    for (size_t i = 0; i < n; i++)
-        th.emplace_back([&, i] {
-            try { rc[i] = f(dev->members[i], (int)i); if (rc[i] != YRT_OK) err[i] = yrtGetLastError_core(); }
-            catch (const std::exception& e) { rc[i] = YRT_ERROR; err[i] = e.what(); }
-        });
-    for (auto& t : th) t.join();
+    std::vector<std::string> err(n); std::vector<int> rc(n, YRT_OK);
+    workers(dev).run([&](size_t i) {
+        try { rc[i] = f(dev->members[i], (int)i); if (rc[i] != YRT_OK) err[i] = yrtGetLastError_core(); }
+        catch (const std::exception& e) { rc[i] = YRT_ERROR; err[i] = e.what(); }
+    });
     for (size_t i = 0; i < n; i++) if (rc[i] != YRT_OK) { yrt::g_lastError = err[i]; return YRT_ERROR; }
     return YRT_OK;
 }
@@ -128,6 +168,7 @@ yrt_device* yrtCreateDevice(const char* parms, size_t numThreads, int threadsPri
     } catch (const std::exception& e) { fail(e); return nullptr; }
 }
 void yrtDestroyDevice(yrt_device* dev) {
+    drop_workers(dev);
     std::vector<std::thread> th;                       // releasing ~11 GB of wavefront state per GPU takes over a second: all members at once
     for (yrt_device* m : dev->members) th.emplace_back([m] { yrtDestroyDevice_core(m); });
     for (auto& t : th) t.join();
