@@ -14,7 +14,8 @@ cyclically, so the default K = 12 is exactly one stereo cube map. Metric = the r
   e2e     host wall-clock of the reference-facing loop per face: rtUpdatePrimitive x prims, rtCommit(scene),
           rtRenderFrame, rtSwapBuffers, rtMapFrameBuffer -> the frame is in the (pinned) host buffer; host->device
           bytes = sample table / constants actually uploaded, device->host bytes = the frame
-  N > 1   one process per GPU (torchrun); the scene is replicated, every face is split into the reference's 4-row
+  N > 1   (without torchrun: one process, the group device of csrc/group_api.cu, cfg gpus=N)
+          one process per GPU (torchrun, the driver's launch); the scene is replicated, every face is split into the reference's 4-row
           bands dealt round-robin to the ranks (api/swapchain.h:57-70, the reference's own network-device partition) and
           the bands are gathered on rank 0 over NCCL; strong scaling (total work fixed).
 --impl reference runs the reference's own CPU path (oracle/_ref: devices/device_singleray sources + embree2 shim) on all
@@ -186,7 +187,12 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    dev = Device.cuda(cfg=f"gpu={local_rank},serverID={rank},serverCount={world}" + ("," + args.cfg if args.cfg else ""))
+    # --gpus N without torchrun (one process): the group device (cfg gpus=N, csrc/group_api.cu) spreads every face over N GPUs behind the
+    # one Device; under torchrun (the driver's launch) every rank owns one GPU and the bands are exchanged over NCCL.
+    in_process = args.gpus if (world == 1 and args.gpus > 1) else 1
+    if in_process > 1:
+        config["partition"] = f"4-row bands round-robin over {in_process} GPUs of one process (group device), scene replicated"
+    dev = Device.cuda(cfg=(f"gpus={in_process}" if in_process > 1 else f"gpu={local_rank},serverID={rank},serverCount={world}") + ("," + args.cfg if args.cfg else ""))
     s = build_workload(dev, args.workload, size, spp, depth, "RGB8")
     stride = (3 * size + 3) // 4 * 4
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
@@ -195,10 +201,12 @@ def main():
     class _DevView:                      # zero-copy view of the device framebuffer for torch
         def __init__(self, ptr, nbytes):
             self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 3}
-    ptr, nbytes, _ = dev.framebuffer_device(s.framebuffer)
-    fb_t = torch.as_tensor(_DevView(ptr, nbytes), device="cuda")
-    from yulio_raytracer_b200 import bands
-    gatherer = bands.BandGather(size, stride, rank, world, "cuda") if world > 1 else None
+    fb_t = gatherer = None
+    if world > 1:
+        ptr, nbytes, _ = dev.framebuffer_device(s.framebuffer)
+        fb_t = torch.as_tensor(_DevView(ptr, nbytes), device="cuda")
+        from yulio_raytracer_b200 import bands
+        gatherer = bands.BandGather(size, stride, rank, world, "cuda")
 
     def gather_bands():
         if world == 1:
@@ -218,7 +226,7 @@ def main():
     # ---- traversal statistics of the workload (stats=1 replay of one face on a second device handle, untimed) ----
     nbar = None
     if rank == 0:
-        sdev = Device.cuda(cfg=f"gpu={local_rank},stats=1,serverID={rank},serverCount={world}")
+        sdev = Device.cuda(cfg=f"gpu={local_rank},stats=1,serverID={rank},serverCount={world * in_process}")
         ss = build_workload(sdev, args.workload, size, spp, depth, "RGB8")
         sdev.set_readback(False)
         render_face(sdev, ss, face_camera(sdev, ss, 0))
@@ -291,7 +299,8 @@ def main():
     # dominant kernel: closest-hit traversal. Algorithmic bytes/ray = 32 (ray in) + 16 (hit out: t,u,v,triangle index — SURVEY §8d planned
     # 32, the record shrank when the shading data moved into per-triangle records) + 80*Nnode + 48*Ntri
     bpr = 48 + 80 * nbar["nodes_per_ray"] + 48 * nbar["tris_per_ray"]
-    achieved = agg["closest_rays"] * bpr / (agg["closest_ms"] * 1e-3) / 1e9 if agg["closest_ms"] > 0 else None
+    per_gpu_closest = agg["closest_rays"] / in_process      # the roofline is one GPU's (group device: the counters are sums over its GPUs)
+    achieved = per_gpu_closest * bpr / (agg["closest_ms"] * 1e-3) / 1e9 if agg["closest_ms"] > 0 else None
     roofline = {"bound": "hbm", "kernel": "k_trace_closest", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": (achieved / peak) if achieved else None, "traffic": None, "peak_source": peak_src,
                 "bytes_per_ray": bpr, "avg_launch_ms": agg["closest_ms"] / max(1, agg["closest_launches"]),
@@ -299,7 +308,7 @@ def main():
     # secondary roofline: FP32 issue. flops/ray = 190*Nnode + 90*Ntri against 148 SMs x 128 lanes x 2 flop x SM clock
     flops_per_ray = 190 * nbar["nodes_per_ray"] + 90 * nbar["tris_per_ray"]
     fp32_peak = 148 * 128 * 2 * (clk["sm_mhz"] or 1965.0) * 1e6 / 1e12
-    fp32_ach = agg["closest_rays"] * flops_per_ray / (agg["closest_ms"] * 1e-3) / 1e12 if agg["closest_ms"] > 0 else None
+    fp32_ach = per_gpu_closest * flops_per_ray / (agg["closest_ms"] * 1e-3) / 1e12 if agg["closest_ms"] > 0 else None
     roofline["fp32"] = {"achieved": fp32_ach, "peak": fp32_peak, "unit": "TFLOP/s", "frac": (fp32_ach / fp32_peak) if fp32_ach else None,
                         "flops_per_ray": flops_per_ray, "peak_source": "nominal: 148 SMs x 128 FP32 lanes x 2 x sampled SM clock"}
     try:
@@ -307,7 +316,7 @@ def main():
             roofline["traffic"] = json.load(f).get(args.workload)
     except Exception:
         pass
-    line = {"metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+    line = {"metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": world * in_process, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "config": config,
             "s_per_stereo_cube_map": ms_per_step * 12e-3, "e2e_s_per_stereo_cube_map": e2e_total / args.steps * 12,

@@ -178,7 +178,8 @@ void yrtDestroyDevice(yrt_device* dev) {
 
 // ---- objects with special ownership --------------------------------------------------------------------------------------------
 yrt_handle yrtNewData(yrt_device* dev, const char* type, size_t bytes, const void* data) {
-    // "immutable_managed" hands the caller's allocation over (api/data.h:40-45): member 0 takes it, the others copy first
+    // "immutable_managed" hands the caller's allocation over (api/data.h:40-45): member 0 takes it (and frees it with its handle, which is
+    // released together with the others'), members 1.. copy from it
     const bool managed = type && !strcasecmp(type, "immutable_managed");
     return make(dev, [&](yrt_device* m, int i) { return yrtNewData_core(m, (managed && i > 0) ? "immutable" : type, bytes, data); });
 }
