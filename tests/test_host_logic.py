@@ -110,3 +110,25 @@ def test_plugin_exports_reference_factory_symbol():
         pytest.skip("adapter not built (needs the reference headers: yulio_raytracer_b200/adapter/build_adapter.py)")
     lib = ctypes.CDLL(plugin)
     assert hasattr(lib, "create")
+
+
+def test_group_dispatch_layer_covers_the_header():
+    """tools/gen_group_api.py: every entry point of include/yrt_device.h gets a public wrapper, and every wrapper that defers to a
+    hand-written group implementation finds it in csrc/group_api.cu."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("gen_group_api", os.path.join(REPO, "tools", "gen_group_api.py"))
+    gen = importlib.util.module_from_spec(spec); spec.loader.exec_module(gen)
+    protos = gen.prototypes()
+    names = {n for _, n, _ in protos}
+    header = open(os.path.join(REPO, "include", "yrt_device.h")).read()
+    assert names == set(re.findall(r"\b(yrtx?[A-Z]\w+)\s*\(", header))
+    group_src = open(os.path.join(REPO, "yulio_raytracer_b200", "csrc", "group_api.cu")).read()
+    for n in gen.SPECIAL:
+        assert n in names, n
+        assert re.search(r"\b" + n + r"\s*\(", group_src), f"grp::{n} missing in group_api.cu"
+    for ret, n, ps in protos:
+        if n in gen.NO_DEVICE or n == "yrtCreateDevice":
+            continue
+        assert ps and ps[0][0] == "yrt_device*", n
+        if n not in gen.SPECIAL:
+            assert ret in ("yrt_handle", "yrt_status"), f"{n}: no generic group rule for a {ret} function"
