@@ -110,6 +110,27 @@ def test_stop_discards_results(front, tmp_path):
     assert st.state == 3 and not os.path.exists(str(tmp_path / "room_A.ppm"))                  # Stopped, nothing kept
 
 
+def test_stop_keeps_results_and_progress_is_monotonic(front, tmp_path):
+    """StopRT(true) keeps what was written so far (renderer.cpp:728-736); GetCurrentStatusRT reports (stage + tile fraction) / stages,
+    which never decreases during a run (renderer.cpp:99-225)."""
+    import time
+    dae = dae_scene.write_scene(str(tmp_path), "room", views=(("A", (0, 60, 0)), ("B", (-90, 70, 40)), ("C", (60, 50, -40))))
+    p = params(24, 4, 4, debug=True)
+    assert front.StartRT(dae.encode(), ctypes.byref(p))
+    seen = []
+    st = StatusRT()
+    for _ in range(400):
+        front.GetCurrentStatusRT(ctypes.byref(st)); seen.append(st.progress)
+        if os.path.exists(str(tmp_path / "room_A.ppm")) or st.state in (3, 4):
+            break
+        time.sleep(0.01)
+    assert front.StopRT(True)
+    front.GetCurrentStatusRT(ctypes.byref(st))
+    assert st.state in (3, 4) and st.progress == 1.0
+    assert all(b >= a for a, b in zip(seen, seen[1:])), seen
+    assert os.path.exists(str(tmp_path / "room_A.ppm"))                                         # the finished viewpoint stays
+
+
 @pytest.mark.gpu
 def test_cube_map_cuda_matches_reference_backend(tmp_path):
     """Same .dae, same loader, same front end: device_cuda against the reference CPU device. Equal sample tables and per-path
