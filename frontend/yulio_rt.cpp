@@ -163,6 +163,13 @@ static void renderCubeMaps(Session& S) {
         if (face == 0) faces.clear();
         if (S.p.toeIn) { dev->rtSetBool1(cam, "toeIn", true); dev->rtCommit(cam); }  // renderer.cpp:571-576
         dev->rtRenderFrame(S.renderer, cam, scene, S.tonemapper, S.frameBuffer, 0);
+        if (g_stop) {
+            // Stopped inside this face: it is not mapped or saved. The reference goes on to rtMapFrameBuffer here (renderer.cpp:620-626), and
+            // with its CPU device that can wait forever: when every worker sees the stop flag at the top of its tile loop nobody calls
+            // finishTile(forceFinish) and FrameBuffer::wait() never wakes (integratorrenderer.cpp:126,176; api/framebuffer.h:61-77).
+            if (!g_keep) for (const auto& f : saved) remove(f.c_str());
+            break;
+        }
         dev->rtSwapBuffers(S.frameBuffer);
         if (gpuStrip) {
             // frame -> its strip segment on the device (watermark on faces 0-3), JPEG from the device: renderer.cpp:620-718

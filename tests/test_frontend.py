@@ -12,6 +12,9 @@ import pytest
 
 from tests import dae_scene
 
+# a blocked StartRT/StopRT sits in native code: let pytest-timeout end the run instead of waiting forever
+pytestmark = pytest.mark.timeout(300, method="thread")
+
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(REPO, "yulio_raytracer_b200", "lib")
 FRONTEND = os.path.join(LIB, "libyulio_rt.so")
