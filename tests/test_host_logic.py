@@ -132,3 +132,13 @@ def test_group_dispatch_layer_covers_the_header():
         assert ps and ps[0][0] == "yrt_device*", n
         if n not in gen.SPECIAL:
             assert ret in ("yrt_handle", "yrt_status"), f"{n}: no generic group rule for a {ret} function"
+
+
+def test_cabi_header_is_plain_c(tmp_path):
+    """The drop-in boundary is a C ABI: include/yrt_device.h must compile as C99 (plain pointers and sizes, no C++ in the signatures)."""
+    import subprocess
+    src = tmp_path / "abi.c"
+    src.write_text('#include "yrt_device.h"\nint main(void) { yrtx_frame_stats s; (void)s; return yrtGetLastError() == 0; }\n')
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-I" + os.path.join(REPO, "include"), str(src)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
