@@ -195,7 +195,8 @@ yrt_handle yrtNewFrameBuffer(yrt_device* dev, const char* type, size_t width, si
     else { g->format = 2; g->strideBytes = (3 * width + 3) / 4 * 4; }
     for (size_t i = 0; i < g->depth; i++) {
         void* p = ptrs ? ptrs[i] : nullptr; bool own = false;
-        if (!p) { p = calloc(1, g->strideBytes * height ? g->strideBytes * height : 1); own = true; }
+        const size_t bytes = g->strideBytes * height;
+        if (!p) { p = calloc(1, bytes != 0 ? bytes : 1); own = true; }
         g->host.push_back(p); g->owned.push_back(own);
     }
     return h;

@@ -250,7 +250,8 @@ void strip_begin(yrt_device* dev, size_t faceW, size_t faceH) {
     if (s.w != faceW || s.h != faceH || !s.dev) {
         if (s.dev) cudaFree(s.dev);
         s.w = faceW; s.h = faceH; s.dev = nullptr;
-        YRT_CK(cudaMalloc((void**)&s.dev, 12 * faceW * faceH * 3 ? 12 * faceW * faceH * 3 : 1));
+        const size_t bytes = 12 * faceW * faceH * 3;
+        YRT_CK(cudaMalloc((void**)&s.dev, bytes != 0 ? bytes : 1));
     }
     YRT_CK(cudaMemsetAsync(s.dev, 0, 12 * faceW * faceH * 3, dev->stream));
     s.facesAdded = 0;
@@ -288,7 +289,8 @@ void strip_add_face_host(yrt_device* dev, const unsigned char* rgb, size_t strid
     if (!s.dev) throw std::runtime_error("device_cuda: yrtxStripBegin was not called");
     if (w != s.w || h != s.h) throw std::runtime_error("device_cuda: the strip takes RGB8 frames of the size given to yrtxStripBegin");
     unsigned char* tmp = nullptr;
-    YRT_CK(cudaMallocAsync((void**)&tmp, strideBytes * h ? strideBytes * h : 1, dev->stream));
+    const size_t frameBytes = strideBytes * h;
+    YRT_CK(cudaMallocAsync((void**)&tmp, frameBytes != 0 ? frameBytes : 1, dev->stream));
     YRT_CK(cudaMemcpyAsync(tmp, rgb, strideBytes * h, cudaMemcpyHostToDevice, dev->stream));
     const int seg = strip_segment(cubeFaceIndex);
     const bool wm = watermark && s.wm && (((cubeFaceIndex % 12) + 12) % 6) < 4;
