@@ -274,7 +274,9 @@ __device__ __forceinline__ uint32_t warp_alloc(uint32_t* counter, uint32_t count
 template <bool EXT>
 __global__ void __launch_bounds__(YRT_SHADE_THREADS, EXT ? 4 : YRT_SHADE_MINBLOCKS) k_shade(FrameConst fc, WavefrontBuffers wb, int queueSel, uint32_t pixelBegin, int depth) {
     __shared__ float smLobes[YRT_MAX_LOBES * LobesT<EXT>::WORDS * YRT_SHADE_THREADS], smCand[YRT_MAX_LOBES * YRT_CAND_WORDS * YRT_SHADE_THREADS];
+#if YRT_SHADE_REGROUP
     __shared__ uint32_t smHist[16], smPerm[YRT_SHADE_THREADS];
+#endif
     const uint32_t* __restrict__ queue = queueSel ? wb.queueB : wb.queueA;
     uint32_t* __restrict__ nextQueue = queueSel ? wb.queueA : wb.queueB;
     const uint32_t n = wb.counters[queueSel];
