@@ -182,6 +182,20 @@ YRT_API yrt_status yrtxFrameBufferDevice(yrt_device*, yrt_handle frameBuffer, vo
 /* readbackEachFrame == 0: yrtRenderFrame leaves the frame on the GPU and yrtMapFrameBuffer copies it on demand
  * (default 1: the frame is in the host buffer when yrtRenderFrame returns, as in the reference). */
 YRT_API yrt_status yrtxSetReadback(yrt_device*, int readbackEachFrame);
+/* The cube-face loop of the reference's front end (devices/renderer/renderer.cpp:543-632) as ONE call: the numFaces (1..12) cameras of a
+ * viewpoint — same renderer, scene, tone mapper, and one frame buffer per face, all of one size and format — are rendered as one wavefront
+ * (12 times longer ray queues, 12 times fewer kernel launches than 12 yrtRenderFrame calls). Each frame is what yrtRenderFrame would have
+ * produced for that camera (same sample tables, same per-tile sample sets: bit-identical), so the loop
+ *     for (i = 0; i < 12; i++) { rtUpdatePrimitive x prims; rtCommit(scene); rtRenderFrame(.., cameras[i], .., frameBuffer, 0); ... }
+ * becomes  rtUpdatePrimitive x prims; rtCommit(scene); yrtxRenderCubeMap(.., cameras, 12, .., frameBuffers, 0)  — the 12 cameras of a
+ * viewpoint share their "origin" (ColladaLoader.cpp:470-505), so the camera-aligned primitives turn the same way for every face. */
+YRT_API yrt_status yrtxRenderCubeMap(yrt_device*, yrt_handle renderer, const yrt_handle* cameras, size_t numFaces, yrt_handle scene,
+                                     yrt_handle tonemapper, const yrt_handle* frameBuffers, int accumulate);
+
+/* The roofline denominators SURVEY §8d asks to be measured on the box itself (csrc/microbench.cu; not on the render path):
+ * kind 0: FP32 FMA issue, *result in TFLOP/s; kind 1: read bandwidth in GB/s of a `bytes` working set re-read with L1 bypassed (L2 read
+ * bandwidth below the L2 size, HBM read bandwidth far above it); kind 2: warp-instruction issue rate in 1e9 warp instructions / s. */
+YRT_API yrt_status yrtxMicrobench(yrt_device*, int kind, size_t bytes, double* result);
 
 /* ---- the image readers behind yrtNewImageFromFile (common/image/image.cpp:26-58), exposed for tests -----
  * format: 0 RGB8, 1 RGBA8, 2 RGB_FLOAT32, 3 RGBA_FLOAT32; pixels may be NULL (query the size first). File images are RGBA8 with row 0

@@ -151,6 +151,37 @@ YRT_D uint32_t node_test(const uint4 n0, const uint4 n1, const uint4 n2, const u
 
 struct TraceCounters { uint32_t nodes, tris; };
 
+// ---- cache policy of the traversal kernels ----------------------------------------------------------------------------------
+// A bounce moves ~2 GB of ray / hit / queue records through the 126 MB L2 exactly once, while every ray re-reads the same few tens of
+// MB of nodes and triangles. With default caching the stream evicts the BVH (ncu r1, C2: L2 hit 44 %). So: the streams use
+// ld.global.cs / st.global.cs (evict-first, kernels.cu: ClosestIO / ShadowIO), and node / triangle fetches carry an L2 evict_last
+// policy (createpolicy.fractional.L2::evict_last + ld.global.nc.L2::cache_hint) so that they are the last lines L2 gives up.
+#ifndef YRT_BVH_EVICT_LAST
+#define YRT_BVH_EVICT_LAST 1
+#endif
+#ifndef YRT_STREAM_HINTS
+#define YRT_STREAM_HINTS 1
+#endif
+YRT_D uint64_t bvh_policy() {
+#if YRT_BVH_EVICT_LAST
+    uint64_t p; asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p)); return p;
+#else
+    return 0ull;
+#endif
+}
+YRT_D uint4 bvh_ld(const uint4* p, uint64_t pol) {
+#if YRT_BVH_EVICT_LAST
+    uint4 v; asm("ld.global.nc.L2::cache_hint.v4.u32 {%0, %1, %2, %3}, [%4], %5;" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p), "l"(pol));
+    return v;
+#else
+    (void)pol; return __ldg(p);
+#endif
+}
+YRT_D float4 bvh_ld(const float4* p, uint64_t pol) {
+    const uint4 v = bvh_ld((const uint4*)p, pol);
+    return make_float4(__uint_as_float(v.x), __uint_as_float(v.y), __uint_as_float(v.z), __uint_as_float(v.w));
+}
+
 // While-while traversal of the compressed BVH8.  ANY: rtcOccluded semantics (first accepted hit ends).
 // Closest-hit acceptance is order independent: (t, geomID, primID) lexicographic minimum.
 template <bool ANY, bool COUNT>
@@ -254,6 +285,7 @@ YRT_D void trace_stream(const uint4* __restrict__ nodes, const float4* __restric
     uint32_t bestTri = YRT_NO_TRI, tag = 0;
     uint2 G = make_uint2(0u, 0u), T = make_uint2(0u, 0u);
     int sp = 0;
+    const uint64_t pol = bvh_policy();
 
     while (true) {
         // ---- refill idle slots ---------------------------------------------------------------------
@@ -301,7 +333,7 @@ YRT_D void trace_stream(const uint4* __restrict__ nodes, const float4* __restric
                 T.y &= ~(1u << bit);
                 const uint32_t triIdx = T.x + bit;
                 const float4* tp = tris + 3ull * triIdx;
-                const float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
+                const float4 a = bvh_ld(tp, pol), b = bvh_ld(tp + 1, pol), c = bvh_ld(tp + 2, pol);
                 if (COUNT) cnt.tris++;
                 float t, u, v, den; V3 Ng;
                 if (tri_test(r.O, r.D, V3(a.x, a.y, a.z), V3(b.x, b.y, b.z), V3(c.x, c.y, c.z), t, u, v, Ng, den) && t > tnear) {
@@ -337,7 +369,7 @@ YRT_D void trace_stream(const uint4* __restrict__ nodes, const float4* __restric
                     if (sp < YRT_STACK_SIZE) sp++;
                 }
                 const uint4* np = nodes + 5ull * nodeIdx;
-                const uint4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
+                const uint4 n0 = bvh_ld(np, pol), n1 = bvh_ld(np + 1, pol), n2 = bvh_ld(np + 2, pol), n3 = bvh_ld(np + 3, pol), n4 = bvh_ld(np + 4, pol);
                 if (COUNT) cnt.nodes++;
                 const uint32_t hm = node_test(n0, n1, n2, n3, n4, r, tnear, tbest);
                 G = make_uint2(n1.x, (hm & 0xff000000u) | (n0.w >> 24));

@@ -47,12 +47,19 @@ struct WavefrontBuffers {
     uint32_t* sortKeys; uint32_t* sortKeysOut;   // sort keys (origin cell Morton code | direction octant)
 };
 
+// A render call covers numFaces frames of one size (1 for rtRenderFrame, the 12 stereo cube cameras of a viewpoint for
+// yrtxRenderCubeMap) as ONE wavefront: the frames are stacked into a virtual pixel range [0, numFaces * pixelsPerFace), every queue,
+// counter and launch spans all of them, so bounce queues are numFaces times longer and launches numFaces times fewer.
+#define YRT_MAX_FACES 12
+struct FrameCameras { CameraData cam[YRT_MAX_FACES]; };     // by value to the ray-generation kernels only (4.9 KB of kernel parameters)
+struct FaceTarget { float4* accum; void* fb; };             // per face: accumulation buffer and packed output
+
 struct FrameConst {               // everything a frame's kernels need, passed by value
     SceneData scene;
     IntegratorData integ;
-    CameraData camera;
     const float* sampleTable;     // device
-    int width, height;            // raster size
+    int width, height;            // raster size of one face
+    int numFaces; uint32_t pixelsPerFace;   // active (this server's) pixels per face
     int serverID, serverCount;    // row-band interleave of the reference's network device (api/swapchain.h:57-70)
     float rcpWidth, rcpHeight;
     int debugRenderer;            // 1: renderers/debugrenderer.cpp semantics
@@ -60,8 +67,7 @@ struct FrameConst {               // everything a frame's kernels need, passed b
 };
 
 struct FilmParams {
-    float4* accum;                // per pixel (buffer coordinates): sum L.rgb | sum weight
-    void* fbDevice;               // packed output in the framebuffer's format
+    FaceTarget face[YRT_MAX_FACES];   // accum: per pixel (buffer coordinates) sum L.rgb | sum weight; fb: packed output in the framebuffer's format
     int format;                   // 0 RGB_FLOAT32, 1 RGBA8, 2 RGB8
     int fbStrideBytes;
     int accumulate;
@@ -75,14 +81,14 @@ struct LaunchCfg { int blocks; int threads; cudaStream_t stream; };
 
 // pixels [pixelBegin, pixelBegin+numPixels) of the *active-row* enumeration of the frame
 void launch_pixel_sets(const FrameConst& fc, uint8_t* pixelSet, int sets, LaunchCfg lc);
-void launch_raygen(const FrameConst& fc, const WavefrontBuffers& wb, uint32_t pixelBegin, uint32_t numPixels, LaunchCfg lc);
+void launch_raygen(const FrameConst& fc, const FrameCameras& cams, const WavefrontBuffers& wb, uint32_t pixelBegin, uint32_t numPixels, LaunchCfg lc);
 void launch_trace_closest(const FrameConst& fc, const WavefrontBuffers& wb, int queueSel, LaunchCfg lc);
 void launch_shade(const FrameConst& fc, const WavefrontBuffers& wb, int queueSel, uint32_t pixelBegin, int depth, LaunchCfg lc);
 void launch_trace_shadow(const FrameConst& fc, const WavefrontBuffers& wb, LaunchCfg lc);
 void launch_resolve(const FrameConst& fc, const WavefrontBuffers& wb, int queueSel, LaunchCfg lc);
 void launch_film(const FrameConst& fc, const WavefrontBuffers& wb, const FilmParams& fp, uint32_t pixelBegin, uint32_t numPixels, LaunchCfg lc);
 // renderers/debugrenderer.cpp:66-148 (maxDepth 1): primary-hit ID image written straight into the framebuffer
-void launch_debug(const FrameConst& fc, const WavefrontBuffers& wb, const FilmParams& fp, uint32_t numPixels, LaunchCfg lc);
+void launch_debug(const FrameConst& fc, const FrameCameras& cams, const WavefrontBuffers& wb, const FilmParams& fp, uint32_t numPixels, LaunchCfg lc);
 void launch_export_primary(const FrameConst& fc, const WavefrontBuffers& wb, uint32_t pixelBegin, uint32_t numPixels, float* out, LaunchCfg lc);
 // ray sort (sort.cu): keys from the extension rays of queue `queueSel`, CUB radix sort of (key, path id) into wb.queueS
 void launch_sort_keys(const FrameConst& fc, const WavefrontBuffers& wb, int queueSel, uint32_t n, LaunchCfg lc);

@@ -273,6 +273,22 @@ yrt_status yrtRenderFrame(yrt_device* dev, yrt_handle renderer, yrt_handle camer
     } catch (const std::exception& e) { return fail(e); }
 }
 
+yrt_status yrtxRenderCubeMap(yrt_device* dev, yrt_handle renderer, const yrt_handle* cameras, size_t numFaces, yrt_handle scene, yrt_handle tonemapper,
+                             const yrt_handle* fbs, int accumulate) {
+    try {
+        if (!cameras || !fbs || numFaces < 1 || numFaces > YRT_MAX_FACES) throw std::runtime_error("device_cuda: yrtxRenderCubeMap takes 1..12 cameras and frame buffers");
+        gh(renderer); gh(scene); gh(tonemapper);
+        for (size_t f = 0; f < numFaces; f++) { gh(cameras[f]); gh(fbs[f]); }
+        std::lock_guard<std::mutex> lock(dev->mutex);
+        return each_parallel(dev, [&](yrt_device* m, int i) {
+            yrt_handle c[YRT_MAX_FACES], b[YRT_MAX_FACES];
+            for (size_t f = 0; f < numFaces; f++) { c[f] = un(cameras[f], i); b[f] = un(fbs[f], i); }
+            return yrtxRenderCubeMap_core(m, un(renderer, i), c, numFaces, un(scene, i), un(tonemapper, i), b, accumulate); });
+    } catch (const std::exception& e) { return fail(e); }
+}
+
+yrt_status yrtxMicrobench(yrt_device* dev, int kind, size_t bytes, double* result) { return yrtxMicrobench_core(dev->members[0], kind, bytes, result); }
+
 // ---- extensions -----------------------------------------------------------------------------------------------------------------
 yrt_status yrtxGetFrameStats(yrt_device* dev, yrtx_frame_stats* out) {
     if (!out) return YRT_ERROR;

@@ -28,6 +28,7 @@ thread_local std::string g_lastError;
 void scene_set_primitive(yrt_device* dev, SceneHandle* sc, size_t slot, PrimHandle* prim, const Aff3* overrideXfm);
 void scene_commit(yrt_device* dev, SceneHandle* sc);
 void render_frame(yrt_device* dev, RendererHandle* r, CameraHandle* c, SceneHandle* s, ToneMapperHandle* t, FrameBufferHandle* f, int accumulate);
+void render_frames(yrt_device* dev, RendererHandle* r, size_t numFaces, CameraHandle* const* c, SceneHandle* s, ToneMapperHandle* t, FrameBufferHandle* const* f, int accumulate);
 FrameBufferHandle* framebuffer_create(yrt_device* dev, const char* type, size_t w, size_t h, size_t buffers, void** ptrs);
 void* framebuffer_map(yrt_device* dev, FrameBufferHandle* fb, int bufID);
 void trace_rays(yrt_device* dev, SceneHandle* sc, size_t n, const float* rays, void* hits, int closest, int onDevice, float* ms);
@@ -746,6 +747,16 @@ yrt_status yrtxFrameBufferDevice(yrt_device* dev, yrt_handle fb, void** devPtr, 
             if (devPtr) *devPtr = f->devPacked; if (bytes) *bytes = f->bytes(); if (strideBytes) *strideBytes = f->strideBytes)
 }
 yrt_status yrtxSetReadback(yrt_device* dev, int readbackEachFrame) { GUARD_S(dev->readback = readbackEachFrame != 0) }
+double microbench(yrt_device* dev, int kind, size_t bytes);   // microbench.cu
+yrt_status yrtxMicrobench(yrt_device* dev, int kind, size_t bytes, double* result) { GUARD_S(const double v = microbench(dev, kind, bytes); if (result) *result = v) }
+yrt_status yrtxRenderCubeMap(yrt_device* dev, yrt_handle renderer, const yrt_handle* cameras, size_t numFaces, yrt_handle scene, yrt_handle tonemapper,
+                             const yrt_handle* frameBuffers, int accumulate) {
+    GUARD_S(if (!cameras || !frameBuffers || numFaces < 1 || numFaces > YRT_MAX_FACES) throw std::runtime_error("device_cuda: yrtxRenderCubeMap takes 1..12 cameras and frame buffers");
+            CameraHandle* c[YRT_MAX_FACES]; FrameBufferHandle* f[YRT_MAX_FACES];
+            for (size_t i = 0; i < numFaces; i++) { c[i] = cast<CameraHandle>(cameras[i], HK_CAMERA, "camera"); f[i] = cast<FrameBufferHandle>(frameBuffers[i], HK_FRAMEBUFFER, "framebuffer"); }
+            render_frames(dev, cast<RendererHandle>(renderer, HK_RENDERER, "renderer"), numFaces, c, cast<SceneHandle>(scene, HK_SCENE, "scene"),
+                          cast<ToneMapperHandle>(tonemapper, HK_TONEMAPPER, "tonemapper"), f, accumulate))
+}
 
 // ---- decoded images (tests of the format readers) ----------------------------------------------------
 yrt_status yrtxReadImage(yrt_device* dev, yrt_handle image, int* width, int* height, int* format, void* pixels) {

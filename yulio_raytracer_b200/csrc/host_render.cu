@@ -188,27 +188,37 @@ static bool slot_matches(const SceneHandle::SlotLayout& L, const ScenePrim& p) {
     return true;
 }
 
-// Vertices of the patched slots are rewritten in the committed arrays and only the BVH is rebuilt. Returns false when a
-// slot changed more than its vertex data (then the caller re-flattens everything).
-static bool scene_patch(yrt_device* dev, SceneHandle* sc) {
-    if (!sc->committed || sc->structureDirty || sc->layout.size() != sc->prims.size()) return false;
+// Vertices of the patched slots are rewritten in the committed arrays and only the BVH is rebuilt. Returns 0 when a
+// slot changed more than its vertex data (then the caller re-flattens everything), 1 when vertices moved, 2 when every
+// re-set slot carries exactly the vertices already committed — the 12 stereo cube cameras of a viewpoint share their
+// origin, so the front end's per-face rtUpdatePrimitive + rtCommit (renderer.cpp:551-559) reproduces the committed scene
+// for 11 of 12 faces: nothing to rebuild.
+static int scene_patch(yrt_device* dev, SceneHandle* sc) {
+    if (!sc->committed || sc->structureDirty || sc->layout.size() != sc->prims.size()) return 0;
     for (size_t slot : sc->patchSlots) {
-        if (slot >= sc->prims.size() || !sc->prims[slot] || !slot_matches(sc->layout[slot], *sc->prims[slot])) return false;
+        if (slot >= sc->prims.size() || !sc->prims[slot] || !slot_matches(sc->layout[slot], *sc->prims[slot])) return 0;
         const SceneHandle::SlotLayout& L = sc->layout[slot];
         const ShapeObj& s = *sc->prims[slot]->shape;      // same index list and texture coordinates as committed?
-        if (L.nt && memcmp(s.triangles.data(), &sc->hostIndices[L.idxBase], L.nt * sizeof(int4)) != 0) return false;
-        if (L.nuv && memcmp(s.texcoord.data(), &sc->hostUvs[L.uvBase], L.nuv * sizeof(float2)) != 0) return false;
+        if (L.nt && memcmp(s.triangles.data(), &sc->hostIndices[L.idxBase], L.nt * sizeof(int4)) != 0) return 0;
+        if (L.nuv && memcmp(s.texcoord.data(), &sc->hostUvs[L.uvBase], L.nuv * sizeof(float2)) != 0) return 0;
     }
     cudaStream_t st = dev->stream;
+    bool moved = false;
     for (size_t slot : sc->patchSlots) {
         const SceneHandle::SlotLayout& L = sc->layout[slot];
         const ShapeObj& s = *sc->prims[slot]->shape;
-        for (size_t i = 0; i < L.nv; i++) { const V3& q = s.position[i]; sc->hostPositions[L.vtxBase + i] = make_float4(q.x, q.y, q.z, 0.f); }
-        for (size_t i = 0; i < L.nn; i++) { const V3& q = s.normal[i]; sc->hostNormals[L.nrmBase + i] = make_float4(q.x, q.y, q.z, 0.f); }
+        bool slotMoved = false;
+        auto put = [&](float4& dst, const V3& q) {
+            if (memcmp(&dst, &q, 3 * sizeof(float)) != 0) { dst = make_float4(q.x, q.y, q.z, 0.f); slotMoved = true; }
+        };
+        for (size_t i = 0; i < L.nv; i++) put(sc->hostPositions[L.vtxBase + i], s.position[i]);
+        for (size_t i = 0; i < L.nn; i++) put(sc->hostNormals[L.nrmBase + i], s.normal[i]);
+        if (!slotMoved) continue;
+        moved = true;
         if (L.nv) YRT_CK(cudaMemcpyAsync(sc->positions.p + L.vtxBase, &sc->hostPositions[L.vtxBase], L.nv * sizeof(float4), cudaMemcpyHostToDevice, st));
         if (L.nn) YRT_CK(cudaMemcpyAsync(sc->normals.p + L.nrmBase, &sc->hostNormals[L.nrmBase], L.nn * sizeof(float4), cudaMemcpyHostToDevice, st));
     }
-    return true;
+    return moved ? 1 : 2;
 }
 
 void scene_commit(yrt_device* dev, SceneHandle* sc) {
@@ -222,7 +232,9 @@ void scene_commit(yrt_device* dev, SceneHandle* sc) {
         if (dev->verbose) printf("device_cuda: commit %-10s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tc0).count());
     };
 
-    if (scene_patch(dev, sc)) {                                // vertices of a few slots moved: rebuild the BVH over the patched arrays
+    const int patched = dev->alwaysRebuild ? 0 : scene_patch(dev, sc);
+    if (patched == 2) { lap("unchanged"); sc->patchSlots.clear(); sc->dirty = false; return; }
+    if (patched == 1) {                                        // vertices of a few slots moved: rebuild the BVH over the patched arrays
         lap("patch");
         sc->patchSlots.clear();
         sc->releaseDevice();
@@ -529,17 +541,17 @@ static size_t active_rows(int height, int serverID, int serverCount) {
     return n;
 }
 
-static FrameSetup setup_frame(yrt_device* dev, RendererObj& R, const CameraData& cam, SceneHandle* sc, FrameBufferHandle* fb, int iteration) {
+static FrameSetup setup_frame(yrt_device* dev, RendererObj& R, SceneHandle* sc, FrameBufferHandle* fb, int iteration, int numFaces = 1) {
     FrameSetup fs;
     FrameConst& fc = fs.fc;
     if (sc) fc.scene = sc->data;
     fc.scene.tuneRefillMin = dev->tuneRefillMin; fc.scene.tuneTriNum = dev->tuneTriNum; fc.scene.tuneTriDen = dev->tuneTriDen; fc.scene.tuneSimple = dev->tuneSimple;
-    fc.camera = cam;
-    fc.width = (int)fb->width; fc.height = (int)fb->height;
+    fc.width = (int)fb->width; fc.height = (int)fb->height; fc.numFaces = numFaces;
     fc.serverID = dev->serverID; fc.serverCount = dev->serverCount < 1 ? 1 : dev->serverCount;
     fc.rcpWidth = rcpf(float(fb->width)); fc.rcpHeight = rcpf(float(fb->height));
     fc.debugRenderer = R.debug ? 1 : 0; fc.countStats = dev->countStats;
     fs.bufferRows = active_rows(fc.height, fc.serverID, fc.serverCount);
+    fc.pixelsPerFace = (uint32_t)(fs.bufferRows * fb->width);
     IntegratorData& ig = fc.integ;
     ig.maxDepth = R.maxDepth; ig.rrDepth = R.rrDepth; ig.minContribution = R.minContribution; ig.epsilon = R.epsilon;
     ig.tMaxShadowRay = R.tMaxShadowRay; ig.tMaxShadowJitter = R.tMaxShadowJitter; ig.up = R.up;
@@ -573,11 +585,21 @@ static FrameSetup setup_frame(yrt_device* dev, RendererObj& R, const CameraData&
 typedef void (*StatusFn)(const void*);
 struct StatusRec { int state; float progress; };               // RendererStatus  devices/device/device.h:341-344
 
-void render_frame(yrt_device* dev, RendererHandle* rh, CameraHandle* ch, SceneHandle* sc, ToneMapperHandle* th, FrameBufferHandle* fb, int accumulate) {
+// rtRenderFrame (numFaces = 1) and yrtxRenderCubeMap (the faces of one viewpoint, same scene / renderer / tone mapper / frame size):
+// all faces are rendered as one wavefront (device_internal.hpp: FrameConst::numFaces).
+void render_frames(yrt_device* dev, RendererHandle* rh, size_t numFaces, CameraHandle* const* chs, SceneHandle* sc, ToneMapperHandle* th,
+                   FrameBufferHandle* const* fbs, int accumulate) {
     const auto tHost0 = std::chrono::steady_clock::now();
     auto hostLap = [&](const char* what) { if (dev->verbose >= 3) printf("  host %-10s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tHost0).count()); };
     if (!rh->inst) throw std::runtime_error("invalid renderer value");
-    if (!ch->inst) throw std::runtime_error("invalid camera value");
+    if (numFaces < 1 || numFaces > YRT_MAX_FACES) throw std::runtime_error("device_cuda: a render call takes 1.." + std::to_string(YRT_MAX_FACES) + " faces");
+    for (size_t f = 0; f < numFaces; f++) {
+        if (!chs[f]->inst) throw std::runtime_error("invalid camera value");
+        if (fbs[f]->width != fbs[0]->width || fbs[f]->height != fbs[0]->height || fbs[f]->format != fbs[0]->format)
+            throw std::runtime_error("device_cuda: the frame buffers of one render call must have the same size and format");
+        for (size_t g = 0; g < f; g++) if (fbs[g] == fbs[f]) throw std::runtime_error("device_cuda: every face of a render call needs its own frame buffer");
+    }
+    FrameBufferHandle* fb = fbs[0];
     if (!th->inst) throw std::runtime_error("invalid tonemapper value");
     if (!sc->committed) throw std::runtime_error("invalid scene value");
     RendererObj& R = *rh->inst;
@@ -590,8 +612,10 @@ void render_frame(yrt_device* dev, RendererHandle* rh, CameraHandle* ch, SceneHa
     volatile bool* stopFlag = (volatile bool*)R.stopFlag;      // std::atomic<bool>* in the caller (integratorrenderer.h:100-101)
     auto stopRequested = [&]() { return stopFlag && *stopFlag; };
 
-    FrameSetup fs = setup_frame(dev, R, *ch->inst, sc, fb, iteration);
+    FrameSetup fs = setup_frame(dev, R, sc, fb, iteration, (int)numFaces);
     FrameConst& fc = fs.fc;
+    FrameCameras cams; memset(&cams, 0, sizeof(cams));
+    for (size_t f = 0; f < numFaces; f++) cams.cam[f] = *chs[f]->inst;
     if (R.backplate && !R.debug) {                             // backplate image joins the scene's texture table on first use
         int idx = -1;
         for (size_t i = 0; i < sc->hostTextures.size(); i++) if (sc->hostTextures[i].data == R.backplate->devPixels && R.backplate->devPixels) idx = (int)i;
@@ -607,7 +631,9 @@ void render_frame(yrt_device* dev, RendererHandle* rh, CameraHandle* ch, SceneHa
     }
 
     const int spp = fc.integ.spp;
-    const size_t numPixels = fs.bufferRows * fb->width;
+    const size_t facePixels = fs.bufferRows * fb->width;
+    const size_t numPixels = facePixels * numFaces;          // the virtual pixel range of the call
+    if ((uint64_t)numPixels >= 0xfff00000ull) throw std::runtime_error("device_cuda: render call exceeds 2^32 pixels");
     const int nl = fc.scene.numLights > 0 ? fc.scene.numLights : 1;
     // chunk size: paths per wavefront pass, bounded so that one shadow-ray slot per (path, light) fits
     uint64_t capacity = dev->chunkPaths;
@@ -624,7 +650,7 @@ void render_frame(yrt_device* dev, RendererHandle* rh, CameraHandle* ch, SceneHa
     if (capacity < (uint64_t)spp) capacity = spp;
     const uint32_t pixelsPerChunk = (uint32_t)(capacity / spp);
     capacity = (uint64_t)pixelsPerChunk * spp;
-    dev->wf.ensure((uint32_t)capacity, (uint32_t)(capacity * nl), numPixels);
+    dev->wf.ensure((uint32_t)capacity, (uint32_t)(capacity * nl), facePixels);
     const WavefrontBuffers& wb = dev->wf.wb;
 
     hostLap("setup");
@@ -636,13 +662,14 @@ void render_frame(yrt_device* dev, RendererHandle* rh, CameraHandle* ch, SceneHa
     cudaEvent_t evStart = tm.get(), evStop = tm.get();
     YRT_CK(cudaEventRecord(evStart, st));
 
-    FilmParams fp; fp.accum = fb->accum; fp.fbDevice = fb->devPacked; fp.format = fb->format; fp.fbStrideBytes = (int)fb->strideBytes;
+    FilmParams fp; memset(&fp, 0, sizeof(fp)); fp.format = fb->format; fp.fbStrideBytes = (int)fb->strideBytes;
+    for (size_t f = 0; f < numFaces; f++) { fp.face[f].accum = fbs[f]->accum; fp.face[f].fb = fbs[f]->devPacked; }
     fp.accumulate = accumulate ? 1 : 0; fp.gamma = th->inst->gamma; fp.rcpGamma = rcpf(th->inst->gamma); fp.vignetting = th->inst->vignetting ? 1 : 0;
 
     bool stopped = false;
     if (R.debug) {
         if (R.maxDepth > 1) throw std::runtime_error("device_cuda: the debug renderer supports maxDepth = 1 only");
-        launch_debug(fc, wb, fp, (uint32_t)numPixels, lcStream); launches++;
+        launch_debug(fc, cams, wb, fp, (uint32_t)numPixels, lcStream); launches++;
     } else if (numPixels) {
         launch_pixel_sets(fc, wb.pixelSet, fs.sets, lcStream); launches++;
         if (fc.integ.maxDepth <= 0) YRT_CK(cudaMemsetAsync(wb.Lacc, 0, (size_t)capacity * sizeof(float4), st));   // no bounce writes the radiance
@@ -657,7 +684,7 @@ void render_frame(yrt_device* dev, RendererHandle* rh, CameraHandle* ch, SceneHa
             if (stopRequested()) { stopped = true; break; }
             const uint32_t np = (uint32_t)std::min<size_t>(pixelsPerChunk, numPixels - pixelBegin);
             if (timers) tm.begin(TK_RAYGEN_FILM, st);
-            launch_raygen(fc, wb, (uint32_t)pixelBegin, np, lcStream); launches++;
+            launch_raygen(fc, cams, wb, (uint32_t)pixelBegin, np, lcStream); launches++;
             if (timers) tm.end(st);
             int q = 0;
             uint32_t alive = np * (uint32_t)spp;                 // length of the current queue, known on the host
@@ -704,10 +731,13 @@ void render_frame(yrt_device* dev, RendererHandle* rh, CameraHandle* ch, SceneHa
     YRT_CK(cudaEventRecord(evStop, st));
     hostLap("enqueued");
     uint64_t d2h = 0;
-    if (dev->readback) {
-        YRT_CK(cudaMemcpyAsync(fb->host[fb->cur], fb->devPacked, fb->bytes(), cudaMemcpyDeviceToHost, st));
-        d2h = fb->bytes(); fb->pendingBuf = -1;
-    } else fb->pendingBuf = (int)fb->cur;
+    for (size_t f = 0; f < numFaces; f++) {
+        FrameBufferHandle* b = fbs[f];
+        if (dev->readback) {
+            YRT_CK(cudaMemcpyAsync(b->host[b->cur], b->devPacked, b->bytes(), cudaMemcpyDeviceToHost, st));
+            d2h += b->bytes(); b->pendingBuf = -1;
+        } else b->pendingBuf = (int)b->cur;
+    }
     unsigned long long hstats[4] = {0, 0, 0, 0};
     YRT_CK(cudaMemcpyAsync(hstats, wb.stats, sizeof(hstats), cudaMemcpyDeviceToHost, st));
     YRT_CK(cudaStreamSynchronize(st));
@@ -745,6 +775,9 @@ void render_frame(yrt_device* dev, RendererHandle* rh, CameraHandle* ch, SceneHa
     }
     if (statusFn) { status.state = 2; status.progress = 1.f; statusFn(&status); }   // updateStatus(Done)
     (void)stopped;
+}
+void render_frame(yrt_device* dev, RendererHandle* rh, CameraHandle* ch, SceneHandle* sc, ToneMapperHandle* th, FrameBufferHandle* fb, int accumulate) {
+    render_frames(dev, rh, 1, &ch, sc, th, &fb, accumulate);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -793,8 +826,9 @@ void primary_rays(yrt_device* dev, RendererHandle* rh, CameraHandle* ch, FrameBu
     RendererObj& R = *rh->inst;
     if (R.debug) throw std::runtime_error("device_cuda: yrtxPrimaryRays needs the pathtracer renderer");
     cudaStream_t st = dev->stream;
-    FrameSetup fs = setup_frame(dev, R, *ch->inst, nullptr, fb, 0);
+    FrameSetup fs = setup_frame(dev, R, nullptr, fb, 0);
     FrameConst& fc = fs.fc;
+    FrameCameras cams; memset(&cams, 0, sizeof(cams)); cams.cam[0] = *ch->inst;
     const int spp = fc.integ.spp;
     const size_t numPixels = fs.bufferRows * fb->width;
     uint32_t pixelsPerChunk = (uint32_t)std::max<size_t>(1, std::min<size_t>(numPixels, (1u << 22) / (size_t)spp));
@@ -805,7 +839,7 @@ void primary_rays(yrt_device* dev, RendererHandle* rh, CameraHandle* ch, FrameBu
     DevBuf<float> out; out.alloc((size_t)pixelsPerChunk * spp * 8);
     for (size_t pixelBegin = 0; pixelBegin < numPixels; pixelBegin += pixelsPerChunk) {
         const uint32_t np = (uint32_t)std::min<size_t>(pixelsPerChunk, numPixels - pixelBegin);
-        launch_raygen(fc, wb, (uint32_t)pixelBegin, np, lc);
+        launch_raygen(fc, cams, wb, (uint32_t)pixelBegin, np, lc);
         launch_export_primary(fc, wb, (uint32_t)pixelBegin, np, out.p, lc);
         YRT_CK(cudaMemcpyAsync(rays + pixelBegin * spp * 8, out.p, (size_t)np * spp * 32, cudaMemcpyDeviceToHost, st));
         YRT_CK(cudaStreamSynchronize(st));

@@ -64,12 +64,21 @@ void launch_pixel_sets(const FrameConst& fc, uint8_t* pixelSet, int sets, Launch
     k_pixel_sets<<<(tiles + 63) / 64, 64, 0, lc.stream>>>(fc, pixelSet, sets);
 }
 
-// path p of a chunk -> (buffer pixel, sample); raster coordinates
-struct PathCoord { int bx, by, x, y, s; uint32_t bp; };
+// virtual pixel (pixelBegin + p) of a render call -> face, buffer pixel within the face
+struct PixelCoord { int face, bx, by; uint32_t bp; };
+__device__ __forceinline__ PixelCoord pixel_coord(const FrameConst& fc, uint32_t vp) {
+    PixelCoord c;
+    c.face = fc.numFaces > 1 ? (int)(vp / fc.pixelsPerFace) : 0;
+    c.bp = vp - (uint32_t)c.face * fc.pixelsPerFace;
+    c.by = (int)(c.bp / (uint32_t)fc.width); c.bx = (int)(c.bp % (uint32_t)fc.width);
+    return c;
+}
+// path p of a chunk -> (face, buffer pixel, sample); raster coordinates
+struct PathCoord { int face, bx, by, x, y, s; uint32_t bp; };
 __device__ __forceinline__ PathCoord path_coord(const FrameConst& fc, uint32_t pixelBegin, uint32_t pid) {
     PathCoord c; const uint32_t spp = (uint32_t)fc.integ.spp;
-    c.bp = pixelBegin + pid / spp; c.s = (int)(pid % spp);
-    c.by = (int)(c.bp / (uint32_t)fc.width); c.bx = (int)(c.bp % (uint32_t)fc.width);
+    const PixelCoord q = pixel_coord(fc, pixelBegin + pid / spp);
+    c.face = q.face; c.bp = q.bp; c.s = (int)(pid % spp); c.by = q.by; c.bx = q.bx;
     c.x = c.bx; c.y = buffer2raster(c.by, fc.serverID, fc.serverCount);
     return c;
 }
@@ -77,12 +86,12 @@ __device__ __forceinline__ const float* sample_rec(const FrameConst& fc, const u
     return fc.sampleTable + ((size_t)pixelSet[c.bp] * fc.integ.spp + c.s) * fc.integ.recFloats;
 }
 
-__global__ void __launch_bounds__(256) k_raygen(FrameConst fc, WavefrontBuffers wb, uint32_t pixelBegin, uint32_t numPaths) {
+__global__ void __launch_bounds__(256) k_raygen(FrameConst fc, const __grid_constant__ FrameCameras cams, WavefrontBuffers wb, uint32_t pixelBegin, uint32_t numPaths) {
     for (uint32_t pid = blockIdx.x * blockDim.x + threadIdx.x; pid < numPaths; pid += gridDim.x * blockDim.x) {
         const PathCoord c = path_coord(fc, pixelBegin, pid);
         const float* rec = sample_rec(fc, wb.pixelSet, c);
         const float fx = (float(c.x) + rec[0]) * fc.rcpWidth, fy = (float(c.y) + rec[1]) * fc.rcpHeight;   // integratorrenderer.cpp:156-157
-        V3 org, dir; camera_ray(fc.camera, fx, fy, rec[3], rec[4], org, dir);
+        V3 org, dir; camera_ray(cams.cam[c.face], fx, fy, rec[3], rec[4], org, dir);
         wb.rayO[pid] = make_float4(org.x, org.y, org.z, 0.f);
         wb.rayD[pid] = make_float4(dir.x, dir.y, dir.z, INFINITY);
         // throughput (1, unbent), radiance (0) and medium (vacuum) of a fresh path are implied: k_shade(depth 0) does not read them
@@ -90,8 +99,8 @@ __global__ void __launch_bounds__(256) k_raygen(FrameConst fc, WavefrontBuffers 
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) { wb.counters[0] = numPaths; wb.counters[1] = 0; wb.counters[2] = 0; wb.counters[4] = 0; wb.counters[5] = 0; }
 }
-void launch_raygen(const FrameConst& fc, const WavefrontBuffers& wb, uint32_t pixelBegin, uint32_t numPixels, LaunchCfg lc) {
-    k_raygen<<<lc.blocks, 256, 0, lc.stream>>>(fc, wb, pixelBegin, numPixels * (uint32_t)fc.integ.spp);
+void launch_raygen(const FrameConst& fc, const FrameCameras& cams, const WavefrontBuffers& wb, uint32_t pixelBegin, uint32_t numPixels, LaunchCfg lc) {
+    k_raygen<<<lc.blocks, 256, 0, lc.stream>>>(fc, cams, wb, pixelBegin, numPixels * (uint32_t)fc.integ.spp);
 }
 
 __global__ void k_export_primary(FrameConst fc, WavefrontBuffers wb, uint32_t numPaths, float* __restrict__ out) {
@@ -105,24 +114,31 @@ void launch_export_primary(const FrameConst& fc, const WavefrontBuffers& wb, uin
 
 // ---- traversal kernels (persistent warps over the ray queues, bvh.cuh: trace_stream) -----------------------
 // counters[4] / [5] / [6]: next unclaimed queue position of the closest-hit / any-hit / user launch
+#if YRT_STREAM_HINTS
+#define YRT_LD_STREAM(p) __ldcs(p)
+#define YRT_ST_STREAM(p, v) __stcs(p, v)
+#else
+#define YRT_LD_STREAM(p) (*(p))
+#define YRT_ST_STREAM(p, v) (*(p) = (v))
+#endif
 struct ClosestIO {
     WavefrontBuffers wb; const uint32_t* __restrict__ queue;
     __device__ __forceinline__ uint32_t load(uint32_t i, V3& O, V3& D, float& tnear, float& tfar) const {
-        const uint32_t pid = queue[i];
-        const float4 o = wb.rayO[pid], d = wb.rayD[pid];
+        const uint32_t pid = YRT_LD_STREAM(&queue[i]);
+        const float4 o = YRT_LD_STREAM(&wb.rayO[pid]), d = YRT_LD_STREAM(&wb.rayD[pid]);
         O = f4v(o); D = f4v(d); tnear = o.w; tfar = d.w;
         return pid;
     }
     // the wavefront's hit record is (t, u, v, leaf-order triangle index): k_shade finds everything else in SceneData::triShade
     __device__ __forceinline__ void store_hit(uint32_t pid, float t, float u, float v, uint32_t tri, const float4*) const {
-        wb.hitA[pid] = make_float4(t, u, v, __int_as_float(tri == YRT_NO_TRI ? -1 : (int)tri));
+        YRT_ST_STREAM(&wb.hitA[pid], make_float4(t, u, v, __int_as_float(tri == YRT_NO_TRI ? -1 : (int)tri)));
     }
     __device__ __forceinline__ void store_any(uint32_t, bool) const {}
 };
 struct ShadowIO {
     WavefrontBuffers wb;
     __device__ __forceinline__ uint32_t load(uint32_t i, V3& O, V3& D, float& tnear, float& tfar) const {
-        const float4 o = wb.shO[i], d = wb.shD[i];
+        const float4 o = YRT_LD_STREAM(&wb.shO[i]), d = YRT_LD_STREAM(&wb.shD[i]);
         O = f4v(o); D = f4v(d); tnear = o.w; tfar = d.w;
         return i;
     }
@@ -483,13 +499,13 @@ void launch_resolve(const FrameConst& fc, const WavefrontBuffers& wb, int queueS
 // ---- film: per-pixel sample sum, accumulation buffer, tone mapping, packing -------------------
 // SwapChain::update -> AccuBuffer::update api/framebuffer.h:289-304; DefaultToneMapper::eval
 // tonemappers/defaulttonemapper.h:38-51; FrameBufferRGB8/RGBA8/RGBFloat32::set api/framebuffer.h:127-129,171-178,220-226
-__device__ __forceinline__ void pack_pixel(const FilmParams& fp, int bx, int by, Col c) {
+__device__ __forceinline__ void pack_pixel(const FilmParams& fp, void* fb, int bx, int by, Col c) {
     if (fp.format == 0) {
-        float* o = (float*)((char*)fp.fbDevice + (size_t)by * fp.fbStrideBytes) + 3 * bx;
+        float* o = (float*)((char*)fb + (size_t)by * fp.fbStrideBytes) + 3 * bx;
         o[0] = c.x; o[1] = c.y; o[2] = c.z;
     } else {
         const int bpp = fp.format == 1 ? 4 : 3;
-        unsigned char* o = (unsigned char*)fp.fbDevice + (size_t)by * fp.fbStrideBytes + bpp * bx;
+        unsigned char* o = (unsigned char*)fb + (size_t)by * fp.fbStrideBytes + bpp * bx;
         o[0] = (unsigned char)rclamp(c.x * 255.0f, 0.0f, 255.0f);
         o[1] = (unsigned char)rclamp(c.y * 255.0f, 0.0f, 255.0f);
         o[2] = (unsigned char)rclamp(c.z * 255.0f, 0.0f, 255.0f);
@@ -497,23 +513,25 @@ __device__ __forceinline__ void pack_pixel(const FilmParams& fp, int bx, int by,
     }
 }
 
-__global__ void __launch_bounds__(256) k_film(FrameConst fc, WavefrontBuffers wb, FilmParams fp, uint32_t pixelBegin, uint32_t numPixels) {
+__global__ void __launch_bounds__(256) k_film(FrameConst fc, const __grid_constant__ FilmParams fp, WavefrontBuffers wb, uint32_t pixelBegin, uint32_t numPixels) {
     const int spp = fc.integ.spp;
     for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < numPixels; p += gridDim.x * blockDim.x) {
         Col L(0.f);
-        for (int s = 0; s < spp; s++) { const float4 l = wb.Lacc[(size_t)p * spp + s]; L += Col(l.x, l.y, l.z); }
-        const uint32_t bp = pixelBegin + p;
-        const int bx = bp % fc.width, by = bp / fc.width;
+        for (int s = 0; s < spp; s++) { const float4 l = __ldcs(&wb.Lacc[(size_t)p * spp + s]); L += Col(l.x, l.y, l.z); }
+        const PixelCoord pc = pixel_coord(fc, pixelBegin + p);
+        const uint32_t bp = pc.bp;
+        const int bx = pc.bx, by = pc.by;
         const int y = buffer2raster(by, fc.serverID, fc.serverCount);
         const float weight = (float)spp;
+        float4* __restrict__ accum = fp.face[pc.face].accum;
         Col L0;
         if (fp.accumulate) {
-            const float4 cur = fp.accum[bp];
+            const float4 cur = accum[bp];
             const float4 next = make_float4(cur.x + L.x, cur.y + L.y, cur.z + L.z, cur.w + weight);
-            fp.accum[bp] = next;
+            accum[bp] = next;
             L0 = Col(next.x, next.y, next.z) * rcpf(next.w);
         } else {
-            fp.accum[bp] = make_float4(L.x, L.y, L.z, weight);
+            accum[bp] = make_float4(L.x, L.y, L.z, weight);
             L0 = L * rcpf(weight);
         }
         Col c = L0;
@@ -524,26 +542,27 @@ __global__ void __launch_bounds__(256) k_film(FrameConst fc, WavefrontBuffers wb
             const float d = sqrtf(ddx * ddx + ddy * ddy);
             c *= powf(cosf(d * 0.5f), 3.0f);
         }
-        pack_pixel(fp, bx, by, c);
+        pack_pixel(fp, fp.face[pc.face].fb, bx, by, c);
     }
 }
 void launch_film(const FrameConst& fc, const WavefrontBuffers& wb, const FilmParams& fp, uint32_t pixelBegin, uint32_t numPixels, LaunchCfg lc) {
-    k_film<<<lc.blocks, 256, 0, lc.stream>>>(fc, wb, fp, pixelBegin, numPixels);
+    k_film<<<lc.blocks, 256, 0, lc.stream>>>(fc, fp, wb, pixelBegin, numPixels);
 }
 
 
 // ---- debug renderer (renderers/debugrenderer.cpp:66-148, maxDepth 1) -----------------------------
 // Primary rays through the pixel corners with the fixed lens sample (0.5, 0.5); colour = hash of geomID + primID,
 // written without tone mapping or accumulation.
-__global__ void __launch_bounds__(128) k_debug(FrameConst fc, WavefrontBuffers wb, FilmParams fp, uint32_t numPixels) {
+__global__ void __launch_bounds__(128) k_debug(FrameConst fc, const __grid_constant__ FrameCameras cams, const __grid_constant__ FilmParams fp, WavefrontBuffers wb, uint32_t numPixels) {
     const SceneData& sc = fc.scene;
     unsigned long long rays = 0;
     for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < numPixels; p += gridDim.x * blockDim.x) {
-        const int bx = p % fc.width, by = p / fc.width;
+        const PixelCoord pc = pixel_coord(fc, p);
+        const int bx = pc.bx, by = pc.by;
         const int y = buffer2raster(by, fc.serverID, fc.serverCount);
         const float fx = float(bx) * fc.rcpWidth, fy = float(y) * fc.rcpHeight;
         for (int i = 0; i < fc.integ.spp; i++) {
-            V3 org, dir; camera_ray(fc.camera, fx, fy, 0.5f, 0.5f, org, dir);
+            V3 org, dir; camera_ray(cams.cam[pc.face], fx, fy, 0.5f, 0.5f, org, dir);
             HitRec h; TraceCounters cnt = {0, 0};
             if (fc.integ.maxDepth > 0) { trace_ray<false, false>((const uint4*)sc.nodes, sc.tris, sc.numNodes, org, dir, 0.f, INFINITY, h, &cnt); rays++; }
             else { h.geomID = -1; h.primID = -1; }
@@ -554,13 +573,13 @@ __global__ void __launch_bounds__(128) k_debug(FrameConst fc, WavefrontBuffers w
                         float((7342453u * ((unsigned)(id + 8237))) % 255u) / 255.0f,
                         float((9234454u * ((unsigned)(id + 2343))) % 255u) / 255.0f);
             }
-            pack_pixel(fp, bx, by, c);
+            pack_pixel(fp, fp.face[pc.face].fb, bx, by, c);
         }
     }
     if (rays) atomicAdd(&wb.stats[0], rays);
 }
-void launch_debug(const FrameConst& fc, const WavefrontBuffers& wb, const FilmParams& fp, uint32_t numPixels, LaunchCfg lc) {
-    k_debug<<<lc.blocks, 128, 0, lc.stream>>>(fc, wb, fp, numPixels);
+void launch_debug(const FrameConst& fc, const FrameCameras& cams, const WavefrontBuffers& wb, const FilmParams& fp, uint32_t numPixels, LaunchCfg lc) {
+    k_debug<<<lc.blocks, 128, 0, lc.stream>>>(fc, cams, fp, wb, numPixels);
 }
 
 }  // namespace yrt

@@ -79,6 +79,8 @@ _OPTIONAL = {
     "yrtxSampleTable": (C.c_int, [H, H, C.c_int] + [C.POINTER(C.c_int)] * 4 + [C.c_void_p]),
     "yrtxFrameBufferDevice": (C.c_int, [H, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
     "yrtxSetReadback": (C.c_int, [C.c_int]),
+    "yrtxMicrobench": (C.c_int, [C.c_int, C.c_size_t, C.POINTER(C.c_double)]),
+    "yrtxRenderCubeMap": (C.c_int, [H, C.c_void_p, C.c_size_t, H, H, C.c_void_p, C.c_int]),
     "yrtxReadImage": (C.c_int, [H] + [C.POINTER(C.c_int)] * 3 + [C.c_void_p]),
     "yrtxStripBegin": (C.c_int, [C.c_size_t, C.c_size_t]), "yrtxStripSetWatermark": (C.c_int, [_P]),
     "yrtxStripAddFace": (C.c_int, [H, C.c_int, C.c_int]), "yrtxStripRead": (C.c_int, [C.c_void_p]),
@@ -290,6 +292,19 @@ class Device:
     # ---- render calls (device.h:322-329) ---------------------------------------------
     def rtRenderFrame(self, renderer, camera, scene, tonemapper, framebuffer, accumulate=0):
         self._s("yrtRenderFrame", renderer, camera, scene, tonemapper, framebuffer, int(accumulate))
+
+    def microbench(self, kind: int, nbytes: int = 0) -> float:
+        """yrtxMicrobench: 0 FP32 FMA TFLOP/s, 1 read GB/s over an nbytes working set (L1 bypassed), 2 G warp-instructions/s."""
+        v = C.c_double(0)
+        self._s("yrtxMicrobench", int(kind), int(nbytes), C.byref(v))
+        return v.value
+
+    def render_cube_map(self, renderer, cameras, scene, tonemapper, framebuffers, accumulate=0):
+        """yrtxRenderCubeMap: the faces of one viewpoint (1..12 cameras, one frame buffer each) as one wavefront."""
+        n = len(cameras)
+        assert n == len(framebuffers)
+        cams = (C.c_void_p * n)(*cameras); fbs = (C.c_void_p * n)(*framebuffers)
+        self._s("yrtxRenderCubeMap", renderer, cams, n, scene, tonemapper, fbs, int(accumulate))
 
     def rtPick(self, camera, x: float, y: float, scene):
         """(hit, (px, py, pz)) — device.h:329."""
