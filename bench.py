@@ -1,25 +1,28 @@
 #!/usr/bin/env python3
-"""bench.py — the reference's headline benchmark on device_cuda: Mrays/s (path segments) and seconds per stereo
-cube map, driven through the C-ABI (include/yrt_device.h) exactly as the reference's outputMode loop drives a device
+"""bench.py — the reference's headline benchmark on device_cuda: Mrays/s (path segments) and seconds per stereo cube map,
+driven through the C-ABI (include/yrt_device.h) as the reference's outputMode loop drives a device
 (devices/renderer/renderer.cpp:543-632).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c3|c4|c1] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c4|c3|c2|c1|c5] [--impl reference]
 
-A "step" is one rtRenderFrame of one stereo cube face of the workload (BASELINE.json configs[1] by default: the
-sphere_glass scene, 1024x1024 per face, 64 spp, depth 8, 12 stereo cube cameras); K steps walk the faces 0..11
-cyclically, so the default K = 12 is exactly one stereo cube map. Metric = the reference's own counter and timer span:
+A "step" is ONE STEREO CUBE MAP of the workload: the 12 stereo cube cameras of a viewpoint (ColladaLoader.cpp:470-505), rendered by
+yrtxRenderCubeMap as one wavefront after the camera-aligned primitives were turned and the scene committed (renderer.cpp:551-559).
+Default workload = BASELINE.json configs[3], the north-star target: the sample-scene stand-in "office" (the .dae is stripped from the
+reference mount; its 152 real texture images are not: data/sample_scene, read through rtNewImageFromFile), 2048x2048 per face, 16 spp
+(rt_test_dll.cpp:17), DLL defaults otherwise (YulioRT.h:37-50). Metric = the reference's own counter and timer span:
 (rtcIntersect + rtcOccluded equivalents) / render time (integratorrenderer.cpp:99-111, pathtraceintegrator.cpp:74,161).
 
-  value   device-timed (CUDA events on the device's stream around the wavefront loop), frame left in HBM
-  e2e     host wall-clock of the reference-facing loop per face: rtUpdatePrimitive x prims, rtCommit(scene),
-          rtRenderFrame, rtSwapBuffers, rtMapFrameBuffer -> the frame is in the (pinned) host buffer; host->device
-          bytes = sample table / constants actually uploaded, device->host bytes = the frame
-  N > 1   (without torchrun: one process, the group device of csrc/group_api.cu, cfg gpus=N)
-          one process per GPU (torchrun, the driver's launch); the scene is replicated, every face is split into the reference's 4-row
-          bands dealt round-robin to the ranks (api/swapchain.h:57-70, the reference's own network-device partition) and
-          the bands are gathered on rank 0 over NCCL; strong scaling (total work fixed).
---impl reference runs the reference's own CPU path (oracle/_ref: devices/device_singleray sources + embree2 shim) on all
-host cores on a bounded sample (same scene, camera, spp and depth at a reduced face resolution).
+  value   device-timed (CUDA events on the device's stream around the wavefront loop, + the band gather for N > 1), frames left in HBM
+  e2e     host wall-clock of the reference-facing loop per cube map: 12 x rtNewCamera, rtUpdatePrimitive x prims, rtCommit(scene),
+          yrtxRenderCubeMap, rtSwapBuffers + rtMapFrameBuffer x 12 -> every frame is in a (pinned) host buffer
+  N > 1   one process per GPU (torchrun, the driver's launch): the scene is replicated, every face is split into the reference's 4-row
+          bands dealt round-robin to the ranks (api/swapchain.h:57-70, the reference's own network-device partition), each rank renders
+          its bands of all 12 faces as one wavefront, ONE NCCL all-gather per cube map brings them to rank 0; strong scaling.
+          (--gpus N without torchrun: one process, the in-process group device, cfg gpus=N.)
+--impl reference / cpu_baseline: the reference's own CPU path (oracle/_ref: devices/device_singleray sources built -O3 -ffast-math + the
+embree2-API shim) on all host cores; each step is a bounded sample of the SAME faces at the SAME size: every B-th 4-row band of a face
+(the reference's own serverID/serverCount partition), B chosen so that a step is ~2 M paths.
+--workload c5: BASELINE configs[4], raw traversal of a synthetic triangle soup (--tris), rays split over the ranks.
 """
 import argparse
 import json
@@ -36,44 +39,52 @@ import numpy as np  # noqa: E402
 
 METRIC = "Mrays/s (path segments)"
 WORKLOADS = {
-    # name: (builder, description, face size, spp, depth)
-    "c2": ("spheres", "C2 sphere_glass.xml + sphere_view.ecs: stereo cube face 1024x1024, 64 spp, depth 8 (procedural lines texture stands in for lines.ppm)", 1024, 64, 8),
-    "c3": ("atrium", "C3 stand-in (Sponza.DAE stripped): procedural atrium ~276k tris, Uber+alpha+dome light, stereo cube face 1024x1024, 64 spp, depth 10, tMaxShadowRay 120", 1024, 64, 10),
-    "c4": ("atrium4", "C4 stand-in (22 Frederick St .dae stripped): procedural atrium ~1.1M tris, Uber+alpha+thin glass+billboard+dome light, stereo cube face 2048x2048, 16 spp (rt_test_dll.cpp:17), depth 10, tMaxShadowRay 120", 2048, 16, 10),
-    "c1": ("cornell", "C1 cornell_box.ecs: pinhole 512x512, 16 spp, depth 2", 512, 16, 2),
+    # name: (builder, description, face size, spp, depth, faces per step)
+    "c4": ("office", "C4 sample-scene stand-in (22 Frederick St .dae stripped from the mount): procedural office, 1.20 M triangles, the scene's 152 REAL "
+                     "texture images (273 MB as RGBA8, 30 with alpha) on Uber / ThinDielectric materials through rtNewImageFromFile, billboard, dome light, "
+                     "DLL defaults (depth 10, tMaxShadowRay 120, toe-in stereo); stereo cube map = 12 faces of 2048x2048, 16 spp (rt_test_dll.cpp:17)", 2048, 16, 10, 12),
+    "c3": ("atrium", "C3 Sponza stand-in (Sponza.DAE stripped): procedural atrium, 294 k triangles, the 14 REAL models/Sponza JPG textures + 2 RGBA cut-outs, "
+                     "Uber + alpha + dome light, tMaxShadowRay 120; stereo cube map = 12 faces of 1024x1024, 64 spp, depth 10", 1024, 64, 10, 12),
+    "c2": ("spheres", "C2 sphere_glass.xml + sphere_view.ecs: stereo cube map = 12 faces of 1024x1024, 64 spp, depth 8 (procedural lines texture stands in for lines.ppm)", 1024, 64, 8, 12),
+    "c1": ("cornell", "C1 cornell_box.ecs: pinhole 512x512, 16 spp, depth 2 (one frame per step)", 512, 16, 2, 1),
 }
 
 
 def build_workload(dev, name, size, spp, depth, fmt):
-    from tests import scenes
+    from yulio_raytracer_b200 import workloads as W
     kind = WORKLOADS[name][0]
-    if kind == "spheres":
-        return scenes.spheres(dev, "glass", size, size, spp, depth, face=0, fmt=fmt)
+    if kind == "office":
+        return W.office(dev, size, size, spp, depth, face=0, detail=112, fmt=fmt)
     if kind == "atrium":
-        return scenes.atrium(dev, size, size, spp, depth, face=0, detail=56, fmt=fmt)
-    if kind == "atrium4":
-        return scenes.atrium(dev, size, size, spp, depth, face=0, detail=112, fmt=fmt, tex_size=512)
-    s = scenes.cornell(dev, size, size, spp, depth, fmt=fmt)
+        return W.atrium(dev, size, size, spp, depth, face=0, detail=56, fmt=fmt, tex_set="sponza")
+    if kind == "spheres":
+        return W.spheres(dev, "glass", size, size, spp, depth, face=0, fmt=fmt)
+    s = W.cornell(dev, size, size, spp, depth, fmt=fmt)
     s.view = None
     return s
 
 
-def face_camera(dev, s, face):
-    from tests import scenes
+def make_cameras(dev, s, faces):
+    from yulio_raytracer_b200 import workloads as W
     if s.view is None:
-        return s.camera
-    pos, target, up = s.view
-    return scenes.stereo_camera(dev, face % 12, pos, target, up)
+        return [s.camera]
+    return W.cube_cameras(dev, s, faces=range(faces))
 
 
-def render_face(dev, s, cam, update=True):
-    """One iteration of the outputMode loop (renderer.cpp:551-580)."""
-    if update and s.view is not None:
-        org = dev.rtGetFloat3(cam, "origin")
-        for j, p in enumerate(s.prims):
-            dev.rtUpdatePrimitive(s.scene, j, p, org, s.view[2])
-        dev.rtCommit(s.scene)
-    dev.rtRenderFrame(s.renderer, cam, s.scene, s.tonemapper, s.framebuffer, 0)
+def render_step(dev, s, cams, fbs, per_face=False):
+    """One stereo cube map: the per-viewpoint body of outputMode (renderer.cpp:551-580)."""
+    from yulio_raytracer_b200 import workloads as W
+    if s.view is None:
+        dev.rtRenderFrame(s.renderer, cams[0], s.scene, s.tonemapper, fbs[0], 0)
+    elif per_face:                                      # the reference's literal loop: update, commit, render — per face
+        for cam, fb in zip(cams, fbs):
+            org = dev.rtGetFloat3(cam, "origin")
+            for j, p in enumerate(s.prims):
+                dev.rtUpdatePrimitive(s.scene, j, p, org, s.view[2])
+            dev.rtCommit(s.scene)
+            dev.rtRenderFrame(s.renderer, cam, s.scene, s.tonemapper, fb, 0)
+    else:
+        W.render_cube_map_batched(dev, s, cams, fbs)
 
 
 class ClockSampler:
@@ -105,6 +116,7 @@ class ClockSampler:
     def summary(self):
         sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
         mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        pw = [float(r[2]) for r in self.rows if len(r) > 2 and r[2].replace(".", "").isdigit()]
         reasons = set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for r in self.rows:
@@ -112,7 +124,7 @@ class ClockSampler:
                 if len(r) > 3 + k and r[3 + k].lower().startswith("active"):
                     reasons.add(n)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(self.rows)}
+                "power_w_max": max(pw) if pw else None, "reasons": sorted(reasons), "samples": len(self.rows)}
 
 
 def measured_peak():
@@ -123,61 +135,208 @@ def measured_peak():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def cpu_reference(workload, steps, warmup, sample_size):
-    """The reference CPU path on the host cores, bounded sample: same scene/camera/spp/depth, face resolution sample_size."""
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def cpu_reference(workload, steps, warmup):
+    """The reference CPU path on the host cores. Same scene / cameras / face size / spp / depth as the GPU arm; one step = the rows of ONE
+    face that server 0 of B renders under the reference's own band partition (every B-th 4-row band, api/swapchain.h:57-70)."""
     from oracle import oracle_device
-    _, desc, size, spp, depth = WORKLOADS[workload]
-    cores = os.cpu_count() or 1
-    dev = oracle_device.open_oracle(num_threads=cores)
-    s = build_workload(dev, workload, sample_size, spp, depth, "RGB8")
+    _, desc, size, spp, depth, faces = WORKLOADS[workload]
+    cores = host_cores()
+    fast = os.path.exists(oracle_device.ORACLE_FAST_LIB)
+    dev = oracle_device.open_oracle(num_threads=cores, fast=fast)
+    bands = max(1, (size * size * spp) >> 21)
+    bands = min(bands, max(1, size // 4))
+    dev.rtSetInt1(None, "serverID", 0); dev.rtSetInt1(None, "serverCount", bands)      # singleray_device.cpp:505-508
+    s = build_workload(dev, workload, size, spp, depth, "RGB8")
+    cams = make_cameras(dev, s, faces)
     rays = secs = wall = 0.0
     for i in range(warmup + steps):
-        cam = face_camera(dev, s, i)
+        cam = cams[i % len(cams)]
         t0 = time.perf_counter()
-        render_face(dev, s, cam)
+        if s.view is not None:
+            org = dev.rtGetFloat3(cam, "origin")
+            for j, p in enumerate(s.prims):
+                dev.rtUpdatePrimitive(s.scene, j, p, org, s.view[2])
+            dev.rtCommit(s.scene)
+        dev.rtRenderFrame(s.renderer, cam, s.scene, s.tonemapper, s.framebuffer, 0)
         dev.rtSwapBuffers(s.framebuffer); dev.rtMapFrameBuffer(s.framebuffer); dev.rtUnmapFrameBuffer(s.framebuffer)
         dt = time.perf_counter() - t0
         st = dev.frame_stats()
         if i >= warmup:
             rays += st.rays_closest; secs += st.render_ms * 1e-3; wall += dt
-    sample = (f"reference devices/device_singleray + embree2-API shim (NOT Intel Embree), {cores} threads, {steps} faces of the same "
-              f"scene/camera/spp/depth at {sample_size}x{sample_size} px per face instead of {size}x{size}")
+    sample = (f"reference devices/device_singleray sources, {'-O3 -ffast-math' if fast else '-O2 strict'} build + embree2-API shim (scalar BVH2; NOT Intel Embree), "
+              f"{cores} threads; {steps} steps, each = one stereo cube face of the same scene at the SAME {size}x{size} px, {spp} spp, depth {depth}, "
+              f"restricted to every {bands}-th 4-row band (serverCount={bands}: {size * size * spp // bands} paths per step)")
     return {"value": rays / secs / 1e6, "unit": "Mrays/s", "cores": cores, "kind": "reference", "sample": sample,
-            "e2e_value": rays / wall / 1e6, "ms_per_step": secs * 1e3 / steps, "rays": rays, "wall_s": wall}
+            "e2e_value": rays / wall / 1e6, "ms_per_step": secs * 1e3 / steps, "rays": rays, "wall_s": wall,
+            "s_per_stereo_cube_map_extrapolated": (wall / steps) * bands * faces}
+
+
+def kernel_rooflines(agg, nbar, peaks, n_gpus_in_process):
+    """Per-kernel algorithmic bytes / flops against the measured denominators. The dominant kernel's block becomes `roofline`."""
+    out = {}
+    hbm, l2, fp32 = peaks["hbm_gbs"], peaks.get("l2_gbs_measured"), peaks.get("fp32_tflops_measured")
+
+    def trav(name, rays, ms, launches, nodes, tris, hit_bytes):
+        if not rays or not ms:
+            return
+        rays /= n_gpus_in_process
+        bpr = 32 + hit_bytes + 80 * nodes + 48 * tris
+        fpr = 190 * nodes + 90 * tris
+        gbs = rays * bpr / (ms * 1e-3) / 1e9
+        tf = rays * fpr / (ms * 1e-3) / 1e12
+        out[name] = {"bound": "hbm", "kernel": name, "achieved": gbs, "peak": hbm, "unit": "GB/s", "frac": gbs / hbm, "traffic": None,
+                     "bytes_per_ray": bpr, "nodes_per_ray": nodes, "tris_per_ray": tris, "avg_launch_ms": ms / max(1, launches),
+                     "l2_gbs_measured": l2, "frac_l2": (gbs / l2) if l2 else None,
+                     "fp32_tflops_measured": fp32, "fp32_tflops_achieved": tf, "frac_fp32": (tf / fp32) if fp32 else None, "flops_per_ray": fpr,
+                     "what_bounds_it": "instruction issue (ncu: profiles/): the BVH is L2-resident, so the memory-side bound is L2 read bandwidth (frac_l2), "
+                                       "not HBM; `frac` is kept as the contract's algorithmic-bytes / HBM-peak figure"}
+    trav("k_trace_closest", agg["closest_rays"], agg["closest_ms"], agg["closest_launches"], nbar["closest_nodes_per_ray"], nbar["closest_tris_per_ray"], 16)
+    trav("k_trace_shadow", agg["shadow_rays"], agg["shadow_ms"], agg["shadow_launches"], nbar["shadow_nodes_per_ray"], nbar["shadow_tris_per_ray"], 4)
+    if agg["shade_ms"] and agg["vertices"]:
+        v = agg["vertices"] / n_gpus_in_process
+        spv = agg["shadow_rays"] / max(1, agg["vertices"])
+        # per path vertex: queue 4 + rayO/rayD/hit/throughput 64 in, 80 shading record, 16 texels, next ray + throughput + queue 52 out, 52 per shadow ray
+        bpv = 4 + 64 + 80 + 16 + 52 + 52 * spv
+        gbs = v * bpv / (agg["shade_ms"] * 1e-3) / 1e9
+        out["k_shade"] = {"bound": "hbm", "kernel": "k_shade", "achieved": gbs, "peak": hbm, "unit": "GB/s", "frac": gbs / hbm, "traffic": None,
+                          "bytes_per_vertex": bpv, "shadow_rays_per_vertex": spv, "avg_launch_ms": agg["shade_ms"] / max(1, agg["shade_launches"]),
+                          "what_bounds_it": "HBM stream of path state in the limit; measured: latency + divergence (ncu: profiles/)"}
+    return out
+
+
+def run_soup(args, rank, world, local_rank):
+    """BASELINE configs[4]: incoherent closest-hit rays through a synthetic triangle soup, scene replicated, rays split over the ranks."""
+    import torch
+    import torch.distributed as dist
+    from yulio_raytracer_b200 import Device, workloads as W
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = Device.cuda(cfg=f"gpu={local_rank}" + ("," + args.cfg if args.cfg else ""))
+    t0 = time.perf_counter()
+    s = W.soup(dev, args.tris, meshes=max(1, args.tris // 4_000_000))
+    build_s = time.perf_counter() - t0
+    st0 = dev.frame_stats()
+    total_rays = 1 << args.log2_rays
+    n = total_rays // world
+    rays_h = W.random_rays(total_rays, tfar=float("inf"))[rank * n:(rank + 1) * n]
+    rays_pin = torch.from_numpy(rays_h).pin_memory()
+    rays_d = rays_pin.cuda()
+    hits_d = torch.zeros((n, 8), dtype=torch.float32, device="cuda")
+    hits_pin = torch.empty((n, 8), dtype=torch.float32).pin_memory()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+    nbar = None
+    if rank == 0:
+        sdev = Device.cuda(cfg=f"gpu={local_rank},stats=1")
+        ss = W.soup(sdev, args.tris, meshes=max(1, args.tris // 4_000_000))
+        m = min(n, 1 << 22)
+        sdev.trace_rays_device(ss.scene, rays_d.data_ptr(), hits_d.data_ptr(), m, True)
+        sst = sdev.frame_stats()
+        nbar = {"nodes_per_ray": sst.node_visits / m, "tris_per_ray": sst.tri_tests / m, "num_triangles": int(sst.num_triangles), "num_nodes": int(sst.num_nodes)}
+        sdev.close()
+    for _ in range(args.warmup):
+        dev.trace_rays_device(s.scene, rays_d.data_ptr(), hits_d.data_ptr(), n, True)
+    barrier()
+    ms = 0.0
+    with ClockSampler(local_rank) as clocks:
+        for i in range(args.steps):
+            flush.fill_(i & 255); torch.cuda.synchronize()
+            ms += dev.trace_rays_device(s.scene, rays_d.data_ptr(), hits_d.data_ptr(), n, True)
+        barrier()
+    clk = clocks.summary()
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):                              # e2e: host rays -> device, trace, hits -> host
+        rays_d.copy_(rays_pin, non_blocking=True); torch.cuda.synchronize()
+        dev.trace_rays_device(s.scene, rays_d.data_ptr(), hits_d.data_ptr(), n, True)
+        hits_pin.copy_(hits_d, non_blocking=True); torch.cuda.synchronize()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    vals = torch.tensor([ms, e2e_s], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(vals, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        ms_t, e2e_t = vals[0].item(), vals[1].item()
+        value = total_rays * args.steps / (ms_t * 1e-3) / 1e6
+        peak, peak_src = measured_peak()
+        bpr = 64 + 80 * nbar["nodes_per_ray"] + 48 * nbar["tris_per_ray"]
+        gbs = n * args.steps * bpr / (ms * 1e-3) / 1e9
+        traffic = None
+        try:
+            with open(os.path.join(REPO, "profiles", "traffic.json")) as f:
+                traffic = json.load(f).get(f"c5_{args.tris}")
+        except Exception:
+            pass
+        line = {"metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms_t / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": f"C5 synthetic soup: {args.tris} triangles ({nbar['num_nodes']} BVH8 nodes, {(nbar['num_nodes'] * 80 + nbar['num_triangles'] * 48) / 1e6:.0f} MB), "
+                                       f"2^{args.log2_rays} incoherent closest-hit rays per step split over {world} rank(s), scene replicated",
+                           "l2": "a 256 MiB buffer is rewritten between timed steps (L2 flush)"},
+                "e2e": {"value": total_rays * args.steps / e2e_t / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": n * 32, "d2h_bytes_per_step": n * 32},
+                "gpu_launches": args.steps * world, "clocks": clk, "traversal": nbar, "build_s_first_commit": build_s, "bvh_build_ms": st0.build_ms,
+                "roofline": {"bound": "hbm", "kernel": "k_trace_user", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak, "traffic": traffic,
+                             "peak_source": peak_src, "bytes_per_ray": bpr, "avg_launch_ms": ms / args.steps}}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=12)
+    ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="cuda")
-    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
-    ap.add_argument("--cpu-sample", type=int, default=256, help="face resolution of the bounded CPU sample")
+    ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS) + ["c5"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cfg", default="", help="extra device cfg keys (development A/B only)")
     ap.add_argument("--size", type=int, default=0, help="override the face resolution (profiling runs only; not a bench line)")
     ap.add_argument("--spp", type=int, default=0, help="override samples per pixel (profiling runs only; not a bench line)")
+    ap.add_argument("--per-face", action="store_true", help="the reference's literal loop: 12 x (update, commit, rtRenderFrame) instead of yrtxRenderCubeMap (A/B)")
+    ap.add_argument("--tris", type=int, default=10_000_000, help="c5: triangles in the soup")
+    ap.add_argument("--log2-rays", type=int, default=24, help="c5: log2 of the rays per step")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    _, desc, size, spp, depth = WORKLOADS[args.workload]
+    if args.workload == "c5":
+        if args.impl == "reference":
+            if rank == 0:
+                print(json.dumps({"impl": "reference", "unavailable": "c5 (raw traversal sweep) has no reference-side driver; the CPU arm covers c1..c4"}))
+            return 0
+        return run_soup(args, rank, world, local_rank)
+    _, desc, size, spp, depth, faces = WORKLOADS[args.workload]
     if args.size or args.spp:
         size = args.size or size; spp = args.spp or spp
         desc += f" [OVERRIDDEN for profiling: {size}x{size}, {spp} spp - not the benchmark configuration]"
-    config = {"workload": desc, "faces_per_cube_map": 12, "partition": f"4-row bands round-robin over {world} rank(s), scene replicated",
-              "l2": "a 256 MiB buffer is rewritten between timed steps (L2 flush); wavefront state per step (>1 GB) also exceeds L2"}
+    config = {"workload": desc, "step": f"one stereo cube map = {faces} faces" if faces > 1 else "one frame",
+              "faces_per_cube_map": faces, "face_px": size, "spp": spp, "max_depth": depth,
+              "partition": f"4-row bands round-robin over {world} rank(s), scene replicated, {'12 x rtRenderFrame' if args.per_face else 'all faces in one wavefront (yrtxRenderCubeMap)'}",
+              "l2": "a 256 MiB buffer is rewritten between timed steps (L2 flush); wavefront state per step (>7 GB) also exceeds L2"}
 
     if args.impl == "reference":
         if rank != 0:
             return 0
-        r = cpu_reference(args.workload, args.steps, max(1, min(args.warmup, 1)), args.cpu_sample)
+        r = cpu_reference(args.workload, args.steps, max(1, min(args.warmup, 2)))
         line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic", "config": config,
                 "cpu_baseline": {"value": r["value"], "unit": "Mrays/s", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]},
                 "e2e": {"value": r["e2e_value"], "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-                "gpu_launches": 0}
+                "s_per_stereo_cube_map_extrapolated": r["s_per_stereo_cube_map_extrapolated"], "gpu_launches": 0}
         print(json.dumps(line))
         return 0
 
@@ -194,27 +353,48 @@ def main():
         config["partition"] = f"4-row bands round-robin over {in_process} GPUs of one process (group device), scene replicated"
     dev = Device.cuda(cfg=(f"gpus={in_process}" if in_process > 1 else f"gpu={local_rank},serverID={rank},serverCount={world}") + ("," + args.cfg if args.cfg else ""))
     s = build_workload(dev, args.workload, size, spp, depth, "RGB8")
+    cams = make_cameras(dev, s, faces)
+    fbs = [s.framebuffer] + [dev.rtNewFrameBuffer("RGB8", size, size, 1) for _ in range(len(cams) - 1)]
     stride = (3 * size + 3) // 4 * 4
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 
-    # ---- multi-GPU gather of the row bands (the only inter-GPU traffic; NCCL over NVLink) ----
+    # ---- measured roofline denominators (csrc/microbench.cu), rank 0 ----
+    peaks = {}
+    peaks["hbm_gbs"], peaks["hbm_source"] = measured_peak()
+    if rank == 0:
+        try:
+            peaks["fp32_tflops_measured"] = dev.microbench(0)
+            peaks["l2_gbs_measured"] = dev.microbench(1, 48 << 20)
+            peaks["hbm_read_gbs_measured"] = dev.microbench(1, 4 << 30)
+            peaks["issue_gwarpinst_s_measured"] = dev.microbench(2)
+        except Exception as e:                             # a group device answers through member 0; anything else is reported, not hidden
+            peaks["microbench_error"] = str(e)
+
+    # ---- multi-GPU gather of the row bands (the only inter-GPU traffic; NCCL over NVLink): one all-gather per cube map ----
     class _DevView:                      # zero-copy view of the device framebuffer for torch
         def __init__(self, ptr, nbytes):
             self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 3}
-    fb_t = gatherer = None
+    fb_t = gatherer = full_host = None
     if world > 1:
-        ptr, nbytes, _ = dev.framebuffer_device(s.framebuffer)
-        fb_t = torch.as_tensor(_DevView(ptr, nbytes), device="cuda")
+        fb_t = []
+        for fb in fbs:
+            ptr, nbytes, _ = dev.framebuffer_device(fb)
+            fb_t.append(torch.as_tensor(_DevView(ptr, nbytes), device="cuda"))
         from yulio_raytracer_b200 import bands
-        gatherer = bands.BandGather(size, stride, rank, world, "cuda")
+        gatherer = bands.CubeBandGather(len(fbs), size, stride, rank, world, "cuda")
+        if rank == 0:
+            full_host = torch.empty(len(fbs) * size * stride, dtype=torch.uint8).pin_memory()
 
-    def gather_bands():
+    def gather_bands(to_host=False):
         if world == 1:
             return 0.0
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        gatherer.gather(fb_t)
-        e1.record(); e1.synchronize()
+        full = gatherer.gather(fb_t)
+        e1.record()
+        if to_host and rank == 0:
+            full_host.copy_(full, non_blocking=True)
+        torch.cuda.synchronize()
         return e0.elapsed_time(e1)
 
     def barrier():
@@ -223,68 +403,91 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- traversal statistics of the workload (stats=1 replay of one face on a second device handle, untimed) ----
+    # ---- traversal statistics of the workload (stats=1 replay of one cube map on a second device handle, untimed) ----
     nbar = None
     if rank == 0:
         sdev = Device.cuda(cfg=f"gpu={local_rank},stats=1,serverID={rank},serverCount={world * in_process}")
         ss = build_workload(sdev, args.workload, size, spp, depth, "RGB8")
         sdev.set_readback(False)
-        render_face(sdev, ss, face_camera(sdev, ss, 0))
+        scams = make_cameras(sdev, ss, faces)
+        sfbs = [ss.framebuffer] + [sdev.rtNewFrameBuffer("RGB8", size, size, 1) for _ in range(len(scams) - 1)]
+        render_step(sdev, ss, scams, sfbs)
         st = sdev.frame_stats()
         nrays = st.rays_closest + st.rays_shadow
+        cn, ct = st.node_visits - st.node_visits_shadow, st.tri_tests - st.tri_tests_shadow
         nbar = {"nodes_per_ray": st.node_visits / max(1, nrays), "tris_per_ray": st.tri_tests / max(1, nrays),
-                "closest_fraction": st.rays_closest / max(1, nrays), "num_triangles": int(st.num_triangles), "num_nodes": int(st.num_nodes)}
+                "closest_nodes_per_ray": cn / max(1, st.rays_closest), "closest_tris_per_ray": ct / max(1, st.rays_closest),
+                "shadow_nodes_per_ray": st.node_visits_shadow / max(1, st.rays_shadow), "shadow_tris_per_ray": st.tri_tests_shadow / max(1, st.rays_shadow),
+                "closest_fraction": st.rays_closest / max(1, nrays), "num_triangles": int(st.num_triangles), "num_nodes": int(st.num_nodes),
+                "bvh_mb": (st.num_nodes * 80 + st.num_triangles * 48) / 1e6, "shading_records_mb": st.num_triangles * 80 / 1e6}
         sdev.close()
 
-    # ---- (1) device-timed: frame stays in HBM ----
+    # ---- (1) device-timed: frames stay in HBM ----
     dev.set_readback(False)
-    cams = [face_camera(dev, s, f) for f in range(12)]
     for i in range(args.warmup):
-        render_face(dev, s, cams[i % 12]); gather_bands()
-    agg = {"rays": 0, "ms": 0.0, "closest_ms": 0.0, "shadow_ms": 0.0, "shade_ms": 0.0, "rf_ms": 0.0, "launches": 0, "closest_rays": 0,
-           "shadow_rays": 0, "closest_launches": 0, "shadow_launches": 0, "gather_ms": 0.0, "sort_ms": 0.0}
+        render_step(dev, s, cams, fbs, args.per_face); gather_bands()
+    keys = ("rays", "ms", "closest_ms", "shadow_ms", "shade_ms", "resolve_ms", "rf_ms", "launches", "closest_rays", "shadow_rays", "closest_launches",
+            "shadow_launches", "shade_launches", "gather_ms", "sort_ms", "vertices", "miss_ms")
+    agg = {k: 0.0 for k in keys}
     barrier()
     with ClockSampler(local_rank) as clocks:
         t_wall0 = time.perf_counter()
         for i in range(args.steps):
             flush.fill_(i & 255); torch.cuda.synchronize()
-            render_face(dev, s, cams[i % 12])
-            st = dev.frame_stats()
+            if args.per_face and s.view is not None:
+                rows = []
+                for cam, fb in zip(cams, fbs):
+                    render_step(dev, s, [cam], [fb], True); rows.append(dev.frame_stats())
+            else:
+                render_step(dev, s, cams, fbs); rows = [dev.frame_stats()]
             g = gather_bands()
-            agg["rays"] += st.rays_closest + st.rays_shadow; agg["ms"] += st.render_ms + g; agg["gather_ms"] += g
-            agg["closest_ms"] += st.closest_ms; agg["shadow_ms"] += st.shadow_ms; agg["shade_ms"] += st.shade_ms; agg["rf_ms"] += st.raygen_film_ms; agg["sort_ms"] += st.sort_ms
-            agg["launches"] += st.kernel_launches; agg["closest_rays"] += st.rays_closest; agg["shadow_rays"] += st.rays_shadow
-            agg["closest_launches"] += st.closest_launches; agg["shadow_launches"] += st.shadow_launches
+            agg["ms"] += g; agg["gather_ms"] += g
+            for st in rows:
+                agg["rays"] += st.rays_closest + st.rays_shadow; agg["ms"] += st.render_ms
+                agg["closest_ms"] += st.closest_ms; agg["shadow_ms"] += st.shadow_ms; agg["shade_ms"] += st.shade_ms; agg["resolve_ms"] += st.resolve_ms
+                agg["rf_ms"] += st.raygen_film_ms; agg["sort_ms"] += st.sort_ms; agg["miss_ms"] += st.miss_ms
+                agg["launches"] += st.kernel_launches; agg["closest_rays"] += st.rays_closest; agg["shadow_rays"] += st.rays_shadow
+                agg["closest_launches"] += st.closest_launches; agg["shadow_launches"] += st.shadow_launches; agg["shade_launches"] += st.shade_launches
+                agg["vertices"] += st.path_vertices
         barrier()
         wall_dev = time.perf_counter() - t_wall0
     clk = clocks.summary()
 
-    # ---- (2) end to end through the reference-facing loop, frame read back to the host every step ----
-    dev.set_readback(True)
+    # ---- (2) end to end through the reference-facing loop, every frame read back to the host every step ----
+    dev.set_readback(world == 1)           # N > 1: the bands are gathered on the GPU first, rank 0 copies the assembled frames to the host
     for i in range(2):
-        render_face(dev, s, cams[i % 12]); dev.rtSwapBuffers(s.framebuffer); dev.rtMapFrameBuffer(s.framebuffer); dev.rtUnmapFrameBuffer(s.framebuffer)
+        render_step(dev, s, cams, fbs, args.per_face); gather_bands(to_host=True)
     barrier()
     e2e_rays = 0; h2d = d2h = 0
     t0 = time.perf_counter()
     for i in range(args.steps):
-        cam = face_camera(dev, s, i)                       # camera creation + commit is part of the caller's per-face work
-        render_face(dev, s, cam)
-        dev.rtSwapBuffers(s.framebuffer)
-        p = dev.rtMapFrameBuffer(s.framebuffer); dev.rtUnmapFrameBuffer(s.framebuffer)
-        gather_bands()
+        c2 = make_cameras(dev, s, faces)                   # camera creation + commit is part of the caller's per-viewpoint work
+        render_step(dev, s, c2, fbs, args.per_face)
         st = dev.frame_stats()
-        e2e_rays += st.rays_closest + st.rays_shadow; h2d += st.h2d_bytes + 4096; d2h += st.d2h_bytes
+        for fb in fbs:
+            dev.rtSwapBuffers(fb); dev.rtMapFrameBuffer(fb); dev.rtUnmapFrameBuffer(fb)
+        gather_bands(to_host=True)
+        if args.per_face and s.view is not None:
+            e2e_rays += agg["rays"] / args.steps
+        else:
+            e2e_rays += st.rays_closest + st.rays_shadow
+        h2d += st.h2d_bytes + 4096
+        d2h += (len(fbs) * size * stride) if (world > 1 and rank == 0) else (st.d2h_bytes if world == 1 else 0)
+        if world == 1 and args.per_face:
+            d2h += (len(fbs) - 1) * size * stride
+        for c in c2:
+            dev.rtDecRef(c)
     barrier()
     e2e_s = time.perf_counter() - t0
 
     # ---- reduce over ranks: max time, sum rays ----
-    vals = torch.tensor([agg["ms"], e2e_s, float(agg["rays"]), float(e2e_rays), float(agg["launches"]), agg["closest_ms"], agg["shadow_ms"]],
+    vals = torch.tensor([agg["ms"], e2e_s, float(agg["rays"]), float(e2e_rays), float(agg["launches"]), float(d2h), float(h2d)],
                         dtype=torch.float64, device="cuda")
     if world > 1:
         mx = vals.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
         sm = vals.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
         ms_total, e2e_total = mx[0].item(), mx[1].item()
-        rays_total, e2e_rays_total, launches_total = sm[2].item(), sm[3].item(), sm[4].item()
+        rays_total, e2e_rays_total, launches_total, d2h, h2d = sm[2].item(), sm[3].item(), sm[4].item(), sm[5].item(), sm[6].item()
     else:
         ms_total, e2e_total, rays_total, e2e_rays_total, launches_total = agg["ms"], e2e_s, agg["rays"], e2e_rays, agg["launches"]
     if rank != 0:
@@ -295,40 +498,35 @@ def main():
     value = rays_total / (ms_total * 1e-3) / 1e6
     e2e_value = e2e_rays_total / e2e_total / 1e6
     ms_per_step = ms_total / args.steps
-    peak, peak_src = measured_peak()
-    # dominant kernel: closest-hit traversal. Algorithmic bytes/ray = 32 (ray in) + 16 (hit out: t,u,v,triangle index — SURVEY §8d planned
-    # 32, the record shrank when the shading data moved into per-triangle records) + 80*Nnode + 48*Ntri
-    bpr = 48 + 80 * nbar["nodes_per_ray"] + 48 * nbar["tris_per_ray"]
-    per_gpu_closest = agg["closest_rays"] / in_process      # the roofline is one GPU's (group device: the counters are sums over its GPUs)
-    achieved = per_gpu_closest * bpr / (agg["closest_ms"] * 1e-3) / 1e9 if agg["closest_ms"] > 0 else None
-    roofline = {"bound": "hbm", "kernel": "k_trace_closest", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": (achieved / peak) if achieved else None, "traffic": None, "peak_source": peak_src,
-                "bytes_per_ray": bpr, "avg_launch_ms": agg["closest_ms"] / max(1, agg["closest_launches"]),
-                "note": "BVH of this workload is L2-resident; node/triangle bytes are served by L1/L2, not HBM (DESIGN.md)"}
-    # secondary roofline: FP32 issue. flops/ray = 190*Nnode + 90*Ntri against 148 SMs x 128 lanes x 2 flop x SM clock
-    flops_per_ray = 190 * nbar["nodes_per_ray"] + 90 * nbar["tris_per_ray"]
-    fp32_peak = 148 * 128 * 2 * (clk["sm_mhz"] or 1965.0) * 1e6 / 1e12
-    fp32_ach = per_gpu_closest * flops_per_ray / (agg["closest_ms"] * 1e-3) / 1e12 if agg["closest_ms"] > 0 else None
-    roofline["fp32"] = {"achieved": fp32_ach, "peak": fp32_peak, "unit": "TFLOP/s", "frac": (fp32_ach / fp32_peak) if fp32_ach else None,
-                        "flops_per_ray": flops_per_ray, "peak_source": "nominal: 148 SMs x 128 FP32 lanes x 2 x sampled SM clock"}
+    kr = kernel_rooflines(agg, nbar, peaks, in_process)
+    stage = {"k_trace_closest": agg["closest_ms"], "k_trace_shadow": agg["shadow_ms"], "k_shade": agg["shade_ms"]}
+    dominant = max(stage, key=stage.get)
+    roofline = dict(kr.get(dominant, {"bound": "hbm", "kernel": dominant, "achieved": None, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": None, "traffic": None}))
+    roofline["peak_source"] = peaks["hbm_source"]
+    roofline["share_of_step"] = stage[dominant] / max(1e-9, agg["ms"])
+    roofline["measured_peaks"] = {k: v for k, v in peaks.items() if k.endswith("_measured") or k == "microbench_error"}
+    roofline["other_kernels"] = {k: {kk: v[kk] for kk in ("achieved", "frac", "frac_l2", "frac_fp32", "avg_launch_ms") if kk in v} for k, v in kr.items() if k != dominant}
     try:
         with open(os.path.join(REPO, "profiles", "traffic.json")) as f:
-            roofline["traffic"] = json.load(f).get(args.workload)
+            tj = json.load(f)
+        roofline["traffic"] = (tj.get(args.workload) or {}).get(dominant)
+        roofline["ncu"] = (tj.get(args.workload) or {}).get(dominant + "_ncu")
     except Exception:
         pass
     line = {"metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": world * in_process, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "config": config,
-            "s_per_stereo_cube_map": ms_per_step * 12e-3, "e2e_s_per_stereo_cube_map": e2e_total / args.steps * 12,
-            "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": h2d // args.steps, "d2h_bytes_per_step": d2h // args.steps},
+            "s_per_stereo_cube_map": ms_per_step * 1e-3, "e2e_s_per_stereo_cube_map": e2e_total / args.steps,
+            "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": int(h2d // args.steps), "d2h_bytes_per_step": int(d2h // args.steps)},
             "gpu_launches": int(launches_total), "clocks": clk, "roofline": roofline,
             "stage_ms_per_step": {"closest": agg["closest_ms"] / args.steps, "shadow": agg["shadow_ms"] / args.steps,
-                                  "shade": agg["shade_ms"] / args.steps, "raygen_film": agg["rf_ms"] / args.steps, "sort": agg["sort_ms"] / args.steps,
-                                  "gather": agg["gather_ms"] / args.steps},
+                                  "shade": agg["shade_ms"] / args.steps, "resolve": agg["resolve_ms"] / args.steps, "miss": agg["miss_ms"] / args.steps,
+                                  "raygen_film": agg["rf_ms"] / args.steps, "sort": agg["sort_ms"] / args.steps, "gather": agg["gather_ms"] / args.steps},
             "traversal": nbar, "rays_per_step": rays_total / args.steps, "wall_s_timed_region": wall_dev}
     if not args.no_cpu_baseline and world == 1:
-        r = cpu_reference(args.workload, 4, 1, args.cpu_sample)
-        line["cpu_baseline"] = {"value": r["value"], "unit": "Mrays/s", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]}
+        r = cpu_reference(args.workload, 3, 1)
+        line["cpu_baseline"] = {"value": r["value"], "unit": "Mrays/s", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"],
+                                "s_per_stereo_cube_map_extrapolated": r["s_per_stereo_cube_map_extrapolated"]}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -151,6 +151,13 @@ typedef struct yrtx_frame_stats {
     uint64_t d2h_bytes;        /* device->host bytes moved by the last yrtRenderFrame (the frame) */
     double   sort_ms;          /* CUDA-event time of the ray-sort launches (key generation + radix sort) */
     uint64_t bvh_builds;       /* BVH builds since the scene handle was created (F8: commits that did not change geometry reuse it) */
+    double   resolve_ms;       /* CUDA-event time of the resolve + counter-reset launches (shade_ms is the shading kernel alone) */
+    uint64_t node_visits_shadow; /* stats=1: the any-hit kernel's share of node_visits */
+    uint64_t tri_tests_shadow;   /* stats=1: the any-hit kernel's share of tri_tests */
+    uint64_t path_vertices;    /* queue entries processed by the shading kernel (hits + misses) */
+    uint64_t shade_launches;   /* number of shading-kernel launches */
+    double   miss_ms;          /* CUDA-event time of the miss / environment kernel launches */
+    uint64_t errors;           /* device error flags raised during the call (bit 0: traversal stack overflow); non-zero fails the call */
 } yrtx_frame_stats;
 YRT_API yrt_status yrtxGetFrameStats(yrt_device*, yrtx_frame_stats* out);
 

@@ -11,6 +11,11 @@ Needs /root/reference (present in the build container only). The GPU box uses th
 Flags: -O2 -msse4.2 -fno-fast-math -ffp-contract=off for the reference sources (strict IEEE so the
 oracle is reproducible; the shipped build uses fast-math); the shim adds -mfma
 because its arithmetic contract YRT-PLUECKER-1 uses explicit fused multiply-adds.
+
+A second library, oracle/_ref/liboracle_singleray_fast.so, is the BASELINE build bench.py times (cpu_baseline, --impl reference):
+the reference's release flags -O3 -ffast-math (common/cmake/gcc.cmake:27) plus -msse4.2, its own approximate rcp / rsqrt (overlay
+without pin P3), -fno-finite-math-only so that the infinite tfar / tMaxShadowRay the path relies on stay defined. It is never used
+for parity.
 """
 import os
 import subprocess
@@ -37,22 +42,32 @@ def main():
     if not os.path.isdir(REF):
         print("build_ref: no reference tree at", REF, "- keeping prebuilt oracle/_ref", file=sys.stderr)
         return 0 if os.path.exists(os.path.join(OUT, "liboracle_singleray.so")) else 1
-    subprocess.check_call([sys.executable, os.path.join(HERE, "make_overlay.py")])
+    build(False)
+    build(True)
+    return 0
+
+
+def build(fast):
+    global OVL, OBJ
+    OVL = os.path.join(REPO, "build", "oracle_overlay" + ("_fast" if fast else ""))
+    OBJ = os.path.join(REPO, "build", "oracle_obj" + ("_fast" if fast else ""))
+    subprocess.check_call([sys.executable, os.path.join(HERE, "make_overlay.py")] + (["--fast"] if fast else []))
     os.makedirs(OBJ, exist_ok=True)
     os.makedirs(OUT, exist_ok=True)
     inc = ["-I" + OVL, "-I" + os.path.join(OVL, "common"), "-I" + os.path.join(OVL, "devices"),
            "-I" + os.path.join(OVL, "devices", "device_singleray"), "-I" + HERE,
            "-I" + os.path.join(REF, "3rd party", "Embree v2.15.0 x64", "include"),
            "-I" + os.path.join(REF, "3rd party", "glm-0.9.8.4")]
-    base = ["g++", "-std=c++14", "-O2", "-msse4.2", "-fno-fast-math", "-ffp-contract=off", "-fPIC",
-            "-fpermissive", "-w", "-DNDEBUG", "-pthread"] + inc
+    opt = ["-O3", "-ffast-math", "-fno-finite-math-only"] if fast else ["-O2", "-fno-fast-math", "-ffp-contract=off"]
+    base = ["g++", "-std=c++14", "-msse4.2"] + opt + ["-fPIC", "-fpermissive", "-w", "-DNDEBUG", "-pthread"] + inc
+    strict = ["g++", "-std=c++14", "-msse4.2", "-O3" if fast else "-O2", "-fno-fast-math", "-ffp-contract=off", "-fPIC", "-fpermissive", "-w", "-DNDEBUG", "-pthread"] + inc
     jobs = []
     for s in SINGLERAY:
         jobs.append((os.path.join(OVL, "devices", "device_singleray", s), base))
     for s in COMMON:
         jobs.append((os.path.join(OVL, "common", s), base))
-    jobs.append((os.path.join(HERE, "embree2_shim.cpp"), base + ["-mfma"]))
-    jobs.append((os.path.join(HERE, "oracle_capi.cpp"), base))
+    jobs.append((os.path.join(HERE, "embree2_shim.cpp"), strict + ["-mfma"]))     # the shim keeps its arithmetic contract in both builds
+    jobs.append((os.path.join(HERE, "oracle_capi.cpp"), strict))
     jobs.append((os.path.join(HERE, "oracle_stubs.cpp"), base))
 
     def cc(job):
@@ -66,10 +81,9 @@ def main():
 
     with ThreadPoolExecutor(max_workers=os.cpu_count() or 4) as ex:
         objs = list(ex.map(cc, jobs))
-    so = os.path.join(OUT, "liboracle_singleray.so")
+    so = os.path.join(OUT, "liboracle_singleray_fast.so" if fast else "liboracle_singleray.so")
     subprocess.check_call(["g++", "-shared", "-o", so] + objs + ["-ldl", "-pthread", "-Wl,--no-undefined"])
     print("built", so)
-    return 0
 
 
 if __name__ == "__main__":

@@ -53,6 +53,12 @@ def patch(rel, old, new, count=1):
 
 
 def main():
+    global OUT
+    # --fast: the overlay of the BASELINE build (build_ref.py: -O3 -ffast-math, the reference's release flags, common/cmake/gcc.cmake:27):
+    # portability patches and pins P1, P2, P4 only — the reference's own approximate rcp / rsqrt stay (no P3).
+    fast = "--fast" in sys.argv
+    if fast:
+        OUT = OUT + "_fast"
     if not os.path.isdir(REF):
         raise SystemExit(f"reference tree not found at {REF}")
     if os.path.isdir(OUT):
@@ -97,24 +103,25 @@ def main():
           "__forceinline uint64 __yrt_unused_rdpmc(int i) {\n  uint32 high,low;")
 
     # ---- P3 exact reciprocal / reciprocal square root ------------------------
-    patch("common/math/math.h",
-          "return _mm_cvtss_f32(_mm_sub_ps(_mm_add_ps(r, r), _mm_mul_ps(_mm_mul_ps(r, r), vx)));",
-          "(void)r; return 1.0f / x; /* PIN P3 */")
-    patch("common/math/math.h",
-          "return _mm_cvtss_f32(c);",
-          "(void)c; return 1.0f / sqrtf(x); /* PIN P3 */")
-    patch("common/math/vector3f_sse.h",
-          "return _mm_sub_ps(_mm_add_ps(r, r), _mm_mul_ps(_mm_mul_ps(r, r), a));",
-          "(void)r; return _mm_div_ps(_mm_set1_ps(1.0f), a.m128); /* PIN P3 */")
-    patch("common/math/vector3f_sse.h",
-          "return _mm_add_ps(_mm_mul_ps(_mm_set1_ps(1.5f),r), _mm_mul_ps(_mm_mul_ps(_mm_mul_ps(a, _mm_set1_ps(-0.5f)), r), _mm_mul_ps(r, r)));",
-          "(void)r; return _mm_div_ps(_mm_set1_ps(1.0f), _mm_sqrt_ps(a.m128)); /* PIN P3 */")
-    patch("common/math/color_sse.h",
-          "return _mm_sub_ps(_mm_add_ps(r, r), _mm_mul_ps(_mm_mul_ps(r, r), a));",
-          "(void)r; return _mm_div_ps(_mm_set1_ps(1.0f), a.m128); /* PIN P3 */")
-    patch("common/math/color_sse.h",
-          "return _mm_add_ps(_mm_mul_ps(_mm_set1_ps(1.5f),r), _mm_mul_ps(_mm_mul_ps(_mm_mul_ps(a, _mm_set1_ps(-0.5f)), r), _mm_mul_ps(r, r)));",
-          "(void)r; return _mm_div_ps(_mm_set1_ps(1.0f), _mm_sqrt_ps(a.m128)); /* PIN P3 */")
+    if not fast:
+      patch("common/math/math.h",
+            "return _mm_cvtss_f32(_mm_sub_ps(_mm_add_ps(r, r), _mm_mul_ps(_mm_mul_ps(r, r), vx)));",
+            "(void)r; return 1.0f / x; /* PIN P3 */")
+      patch("common/math/math.h",
+            "return _mm_cvtss_f32(c);",
+            "(void)c; return 1.0f / sqrtf(x); /* PIN P3 */")
+      patch("common/math/vector3f_sse.h",
+            "return _mm_sub_ps(_mm_add_ps(r, r), _mm_mul_ps(_mm_mul_ps(r, r), a));",
+            "(void)r; return _mm_div_ps(_mm_set1_ps(1.0f), a.m128); /* PIN P3 */")
+      patch("common/math/vector3f_sse.h",
+            "return _mm_add_ps(_mm_mul_ps(_mm_set1_ps(1.5f),r), _mm_mul_ps(_mm_mul_ps(_mm_mul_ps(a, _mm_set1_ps(-0.5f)), r), _mm_mul_ps(r, r)));",
+            "(void)r; return _mm_div_ps(_mm_set1_ps(1.0f), _mm_sqrt_ps(a.m128)); /* PIN P3 */")
+      patch("common/math/color_sse.h",
+            "return _mm_sub_ps(_mm_add_ps(r, r), _mm_mul_ps(_mm_mul_ps(r, r), a));",
+            "(void)r; return _mm_div_ps(_mm_set1_ps(1.0f), a.m128); /* PIN P3 */")
+      patch("common/math/color_sse.h",
+            "return _mm_add_ps(_mm_mul_ps(_mm_set1_ps(1.5f),r), _mm_mul_ps(_mm_mul_ps(_mm_mul_ps(a, _mm_set1_ps(-0.5f)), r), _mm_mul_ps(r, r)));",
+            "(void)r; return _mm_div_ps(_mm_set1_ps(1.0f), _mm_sqrt_ps(a.m128)); /* PIN P3 */")
 
     # ---- P1 + P2 shadow-ray jitter --------------------------------------------
     patch("devices/device_singleray/integrators/pathtraceintegrator.cpp",

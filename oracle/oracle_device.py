@@ -21,8 +21,12 @@ def available() -> bool:
     return os.path.exists(ORACLE_LIB)
 
 
-def open_oracle(num_threads: int = 0, cfg: str = "") -> Device:
-    return Device(ORACLE_LIB, num_threads=num_threads, cfg=cfg)
+ORACLE_FAST_LIB = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref", "liboracle_singleray_fast.so")
+
+
+def open_oracle(num_threads: int = 0, cfg: str = "", fast: bool = False) -> Device:
+    """fast=True: the -O3 -ffast-math build of the same sources (oracle/build_ref.py), for bench.py's CPU baseline only — never parity."""
+    return Device(ORACLE_FAST_LIB if fast else ORACLE_LIB, num_threads=num_threads, cfg=cfg)
 
 
 class RayLog:

@@ -103,6 +103,33 @@ def test_band_gather_world2_gloo(tmp_path):
     assert (full == full[:, :1]).all()
 
 
+def _cube_gather_worker(rank, world, port, faces, height, stride, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    g = bands.CubeBandGather(faces, height, stride, rank, world, "cpu")
+    locals_ = []
+    for f in range(faces):                                     # row y of face f -> value (7 f + y) % 251
+        local = torch.zeros(height * stride, dtype=torch.uint8)
+        for b, y in enumerate(bands.active_rows(height, rank, world)):
+            local.view(height, stride)[b] = (7 * f + y) % 251
+        locals_.append(local)
+    full = g.gather(locals_)
+    if rank == 0:
+        torch.save(full, out)
+    dist.destroy_process_group()
+
+
+def test_cube_band_gather_world2_gloo(tmp_path):
+    """One all-gather per stereo cube map (bench.py --gpus N under torchrun): every face re-interleaved on rank 0."""
+    faces, height, stride, world = 3, 38, 20, 2
+    out = str(tmp_path / "cube.pt")
+    mp.spawn(_cube_gather_worker, args=(world, 29519, faces, height, stride, out), nprocs=world, join=True)
+    full = torch.load(out).view(faces, height, stride)
+    for f in range(faces):
+        assert torch.equal(full[f, :, 0], torch.tensor([(7 * f + y) % 251 for y in range(height)], dtype=torch.uint8))
+    assert (full == full[:, :, :1]).all()
+
+
 def test_plugin_exports_reference_factory_symbol():
     """libdevice_cuda.so is what Device::rtCreateDevice dlopens; it must export `create` (devices/device/device.cpp:24-35)."""
     plugin = os.path.join(os.path.dirname(CUDA_LIB), "libdevice_cuda.so")

@@ -56,3 +56,38 @@ class BandGather:
                 return None
         self.full.view(self.height + 1, self.stride).index_copy_(0, self.index, self.block.view(-1, self.stride))
         return self.full[: self.height * self.stride]
+
+
+class CubeBandGather:
+    """The same exchange for all faces of a stereo cube map at once: ONE all-gather per cube map, then one index-copy on rank 0
+    re-interleaves every face. `faces` frame buffers of `height` rows each; returns faces * height * stride bytes, face-major."""
+
+    def __init__(self, faces: int, height: int, stride_bytes: int, rank: int, world: int, device):
+        self.faces, self.height, self.stride, self.rank, self.world, self.device = faces, height, stride_bytes, rank, world, device
+        rows = [active_rows(height, r, world) for r in range(world)]
+        self.max_rows = max(len(r) for r in rows)
+        self.send = torch.empty(faces * self.max_rows * stride_bytes, dtype=torch.uint8, device=device)
+        self.block = torch.empty(world * faces * self.max_rows * stride_bytes, dtype=torch.uint8, device=device)
+        self.full: Optional[torch.Tensor] = None
+        if rank == 0:
+            self.full = torch.zeros((faces * height + 1) * stride_bytes, dtype=torch.uint8, device=device)
+            idx = []
+            for r in rows:
+                for f in range(faces):
+                    idx += [f * height + y for y in r] + [faces * height] * (self.max_rows - len(r))
+            self.index = torch.tensor(idx, dtype=torch.long, device=device)
+
+    def gather(self, locals_: List[torch.Tensor]) -> Optional[torch.Tensor]:
+        """`locals_`: this rank's `faces` framebuffers as byte tensors (compacted rows first). Returns the cube map's frames on rank 0."""
+        n = self.max_rows * self.stride
+        sv = self.send.view(self.faces, n)
+        for f, l in enumerate(locals_):
+            sv[f].copy_(l[:n])
+        if self.world == 1:
+            self.block.copy_(self.send)
+        else:
+            dist.all_gather_into_tensor(self.block, self.send)
+            if self.rank != 0:
+                return None
+        self.full.view(self.faces * self.height + 1, self.stride).index_copy_(0, self.index, self.block.view(-1, self.stride))
+        return self.full[: self.faces * self.height * self.stride]

@@ -149,7 +149,7 @@ YRT_D uint32_t node_test(const uint4 n0, const uint4 n1, const uint4 n2, const u
     return hitmask;
 }
 
-struct TraceCounters { uint32_t nodes, tris; };
+struct TraceCounters { uint32_t nodes, tris; uint32_t overflow; };   // overflow: a traversal stack ran out of its YRT_STACK_SIZE entries
 
 // ---- cache policy of the traversal kernels ----------------------------------------------------------------------------------
 // A bounce moves ~2 GB of ray / hit / queue records through the 126 MB L2 exactly once, while every ray re-reads the same few tens of
@@ -204,7 +204,7 @@ YRT_D bool trace_ray(const uint4* __restrict__ nodes, const float4* __restrict__
             const uint32_t slot = (bit - 24u) ^ r.octinv;
             const uint32_t nodeIdx = G.x + __popc((G.y & 0xffu) & ~(0xffffffffu << slot));
             if (G.y & 0xff000000u) {
-                if (sp < YRT_STACK_SIZE) stack[sp++] = G;
+                if (sp < YRT_STACK_SIZE) stack[sp++] = G; else cnt->overflow = 1u;     // reported by the caller: never a silent drop
             }
             const uint4* np = nodes + 5ull * nodeIdx;
             const uint4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
@@ -356,7 +356,7 @@ YRT_D void trace_stream(const uint4* __restrict__ nodes, const float4* __restric
                 if (T.y) {                                       // postpone the pending triangles
                     if (sp < YRT_SM_STACK) smStack[sp * YRT_TRACE_THREADS + threadIdx.x] = T;
                     else if (sp < YRT_STACK_SIZE) lstack[sp - YRT_SM_STACK] = T;
-                    if (sp < YRT_STACK_SIZE) sp++;
+                    if (sp < YRT_STACK_SIZE) sp++; else cnt.overflow = 1u;
                     T.y = 0u;
                 }
                 const uint32_t bit = 31u - __clz(G.y);
@@ -366,7 +366,7 @@ YRT_D void trace_stream(const uint4* __restrict__ nodes, const float4* __restric
                 if (G.y & 0xff000000u) {
                     if (sp < YRT_SM_STACK) smStack[sp * YRT_TRACE_THREADS + threadIdx.x] = G;
                     else if (sp < YRT_STACK_SIZE) lstack[sp - YRT_SM_STACK] = G;
-                    if (sp < YRT_STACK_SIZE) sp++;
+                    if (sp < YRT_STACK_SIZE) sp++; else cnt.overflow = 1u;
                 }
                 const uint4* np = nodes + 5ull * nodeIdx;
                 const uint4 n0 = bvh_ld(np, pol), n1 = bvh_ld(np + 1, pol), n2 = bvh_ld(np + 2, pol), n3 = bvh_ld(np + 3, pol), n4 = bvh_ld(np + 4, pol);

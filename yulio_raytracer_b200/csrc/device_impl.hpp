@@ -118,6 +118,7 @@ struct FrameTimers {                           // CUDA-event pairs collected dur
 
 namespace yrt {
 // the stereo cube-map strip being assembled on the device (image_codecs.cu; devices/renderer/renderer.cpp:665-725)
+double microbench(yrt_device* dev, int kind, size_t bytes);   // microbench.cu
 struct CubeStrip { unsigned char* dev = nullptr; size_t w = 0, h = 0; uchar4* wm = nullptr; int wmW = 0, wmH = 0; int facesAdded = 0; };
 }
 struct yrt_device {

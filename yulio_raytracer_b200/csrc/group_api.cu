@@ -301,6 +301,8 @@ yrt_status yrtxGetFrameStats(yrt_device* dev, yrtx_frame_stats* out) {
         a.render_ms = std::max(a.render_ms, s.render_ms); a.build_ms = std::max(a.build_ms, s.build_ms); a.host_ms = std::max(a.host_ms, s.host_ms);
         a.trace_ms = std::max(a.trace_ms, s.trace_ms); a.closest_ms = std::max(a.closest_ms, s.closest_ms); a.shadow_ms = std::max(a.shadow_ms, s.shadow_ms);
         a.shade_ms = std::max(a.shade_ms, s.shade_ms); a.raygen_film_ms = std::max(a.raygen_film_ms, s.raygen_film_ms); a.sort_ms = std::max(a.sort_ms, s.sort_ms);
+        a.resolve_ms = std::max(a.resolve_ms, s.resolve_ms); a.miss_ms = std::max(a.miss_ms, s.miss_ms);
+        a.node_visits_shadow += s.node_visits_shadow; a.tri_tests_shadow += s.tri_tests_shadow; a.path_vertices += s.path_vertices; a.shade_launches += s.shade_launches; a.errors |= s.errors;
         a.rays_closest += s.rays_closest; a.rays_shadow += s.rays_shadow; a.kernel_launches += s.kernel_launches; a.node_visits += s.node_visits;
         a.tri_tests += s.tri_tests; a.closest_launches += s.closest_launches; a.shadow_launches += s.shadow_launches; a.h2d_bytes += s.h2d_bytes; a.d2h_bytes += s.d2h_bytes;
     }

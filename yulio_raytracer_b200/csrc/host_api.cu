@@ -747,8 +747,7 @@ yrt_status yrtxFrameBufferDevice(yrt_device* dev, yrt_handle fb, void** devPtr, 
             if (devPtr) *devPtr = f->devPacked; if (bytes) *bytes = f->bytes(); if (strideBytes) *strideBytes = f->strideBytes)
 }
 yrt_status yrtxSetReadback(yrt_device* dev, int readbackEachFrame) { GUARD_S(dev->readback = readbackEachFrame != 0) }
-double microbench(yrt_device* dev, int kind, size_t bytes);   // microbench.cu
-yrt_status yrtxMicrobench(yrt_device* dev, int kind, size_t bytes, double* result) { GUARD_S(const double v = microbench(dev, kind, bytes); if (result) *result = v) }
+yrt_status yrtxMicrobench(yrt_device* dev, int kind, size_t bytes, double* result) { GUARD_S(const double v = yrt::microbench(dev, kind, bytes); if (result) *result = v) }
 yrt_status yrtxRenderCubeMap(yrt_device* dev, yrt_handle renderer, const yrt_handle* cameras, size_t numFaces, yrt_handle scene, yrt_handle tonemapper,
                              const yrt_handle* frameBuffers, int accumulate) {
     GUARD_S(if (!cameras || !frameBuffers || numFaces < 1 || numFaces > YRT_MAX_FACES) throw std::runtime_error("device_cuda: yrtxRenderCubeMap takes 1..12 cameras and frame buffers");

@@ -486,7 +486,7 @@ void FrameTimers::begin(int kind, cudaStream_t s) { Span sp; sp.kind = kind; sp.
 void FrameTimers::end(cudaStream_t s) { Span& sp = spans.back(); sp.b = get(); YRT_CK(cudaEventRecord(sp.b, s)); }
 void FrameTimers::release() { for (auto e : pool) cudaEventDestroy(e); pool.clear(); used = 0; spans.clear(); }
 
-enum { TK_RAYGEN_FILM = 0, TK_CLOSEST = 1, TK_SHADE = 2, TK_SHADOW = 3, TK_SORT = 4 };
+enum { TK_RAYGEN_FILM = 0, TK_CLOSEST = 1, TK_SHADE = 2, TK_SHADOW = 3, TK_SORT = 4, TK_RESOLVE = 5, TK_MISS = 6 };
 
 // ------------------------------------------------------------------------------------------------
 // per-frame setup shared by render_frame / primary_rays / sample_table
@@ -657,7 +657,7 @@ void render_frames(yrt_device* dev, RendererHandle* rh, size_t numFaces, CameraH
     LaunchCfg lcTrace{dev->numSMs * dev->traceCtas, 128, st}, lcStream{dev->numSMs * 8, 256, st}, lcShade{dev->numSMs * dev->shadeCtas, 128, st};
     FrameTimers& tm = dev->timers; tm.reset();
     const bool timers = dev->useTimers != 0;
-    uint64_t launches = 0, closestLaunches = 0, shadowLaunches = 0;
+    uint64_t launches = 0, closestLaunches = 0, shadowLaunches = 0, shadeLaunches = 0;
     YRT_CK(cudaMemsetAsync(wb.stats, 0, 8 * sizeof(unsigned long long), st));
     cudaEvent_t evStart = tm.get(), evStop = tm.get();
     YRT_CK(cudaEventRecord(evStart, st));
@@ -701,7 +701,7 @@ void render_frames(yrt_device* dev, RendererHandle* rh, size_t numFaces, CameraH
                 if (timers) tm.begin(TK_CLOSEST, st);
                 launch_trace_closest(fc, wq, q, lcTrace); launches++; closestLaunches++;
                 if (timers) { tm.end(st); tm.begin(TK_SHADE, st); }
-                launch_shade(fc, wq, q, (uint32_t)pixelBegin, depth, lcShade); launches++;
+                launch_shade(fc, wq, q, (uint32_t)pixelBegin, depth, lcShade); launches++; shadeLaunches++;
                 if (timers) tm.end(st);
                 // queue lengths of the next bounce: one small read-back per bounce buys the early exit and the sort size. Below
                 // syncMinPaths the round trip costs more than the (short, self-terminating) launches it could save: `alive` then
@@ -715,9 +715,9 @@ void render_frames(yrt_device* dev, RendererHandle* rh, size_t numFaces, CameraH
                 if (fc.scene.numLights > 0) {
                     if (timers) tm.begin(TK_SHADOW, st);
                     launch_trace_shadow(fc, wq, lcTrace); launches++; shadowLaunches++;
-                    if (timers) { tm.end(st); tm.begin(TK_SHADE, st); }
+                    if (timers) { tm.end(st); tm.begin(TK_RESOLVE, st); }
                 }
-                else if (timers) tm.begin(TK_SHADE, st);
+                else if (timers) tm.begin(TK_RESOLVE, st);
                 launch_resolve(fc, wq, q, lcStream); launches += 2;
                 if (timers) tm.end(st);
                 if (readCounters) { YRT_CK(cudaEventSynchronize(evCnt)); alive = dev->hostCounters[q ^ 1]; }
@@ -738,7 +738,7 @@ void render_frames(yrt_device* dev, RendererHandle* rh, size_t numFaces, CameraH
             d2h += b->bytes(); b->pendingBuf = -1;
         } else b->pendingBuf = (int)b->cur;
     }
-    unsigned long long hstats[4] = {0, 0, 0, 0};
+    unsigned long long hstats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     YRT_CK(cudaMemcpyAsync(hstats, wb.stats, sizeof(hstats), cudaMemcpyDeviceToHost, st));
     YRT_CK(cudaStreamSynchronize(st));
     YRT_CK(cudaGetLastError());
@@ -746,17 +746,19 @@ void render_frames(yrt_device* dev, RendererHandle* rh, size_t numFaces, CameraH
 
     yrtx_frame_stats& S = dev->stats;
     float ms = 0.f; YRT_CK(cudaEventElapsedTime(&ms, evStart, evStop));
-    S.render_ms = ms; S.rays_closest = hstats[0]; S.rays_shadow = hstats[1]; S.node_visits = hstats[2]; S.tri_tests = hstats[3];
-    S.kernel_launches = launches; S.closest_launches = closestLaunches; S.shadow_launches = shadowLaunches;
-    S.closest_ms = S.shadow_ms = S.shade_ms = S.raygen_film_ms = S.sort_ms = 0.0;
+    S.render_ms = ms; S.rays_closest = hstats[0]; S.rays_shadow = hstats[1]; S.node_visits = hstats[2] + hstats[4]; S.tri_tests = hstats[3] + hstats[5];
+    S.node_visits_shadow = hstats[4]; S.tri_tests_shadow = hstats[5]; S.path_vertices = R.debug ? 0 : hstats[0]; S.errors = hstats[7];
+    S.kernel_launches = launches; S.closest_launches = closestLaunches; S.shadow_launches = shadowLaunches; S.shade_launches = shadeLaunches;
+    S.closest_ms = S.shadow_ms = S.shade_ms = S.raygen_film_ms = S.sort_ms = S.resolve_ms = S.miss_ms = 0.0;
     for (const auto& sp : tm.spans) {
         if (!sp.b) continue;
         float t = 0.f; YRT_CK(cudaEventElapsedTime(&t, sp.a, sp.b));
         if (sp.kind == TK_CLOSEST) S.closest_ms += t; else if (sp.kind == TK_SHADOW) S.shadow_ms += t;
-        else if (sp.kind == TK_SHADE) S.shade_ms += t; else if (sp.kind == TK_SORT) S.sort_ms += t; else S.raygen_film_ms += t;
+        else if (sp.kind == TK_SHADE) S.shade_ms += t; else if (sp.kind == TK_SORT) S.sort_ms += t;
+        else if (sp.kind == TK_RESOLVE) S.resolve_ms += t; else if (sp.kind == TK_MISS) S.miss_ms += t; else S.raygen_film_ms += t;
     }
     if (dev->verbose >= 2) {   // stage times in launch order (first 160 spans)
-        static const char* names[] = {"raygen/film", "closest", "shade", "shadow", "sort"};
+        static const char* names[] = {"raygen/film", "closest", "shade", "shadow", "sort", "resolve", "miss"};
         size_t shown = 0;
         for (const auto& sp : tm.spans) {
             if (!sp.b || shown++ >= 160) break;
@@ -775,6 +777,7 @@ void render_frames(yrt_device* dev, RendererHandle* rh, size_t numFaces, CameraH
     }
     if (statusFn) { status.state = 2; status.progress = 1.f; statusFn(&status); }   // updateStatus(Done)
     (void)stopped;
+    if (hstats[7] & 1ull) throw std::runtime_error("device_cuda: BVH traversal stack overflow (more than 96 postponed entries on one ray): the frame is incomplete");
 }
 void render_frame(yrt_device* dev, RendererHandle* rh, CameraHandle* ch, SceneHandle* sc, ToneMapperHandle* th, FrameBufferHandle* fb, int accumulate) {
     render_frames(dev, rh, 1, &ch, sc, th, &fb, accumulate);
@@ -797,7 +800,7 @@ void trace_rays(yrt_device* dev, SceneHandle* sc, size_t n, const float* rays, v
         rp = dRays.p; hp = dHits.p;
     }
     dev->wf.ensure(0, 0, 0);
-    if (dev->countStats) YRT_CK(cudaMemsetAsync(dev->wf.wb.stats, 0, 8 * sizeof(unsigned long long), st));
+    YRT_CK(cudaMemsetAsync(dev->wf.wb.stats, 0, 8 * sizeof(unsigned long long), st));
     cudaEvent_t a, b; YRT_CK(cudaEventCreate(&a)); YRT_CK(cudaEventCreate(&b));
     LaunchCfg lc{dev->numSMs * 8, 128, st};
     YRT_CK(cudaEventRecord(a, st));
@@ -807,10 +810,11 @@ void trace_rays(yrt_device* dev, SceneHandle* sc, size_t n, const float* rays, v
     launch_trace_user(sd, rp, hp, n, closest, dev->countStats, dev->wf.wb.stats, dev->wf.wb.counters + 6, lc);
     YRT_CK(cudaEventRecord(b, st));
     if (!onDevice) YRT_CK(cudaMemcpyAsync(hits, dHits.p, 32 * n, cudaMemcpyDeviceToHost, st));
-    unsigned long long hstats[4] = {0, 0, 0, 0};
-    if (dev->countStats) YRT_CK(cudaMemcpyAsync(hstats, dev->wf.wb.stats, sizeof(hstats), cudaMemcpyDeviceToHost, st));
+    unsigned long long hstats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    YRT_CK(cudaMemcpyAsync(hstats, dev->wf.wb.stats, sizeof(hstats), cudaMemcpyDeviceToHost, st));
     YRT_CK(cudaStreamSynchronize(st));
     YRT_CK(cudaGetLastError());
+    if (hstats[7] & 1ull) throw std::runtime_error("device_cuda: BVH traversal stack overflow in yrtxTraceRays");
     float t = 0.f; YRT_CK(cudaEventElapsedTime(&t, a, b));
     cudaEventDestroy(a); cudaEventDestroy(b);
     if (ms) *ms = t;

@@ -168,13 +168,14 @@ struct UserIO {
 
 // ---- A/B baseline: one ray per thread for the life of the thread (bvh.cuh: trace_ray), cfg trav=0 ------------
 template <bool ANY, class IO>
-__global__ void __launch_bounds__(YRT_TRACE_THREADS) k_trace_simple(SceneData sc, IO io, const uint32_t* __restrict__ nPtr, uint32_t nImm) {
+__global__ void __launch_bounds__(YRT_TRACE_THREADS) k_trace_simple(SceneData sc, IO io, const uint32_t* __restrict__ nPtr, uint32_t nImm, unsigned long long* errFlags) {
     const uint32_t n = nPtr ? *nPtr : nImm;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         V3 O, D; float tnear, tfar;
         const uint32_t tag = io.load(i, O, D, tnear, tfar);
-        HitRec h; TraceCounters cnt;
+        HitRec h; TraceCounters cnt = {0, 0, 0};
         const bool hit = trace_ray<ANY, false>((const uint4*)sc.nodes, sc.tris, sc.numNodes, O, D, tnear, tfar, h, &cnt);
+        if (cnt.overflow) atomicOr(errFlags, 1ull);
         if (ANY) io.store_any(tag, hit);
         else io.store_hit(tag, h.t, hit ? h.u : 0.f, hit ? h.v : 0.f, hit ? h.tri : YRT_NO_TRI, sc.tris);
     }
@@ -186,17 +187,18 @@ __global__ void __launch_bounds__(YRT_TRACE_THREADS) k_trace_simple(SceneData sc
 template <bool COUNT>
 __global__ void __launch_bounds__(YRT_TRACE_THREADS, YRT_CLOSEST_MINBLOCKS) k_trace_closest(SceneData sc, WavefrontBuffers wb, int queueSel) {
     const uint32_t n = wb.counters[queueSel];
-    TraceCounters cnt = {0, 0};
+    TraceCounters cnt = {0, 0, 0};
     ClosestIO io{wb, queueSel ? wb.queueB : wb.queueA};
     trace_stream<false, COUNT>((const uint4*)sc.nodes, sc.tris, sc.numNodes, n, &wb.counters[4], io, cnt, TraceTune{sc.tuneRefillMin, sc.tuneTriNum, sc.tuneTriDen});
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&wb.stats[0], (unsigned long long)n);
+    if (cnt.overflow) atomicOr(&wb.stats[7], 1ull);
     if (COUNT) { atomicAdd(&wb.stats[2], (unsigned long long)cnt.nodes); atomicAdd(&wb.stats[3], (unsigned long long)cnt.tris); }
 }
 __global__ void k_count_closest(WavefrontBuffers wb, int queueSel) { atomicAdd(&wb.stats[0], (unsigned long long)wb.counters[queueSel]); }
 void launch_trace_closest(const FrameConst& fc, const WavefrontBuffers& wb, int queueSel, LaunchCfg lc) {
     if (fc.scene.tuneSimple) {
         ClosestIO io{wb, queueSel ? wb.queueB : wb.queueA};
-        k_trace_simple<false><<<lc.blocks, YRT_TRACE_THREADS, 0, lc.stream>>>(fc.scene, io, &wb.counters[queueSel], 0u);
+        k_trace_simple<false><<<lc.blocks, YRT_TRACE_THREADS, 0, lc.stream>>>(fc.scene, io, &wb.counters[queueSel], 0u, &wb.stats[7]);
         k_count_closest<<<1, 1, 0, lc.stream>>>(wb, queueSel);
         return;
     }
@@ -207,13 +209,14 @@ void launch_trace_closest(const FrameConst& fc, const WavefrontBuffers& wb, int 
 template <bool COUNT>
 __global__ void __launch_bounds__(YRT_TRACE_THREADS) k_trace_shadow(SceneData sc, WavefrontBuffers wb) {
     const uint32_t n = wb.counters[2];
-    TraceCounters cnt = {0, 0};
+    TraceCounters cnt = {0, 0, 0};
     ShadowIO io{wb};
     trace_stream<true, COUNT>((const uint4*)sc.nodes, sc.tris, sc.numNodes, n, &wb.counters[5], io, cnt, TraceTune{sc.tuneRefillMin, sc.tuneTriNum, sc.tuneTriDen});
-    if (COUNT) { atomicAdd(&wb.stats[2], (unsigned long long)cnt.nodes); atomicAdd(&wb.stats[3], (unsigned long long)cnt.tris); }
+    if (cnt.overflow) atomicOr(&wb.stats[7], 1ull);
+    if (COUNT) { atomicAdd(&wb.stats[4], (unsigned long long)cnt.nodes); atomicAdd(&wb.stats[5], (unsigned long long)cnt.tris); }
 }
 void launch_trace_shadow(const FrameConst& fc, const WavefrontBuffers& wb, LaunchCfg lc) {
-    if (fc.scene.tuneSimple) { ShadowIO io{wb}; k_trace_simple<true><<<lc.blocks, YRT_TRACE_THREADS, 0, lc.stream>>>(fc.scene, io, &wb.counters[2], 0u); return; }
+    if (fc.scene.tuneSimple) { ShadowIO io{wb}; k_trace_simple<true><<<lc.blocks, YRT_TRACE_THREADS, 0, lc.stream>>>(fc.scene, io, &wb.counters[2], 0u, &wb.stats[7]); return; }
     if (fc.countStats) k_trace_shadow<true><<<lc.blocks, YRT_TRACE_THREADS, 0, lc.stream>>>(fc.scene, wb);
     else k_trace_shadow<false><<<lc.blocks, YRT_TRACE_THREADS, 0, lc.stream>>>(fc.scene, wb);
 }
@@ -221,9 +224,10 @@ void launch_trace_shadow(const FrameConst& fc, const WavefrontBuffers& wb, Launc
 template <bool ANY, bool COUNT>
 __global__ void __launch_bounds__(YRT_TRACE_THREADS) k_trace_user(SceneData sc, const float4* __restrict__ rays, float4* __restrict__ hits, uint32_t n,
                                                                   uint32_t* workCounter, unsigned long long* stats) {
-    TraceCounters cnt = {0, 0};
+    TraceCounters cnt = {0, 0, 0};
     UserIO io{rays, hits};
     trace_stream<ANY, COUNT>((const uint4*)sc.nodes, sc.tris, sc.numNodes, n, workCounter, io, cnt, TraceTune{sc.tuneRefillMin, sc.tuneTriNum, sc.tuneTriDen});
+    if (cnt.overflow && stats) atomicOr(&stats[7], 1ull);
     if (COUNT && stats) { atomicAdd(&stats[2], (unsigned long long)cnt.nodes); atomicAdd(&stats[3], (unsigned long long)cnt.tris); }
 }
 void launch_trace_user(const SceneData& sc, const float* rays, float* hits, size_t n, int closest, int countStats,
@@ -231,8 +235,8 @@ void launch_trace_user(const SceneData& sc, const float* rays, float* hits, size
     const float4* r = (const float4*)rays; float4* h = (float4*)hits; const uint32_t m = (uint32_t)n;
     if (sc.tuneSimple) {
         UserIO io{r, h};
-        if (closest) k_trace_simple<false><<<lc.blocks, YRT_TRACE_THREADS, 0, lc.stream>>>(sc, io, nullptr, m);
-        else k_trace_simple<true><<<lc.blocks, YRT_TRACE_THREADS, 0, lc.stream>>>(sc, io, nullptr, m);
+        if (closest) k_trace_simple<false><<<lc.blocks, YRT_TRACE_THREADS, 0, lc.stream>>>(sc, io, nullptr, m, stats + 7);
+        else k_trace_simple<true><<<lc.blocks, YRT_TRACE_THREADS, 0, lc.stream>>>(sc, io, nullptr, m, stats + 7);
         return;
     }
     if (closest) {
@@ -563,8 +567,8 @@ __global__ void __launch_bounds__(128) k_debug(FrameConst fc, const __grid_const
         const float fx = float(bx) * fc.rcpWidth, fy = float(y) * fc.rcpHeight;
         for (int i = 0; i < fc.integ.spp; i++) {
             V3 org, dir; camera_ray(cams.cam[pc.face], fx, fy, 0.5f, 0.5f, org, dir);
-            HitRec h; TraceCounters cnt = {0, 0};
-            if (fc.integ.maxDepth > 0) { trace_ray<false, false>((const uint4*)sc.nodes, sc.tris, sc.numNodes, org, dir, 0.f, INFINITY, h, &cnt); rays++; }
+            HitRec h; TraceCounters cnt = {0, 0, 0};
+            if (fc.integ.maxDepth > 0) { trace_ray<false, false>((const uint4*)sc.nodes, sc.tris, sc.numNodes, org, dir, 0.f, INFINITY, h, &cnt); rays++; if (cnt.overflow) atomicOr(&wb.stats[7], 1ull); }
             else { h.geomID = -1; h.primID = -1; }
             Col c(1.f);
             if (h.geomID >= 0) {

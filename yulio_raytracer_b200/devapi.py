@@ -36,6 +36,8 @@ class FrameStats(C.Structure):
         ("closest_ms", C.c_double), ("shadow_ms", C.c_double), ("shade_ms", C.c_double), ("raygen_film_ms", C.c_double),
         ("closest_launches", C.c_uint64), ("shadow_launches", C.c_uint64),
         ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("sort_ms", C.c_double), ("bvh_builds", C.c_uint64),
+        ("resolve_ms", C.c_double), ("node_visits_shadow", C.c_uint64), ("tri_tests_shadow", C.c_uint64), ("path_vertices", C.c_uint64),
+        ("shade_launches", C.c_uint64), ("miss_ms", C.c_double), ("errors", C.c_uint64),
     ]
 
 
