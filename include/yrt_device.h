@@ -62,6 +62,9 @@ YRT_API const char* yrtGetLastError(void);                             /* messag
 
 /* ---- creation of objects (device.h:126-223) ----------------------------------------- */
 YRT_API yrt_handle yrtNewCamera(yrt_device*, const char* type);                                   /* device.h:126 */
+/* type "immutable": the bytes are copied. type "immutable_managed": the library takes ownership of `data`, which must be a block
+ * returned by malloc(); it is released with free(). (The reference's callers allocate managed blocks with embree::alignedMalloc, an
+ * interior pointer: the C++ plugin adapter/device_cuda_plugin.cpp copies those and releases them with the alignedFree convention.) */
 YRT_API yrt_handle yrtNewData(yrt_device*, const char* type, size_t bytes, const void* data);     /* device.h:134 */
 YRT_API yrt_handle yrtNewDataFromFile(yrt_device*, const char* type, const char* file, size_t offset, size_t bytes); /* device.h:144 */
 YRT_API yrt_handle yrtNewImage(yrt_device*, const char* type, size_t width, size_t height, const void* data, int copy); /* device.h:151 */

@@ -30,6 +30,9 @@ dependent; DESIGN.md "Parity contract" lists them):
      1/sqrt(x) the reference itself uses in its non-SSE branch (math.h:65,69) [SURVEY F5]
   P4 renderers/integratorrenderer.cpp: ray counter + timing exported through
      a C hook so bench.py can read Mrays/s without scraping stdout (no behaviour change).
+  P5 textures/Bilinear.h:31-34: texels x+1 / y+1 are read past the allocation for a 1-pixel-wide / -tall image (the 1x1
+     white fallback of a missing texture, and the sample scene's own 1x1 JPEGs): the neighbour index is clamped, which is
+     the variant the reference left commented out two lines below (Bilinear.h:36-37). Images >= 2 px per axis are unaffected.
 """
 import os
 import shutil
@@ -87,12 +90,13 @@ def main():
           '#include "materials/uber.h"', '#include "materials/Uber.h"')
     patch("devices/device_singleray/textures/Bilinear.h",
           "return invert ? Color4(1.f) - c : c;", "return invert ? Color4((Color4(1.f) - c).m128) : c;")
+    # B5 + PIN P5 (clamped neighbour texel; the uncommented statement only — the commented-out variant below it stays as it is)
     patch("devices/device_singleray/textures/Bilinear.h",
-          "const Color4 c = (image->get(x, y) * u_opposite",
-          "const Color4 c = Color4((__m128)((image->get(x, y) * u_opposite", count=0)
-    patch("devices/device_singleray/textures/Bilinear.h",
-          "(image->get(x, y + 1) * u_opposite + image->get(x + 1, y + 1) * u_ratio) * v_ratio;",
-          "(image->get(x, y + 1) * u_opposite + image->get(x + 1, y + 1) * u_ratio) * v_ratio));")
+          "const Color4 c = (image->get(x, y) * u_opposite + image->get(x + 1, y) * u_ratio) * v_opposite +\n"
+          "\t\t\t\t(image->get(x, y + 1) * u_opposite + image->get(x + 1, y + 1) * u_ratio) * v_ratio;",
+          "const int x1 = x + 1 > int(image->width) - 1 ? x : x + 1, y1 = y + 1 > int(image->height) - 1 ? y : y + 1; /* PIN P5 */\n"
+          "\t\t\tconst Color4 c = Color4((__m128)((image->get(x, y) * u_opposite + image->get(x1, y) * u_ratio) * v_opposite +\n"
+          "\t\t\t\t(image->get(x, y1) * u_opposite + image->get(x1, y1) * u_ratio) * v_ratio));")
     patch("devices/device_singleray/textures/nearestneighbor.h",
           "return invert ? Color4(1.f) - c : c;", "return invert ? Color4((Color4(1.f) - c).m128) : c;")
     patch("common/sys/intrinsics.h",

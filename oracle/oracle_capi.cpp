@@ -7,6 +7,9 @@
 // embree::Device (reference: devices/device/device.h:126-329) of the object returned by the
 // reference's own factory `create` (devices/device_singleray/api/singleray_device.cpp:105-107).
 #include <chrono>
+#include <thread>
+#include <vector>
+#include <algorithm>
 #include <cstring>
 #include <stdexcept>
 #include <string>
@@ -144,7 +147,11 @@ yrt_status yrtxTraceRays(yrt_device*, yrt_handle scene, size_t n, const float* r
         if (!sh || !sh->getInstance()) throw std::runtime_error("invalid scene handle");
         RTCScene rs = sh->getInstance()->scene;
         auto t0 = std::chrono::steady_clock::now();
-        for (size_t i = 0; i < n; i++) {
+        // large batches (the at-size parity tests: millions of primary rays per cube face) are split over the host threads; the shim's
+        // rtcIntersect / rtcOccluded are re-entrant (the reference calls them from all its render threads)
+        const size_t nThreads = n >= 65536 ? std::max<size_t>(1, std::thread::hardware_concurrency()) : 1;
+        auto work = [&](size_t begin, size_t end) {
+        for (size_t i = begin; i < end; i++) {
             RTCRay r; memset(&r, 0, sizeof(r));
             const float* q = rays + 8 * i;
             r.org[0] = q[0]; r.org[1] = q[1]; r.org[2] = q[2]; r.tnear = q[3];
@@ -159,6 +166,14 @@ yrt_status yrtxTraceRays(yrt_device*, yrt_handle scene, size_t n, const float* r
                 rtcOccluded(rs, r);
                 hi[3] = r.geomID == RTC_INVALID_GEOMETRY_ID ? -1 : 0;
             }
+        }
+        };
+        if (nThreads == 1) work(0, n);
+        else {
+            std::vector<std::thread> th;
+            const size_t per = (n + nThreads - 1) / nThreads;
+            for (size_t k = 0; k < nThreads; k++) { const size_t b = std::min(n, k * per), e = std::min(n, b + per); if (b < e) th.emplace_back(work, b, e); }
+            for (auto& t : th) t.join();
         }
         if (ms) *ms = (float)std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
         return YRT_OK;

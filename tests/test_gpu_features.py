@@ -1,0 +1,142 @@
+"""Parity of the objects that were built but had no test of their own: point / spot / directional / distant lights
+(lights/pointlight.h, spotlight.h, directionallight.h, distantlight.h), the depth-of-field camera (cameras/depthoffieldcamera.h), the disk
+shape (shapes/disk.h:46-67), the backplate (integrators/pathtraceintegrator.cpp:79-84) and 1-pixel textures (pin P5). Same call sequence
+on device_cuda and on the oracle; images at equal spp within the stated bound of tests/test_gpu_parity.py, ray counts identical."""
+import numpy as np
+import pytest
+
+from tests import scenes
+from tests.test_gpu_parity import assert_hits_bit_exact, image_close
+
+pytestmark = pytest.mark.gpu
+W = H = 48
+
+
+def _cornell_with(dev, lights, camera=None, extra_prims=(), spp=8, depth=3, **kw):
+    prims = scenes.cornell_prims(dev) + list(extra_prims(dev) if callable(extra_prims) else extra_prims) + lights(dev)
+    cam = camera(dev) if camera else scenes.pinhole(dev, (278, 273, -800), (278, 273, 0), (0, 1, 0), 37.0, W / H)
+    return scenes._bundle(dev, prims, cam, scenes.pathtracer(dev, spp, depth, **kw), W, H)
+
+
+def _light(dev, kind, **p):
+    l = dev.rtNewLight(kind)
+    for k, v in p.items():
+        if isinstance(v, (tuple, list)):
+            dev.rtSetFloat3(l, k, *v)
+        else:
+            dev.rtSetFloat1(l, k, float(v))
+    dev.rtCommit(l)
+    return dev.rtNewLightPrimitive(l, None, None)
+
+
+def _both(cuda_dev, oracle_dev, build, mean_tol=2e-4):
+    imgs = []
+    for d in (cuda_dev, oracle_dev):
+        s = build(d)
+        d.rtRenderFrame(s.renderer, s.camera, s.scene, s.tonemapper, s.framebuffer, 0)
+        imgs.append(d.read_framebuffer(s.framebuffer, "RGB_FLOAT32", W, H))
+    assert imgs[1].mean() > 1e-3, "the oracle image is black: the test lights nothing"
+    image_close(imgs[0], imgs[1], mean_tol=mean_tol)
+    sg, so = cuda_dev.frame_stats(), oracle_dev.frame_stats()
+    assert sg.rays_closest + sg.rays_shadow == so.rays_closest, "ray counts differ (pathtraceintegrator.cpp:74,161)"
+    return imgs
+
+
+LIGHTS = {
+    "pointlight": dict(P=(278, 400, 279), I=(4e5, 3.6e5, 3e5)),
+    "spotlight": dict(P=(278, 540, 279), D=(0.1, -1, 0.05), I=(9e5, 9e5, 8e5), angleMin=20.0, angleMax=40.0),
+    "spotlight_hard": dict(P=(278, 540, 279), D=(0, -1, 0), I=(9e5, 9e5, 8e5), angleMin=35.0, angleMax=35.0),
+    "directionallight": dict(D=(0.3, -1, 0.6), E=(3, 3, 2.5)),
+    "distantlight": dict(D=(0.2, -1, 0.5), L=(900, 850, 800), halfAngle=3.0),
+}
+
+
+@pytest.mark.parametrize("name", sorted(LIGHTS))
+@pytest.mark.parametrize("tmax", [float("inf"), 150.0])
+def test_analytic_lights(cuda_dev, oracle_dev, name, tmax):
+    kind = name.split("_")[0]
+    _both(cuda_dev, oracle_dev, lambda d: _cornell_with(d, lambda dd: [_light(dd, kind, **LIGHTS[name])], tmax_shadow=tmax))
+
+
+def test_transformed_lights(cuda_dev, oracle_dev):
+    """Light::transform through rtNewLightPrimitive's transform (lights/*.h)."""
+    xfm = np.array([0, 0, 1, 0, 1, 0, -1, 0, 0, 20, -30, 10], np.float32)
+
+    def lights(d):
+        out = []
+        for kind, p in (("pointlight", LIGHTS["pointlight"]), ("spotlight", LIGHTS["spotlight"]), ("distantlight", LIGHTS["distantlight"])):
+            l = d.rtNewLight(kind)
+            for k, v in p.items():
+                d.rtSetFloat3(l, k, *v) if isinstance(v, tuple) else d.rtSetFloat1(l, k, float(v))
+            d.rtCommit(l)
+            out.append(d.rtNewLightPrimitive(l, None, xfm))
+        return out
+    _both(cuda_dev, oracle_dev, lambda d: _cornell_with(d, lights, tmax_shadow=150.0))
+
+
+def test_depth_of_field_camera(cuda_dev, oracle_dev):
+    def cam(d):
+        c = d.rtNewCamera("depthoffield")
+        d.rtSetTransform(c, "local2world", scenes.look_at((278, 273, -800), (278, 273, 0), (0, 1, 0)))
+        d.rtSetFloat1(c, "angle", 37.0); d.rtSetFloat1(c, "aspectRatio", W / H)
+        d.rtSetFloat1(c, "lensRadius", 25.0); d.rtSetFloat1(c, "focalDistance", 1000.0)
+        d.rtCommit(c)
+        return c
+    lights = lambda d: scenes.quad_light(d, (213, 548.77, 227), (130, 0, 0), (0, 0, 105), (50, 50, 50))
+    _both(cuda_dev, oracle_dev, lambda d: _cornell_with(d, lights, camera=cam))
+    # primary rays of the lens camera: origins on the lens disk, bit-comparable up to sinf/cosf of the disk sample
+    sg = _cornell_with(cuda_dev, lights, camera=cam)
+    rays, _ = cuda_dev.primary_rays(sg.renderer, sg.camera, sg.framebuffer, W, H, 8)
+    r = np.linalg.norm(rays[:, 0:3] - np.array([278, 273, -800], np.float32), axis=1)
+    assert r.max() <= 25.0 * (1 + 1e-5) and r.max() > 20.0 and np.allclose(np.linalg.norm(rays[:, 4:7], axis=1), 1.0, atol=1e-5)
+
+
+def test_disk_shape(cuda_dev, oracle_dev):
+    def disk(d):
+        m = d.rtNewMaterial("matte"); d.rtSetFloat3(m, "reflectance", .7, .6, .2); d.rtCommit(m)
+        s = d.rtNewShape("disk")
+        d.rtSetFloat3(s, "P", 278, 120, 279); d.rtSetFloat1(s, "h", 60.0); d.rtSetFloat1(s, "r", 150.0); d.rtSetInt1(s, "numTriangles", 24)
+        d.rtCommit(s)
+        return [d.rtNewShapePrimitive(s, m, None)]
+    lights = lambda d: scenes.quad_light(d, (213, 548.77, 227), (130, 0, 0), (0, 0, 105), (50, 50, 50))
+    _both(cuda_dev, oracle_dev, lambda d: _cornell_with(d, lights, extra_prims=disk))
+    # and the tessellation itself: primary hits on the disk bit-exact (geometry built inside each device)
+    sg, so = (_cornell_with(d, lights, extra_prims=disk) for d in (cuda_dev, oracle_dev))
+    rays, _ = cuda_dev.primary_rays(sg.renderer, sg.camera, sg.framebuffer, W, H, 8)
+    hg, _ = cuda_dev.trace_rays(sg.scene, rays, closest=True)
+    ho, _ = oracle_dev.trace_rays(so.scene, rays, closest=True)
+    assert (ho.view(np.int32)[:, 3] == 8).sum() > 100          # geomID 8 = the disk (after the 8 Cornell meshes)
+    assert_hits_bit_exact(hg, ho)
+
+
+def test_backplate(cuda_dev, oracle_dev):
+    """Unbent paths that leave the scene read the backplate image at the pixel position (pathtraceintegrator.cpp:79-84); bent ones the
+    environment lights."""
+    rng = np.random.default_rng(5)
+    plate = rng.random((20, 30, 3)).astype(np.float32)
+
+    def build(d):
+        img = d.rtNewImage("RGB_FLOAT32", 30, 20, plate)
+        prims = scenes.spheres_prims(d, "glass", 12) + [scenes.ambient_light(d, (.4, .5, .6))]
+        cam = scenes.pinhole(d, (-200, 100, 200), (0, 100, 200), (0, 1, 0), 90.0, W / H)
+        return scenes._bundle(d, prims, cam, scenes.pathtracer(d, 8, 4, backplate=img), W, H)
+    imgs = _both(cuda_dev, oracle_dev, build)
+    assert imgs[0][: H // 4].std() > 0.05                      # the noise image shows through the sky part of the frame
+
+
+def test_one_pixel_textures(cuda_dev, oracle_dev):
+    """Pin P5: 1x1 (and 1xN, Nx1) images under the bilinear filter — the missing-texture fallback (singleray_device.cpp:250) and the sample
+    scene's own 1x1 JPEGs — render their single colour on both sides instead of reading past the allocation."""
+    def build(d):
+        prims = []
+        for k, (w, h) in enumerate(((1, 1), (1, 5), (6, 1))):
+            px = np.full((h, w, 4), 255, np.uint8); px[..., k % 3] = 40 + 60 * k; px[..., 3] = 255
+            tex, _ = scenes.texture(d, px)
+            p, n, u, t = scenes.grid_quad((100 + 150 * k, 50, 300), (120, 0, 0), (0, 300, 0), 2, 2, (3, 2))
+            prims.append(d.rtNewShapePrimitive(scenes.add_mesh(d, p, t, normals=n, uvs=u), scenes.uber(d, tex), None))
+        prims += scenes.cornell_prims(d) + scenes.quad_light(d, (213, 548.77, 227), (130, 0, 0), (0, 0, 105), (50, 50, 50))
+        cam = scenes.pinhole(d, (278, 273, -800), (278, 273, 0), (0, 1, 0), 37.0, W / H)
+        return scenes._bundle(d, prims, cam, scenes.pathtracer(d, 8, 3), W, H)
+    a = _both(cuda_dev, oracle_dev, build)[0]
+    b = _both(cuda_dev, oracle_dev, build)[0]
+    assert np.array_equal(a, b), "frames with 1-pixel textures must be reproducible"

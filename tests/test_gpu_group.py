@@ -105,3 +105,50 @@ def test_front_end_on_two_gpus(tmp_path):
     # same scene, same spp, different sample-set assignment per pixel (the per-tile LCG is seeded with the server id): two noisy
     # estimates of the same image
     assert abs(a.mean() - b.mean()) <= 1.5 and np.abs(a - b).mean() <= 12.0, (a.mean(), b.mean(), np.abs(a - b).mean())
+
+
+@needs2
+def test_group_cube_map_and_device_side_assembly():
+    """yrtxRenderCubeMap on a group: every member renders its bands of all faces as one wavefront; the strip takes the frames from member 0's
+    assembled device copy (peer copies over NVLink) — no frame crosses to the host until a frame buffer is mapped."""
+    from yulio_raytracer_b200 import Device
+    W, N = 40, 2
+    grp = Device.cuda(cfg=f"gpus={N}")
+    s = scenes.atrium(grp, W, W, 4, 5, face=0, detail=4, fmt="RGB8", tex_size=32)
+    cams = scenes.cube_cameras(grp, s)
+    fbs = [grp.rtNewFrameBuffer("RGB8", W, W, 1) for _ in cams]
+    scenes.render_cube_map_batched(grp, s, cams, fbs)
+    grp.strip_begin(W, W)
+    for i, fb in enumerate(fbs):
+        grp.strip_add_face(fb, i)
+    assert grp.frame_stats().d2h_bytes == 0, "a member copied its bands to the host"
+    strip = grp.strip_read(W, W)
+    faces = [grp.read_framebuffer(fb, "RGB8", W, W) for fb in fbs]
+    order = [3, 1, 4, 5, 2, 0]
+    ref = np.concatenate([faces[(6 if seg < 6 else 0) + order[seg % 6]] for seg in range(12)], axis=1)
+    assert np.array_equal(strip, ref)
+    # per-face loop on the same group: identical frames
+    for i, _ in scenes.render_cube_map(grp, s, faces=[0, 7]):
+        assert np.array_equal(grp.read_framebuffer(s.framebuffer, "RGB8", W, W), faces[i])
+    grp.close()
+
+
+@needs2
+def test_group_ignores_member_keys_in_the_user_cfg():
+    """cfg "gpus=2,gpu=0,serverID=0,serverCount=1" must still put the members on two GPUs with bands 0/2 and 1/2 (the first
+    match of a key wins in the cfg parser, so the group strips the keys it assigns itself)."""
+    import torch
+    from yulio_raytracer_b200 import Device
+    W = 32
+    free_before = [torch.cuda.mem_get_info(i)[0] for i in range(2)]
+    a = Device.cuda(cfg="gpus=2")
+    b = Device.cuda(cfg="gpus=2,gpu=0,serverID=0,serverCount=1")
+    frames = []
+    for d in (a, b):
+        s = scenes.atrium(d, W, W, 4, 4, face=1, detail=4, fmt="RGB8", tex_size=32)
+        d.rtRenderFrame(s.renderer, s.camera, s.scene, s.tonemapper, s.framebuffer, 0)
+        frames.append(d.read_framebuffer(s.framebuffer, "RGB8", W, W))
+    free_after = [torch.cuda.mem_get_info(i)[0] for i in range(2)]
+    assert np.array_equal(frames[0], frames[1])
+    assert all(free_before[i] - free_after[i] > (64 << 20) for i in range(2)), "a member is missing from one of the GPUs"
+    a.close(); b.close()

@@ -8,6 +8,8 @@
 // are turned back into the std::runtime_error the reference's callers expect (api/singleray_device.cpp:190..435).
 // Nothing else of the reference is linked: the plugin depends only on libyrt_device_cuda.so.
 #include <stdexcept>
+#include <strings.h>
+#include <cstdlib>
 #include <string>
 
 #include "device/device.h"
@@ -27,7 +29,17 @@ public:
     ~CudaDevice() override { yrtDestroyDevice(d); }
 
     RTCamera rtNewCamera(const char* type) override { return (RTCamera)ok(yrtNewCamera(d, type), "rtNewCamera"); }
-    RTData rtNewData(const char* type, size_t bytes, const void* data) override { return (RTData)ok(yrtNewData(d, type, bytes, data), "rtNewData"); }
+    // "immutable_managed" hands over a block the reference's callers allocate with embree::alignedMalloc (xml_loader.cpp:227-267,
+    // network_server.cpp:138) — an INTERIOR pointer whose malloc base lies ((int*)ptr)[-1] bytes before it (common/sys/platform.cpp:171-188).
+    // The C-ABI's managed type owns a plain malloc() block, so here the data is copied and the caller's block released the reference's way.
+    RTData rtNewData(const char* type, size_t bytes, const void* data) override {
+        if (type && !strcasecmp(type, "immutable_managed")) {
+            RTData h = (RTData)ok(yrtNewData(d, "immutable", bytes, data), "rtNewData");
+            if (data) { const int ofs = ((const int*)data)[-1]; free((char*)data - ofs); }     // embree::alignedFree
+            return h;
+        }
+        return (RTData)ok(yrtNewData(d, type, bytes, data), "rtNewData");
+    }
     RTData rtNewDataFromFile(const char* type, const char* file, size_t offset, size_t bytes) override { return (RTData)ok(yrtNewDataFromFile(d, type, file, offset, bytes), "rtNewDataFromFile"); }
     RTImage rtNewImage(const char* type, size_t width, size_t height, const void* data, const bool copy) override { return (RTImage)ok(yrtNewImage(d, type, width, height, data, copy ? 1 : 0), "rtNewImage"); }
     RTImage rtNewImageFromFile(const char* file) override { return (RTImage)ok(yrtNewImageFromFile(d, file), "rtNewImageFromFile"); }

@@ -482,16 +482,29 @@ __global__ void k_collapse(CollapseArgs a) {
 // ---------------------------------------------------------------------------------------------
 // Scratch comes from the stream-ordered pool (cudaMallocAsync): a rebuild per cube face must not pay
 // cudaMalloc/cudaFree round trips (measured: 30 ms ... 1.4 s of wall clock per build with the synchronous allocator).
-static thread_local cudaStream_t g_allocStream = nullptr;   // per host thread: a group device builds on several GPUs at once (group_api.cu)
-template <typename T> static T* dalloc(size_t n) { T* p = nullptr; CK(cudaMallocAsync((void**)&p, (n ? n : 1) * sizeof(T), g_allocStream)); return p; }
-static void dfree(void* p) { if (p) cudaFreeAsync(p, g_allocStream); }
+// Every scratch block and both events belong to a BuildScratch: whatever is still registered when build_bvh leaves — normally or
+// through an exception (out of memory, a failed launch) — is released by its destructor.
+struct BuildScratch {
+    cudaStream_t stream; std::vector<void*> live; cudaEvent_t e0 = nullptr, e1 = nullptr;
+    explicit BuildScratch(cudaStream_t s) : stream(s) {}
+    void forget(void* p) { for (size_t i = live.size(); i-- > 0;) if (live[i] == p) { live.erase(live.begin() + (long)i); return; } }
+    ~BuildScratch() { for (void* p : live) cudaFreeAsync(p, stream); if (e0) cudaEventDestroy(e0); if (e1) cudaEventDestroy(e1); }
+};
+static thread_local BuildScratch* g_scratch = nullptr;      // per host thread: a group device builds on several GPUs at once (group_api.cu)
+template <typename T> static T* dalloc(size_t n) {
+    T* p = nullptr; CK(cudaMallocAsync((void**)&p, (n ? n : 1) * sizeof(T), g_scratch->stream));
+    g_scratch->live.push_back(p);
+    return p;
+}
+static void dfree(void* p) { if (p) { g_scratch->forget(p); cudaFreeAsync(p, g_scratch->stream); } }
 
 void build_bvh(const BvhBuildInput& in, BvhResult& out, cudaStream_t stream) {
     out.nodes = nullptr; out.tris = nullptr; out.triShade = nullptr; out.numNodes = 0; out.numTris = 0; out.buildMs = 0.f; out.launches = 0;
     const uint32_t n = in.numRefs;
     if (n == 0) return;
-    g_allocStream = stream;
-    cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    BuildScratch scratch(stream); g_scratch = &scratch;
+    CK(cudaEventCreate(&scratch.e0)); CK(cudaEventCreate(&scratch.e1));
+    const cudaEvent_t e0 = scratch.e0, e1 = scratch.e1;
     CK(cudaEventRecord(e0, stream));
     const int B = 256; const uint32_t G = (n + B - 1) / B;
 
@@ -590,13 +603,14 @@ void build_bvh(const BvhBuildInput& in, BvhResult& out, cudaStream_t stream) {
     CK(cudaStreamSynchronize(stream));
     CK(cudaEventElapsedTime(&out.buildMs, e0, e1));
     out.nodes = nodes; out.tris = tris; out.triShade = triShade;
+    scratch.forget(nodes); scratch.forget(tris); scratch.forget(triShade);      // the results outlive the build (SceneHandle::releaseDevice)
 
     dfree(nodesTmp); dfree(counters); dfree(tasksA); dfree(tasksB);
     dfree(t.left); dfree(t.right); dfree(t.parent); dfree(t.count);
     dfree(t.lo); dfree(t.hi); dfree(t.visit); dfree(leafLo); dfree(leafHi);
     dfree(tmp); dfree(keys); dfree(keysSorted); dfree(vals); dfree(sortedIdx);
     dfree(boxLo); dfree(boxHi); dfree(sceneBounds);
-    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    g_scratch = nullptr;
 }
 
 }  // namespace yrt

@@ -29,7 +29,7 @@
 #include "gen/core_decls.inc"
 
 namespace yrt { extern thread_local std::string g_lastError;
-void strip_add_face_host(yrt_device* dev, const unsigned char* rgb, size_t strideBytes, size_t w, size_t h, int cubeFaceIndex, int watermark); }
+void strip_add_face_device(yrt_device* dev, const unsigned char* devRgb, size_t strideBytes, size_t w, size_t h, int cubeFaceIndex, int watermark); }
 
 namespace grp {
 
@@ -40,7 +40,13 @@ struct Handle {                                        // one API object on ever
     // frame buffers only
     bool isFrameBuffer = false; int format = 2; size_t width = 0, height = 0, depth = 1, cur = 0, strideBytes = 0;
     std::vector<void*> host; std::vector<bool> owned;
-    ~Handle() { for (size_t i = 0; i < host.size(); i++) if (owned[i]) free(host[i]); }
+    // the assembled frame lives on member 0: `staging` receives every member's compacted bands over NVLink (one cudaMemcpyPeerAsync
+    // per member), k_interleave_bands writes them to their raster rows in `full`
+    int gpu0 = 0; unsigned char* staging = nullptr; unsigned char* full = nullptr; size_t memberBytes = 0; uint64_t hostCopies = 0, peerCopies = 0;
+    ~Handle() {
+        for (size_t i = 0; i < host.size(); i++) if (owned[i]) cudaFreeHost(host[i]);
+        if (staging || full) { cudaSetDevice(gpu0); if (staging) cudaFree(staging); if (full) cudaFree(full); }
+    }
 };
 
 inline bool is(const yrt_device* d) { return d && !d->members.empty(); }
@@ -140,6 +146,21 @@ static long cfg_int(const std::string& cfg, const char* key, long def) {
     return def;
 }
 
+// cfg without the keys the group assigns per member (the first match of a key wins in cfg_int: a user's "gpu=" or "serverID=" must not
+// reach the members, or all of them would land on one GPU / render the same bands)
+static std::string cfg_without_member_keys(const std::string& cfg) {
+    std::string out; size_t pos = 0;
+    while (pos < cfg.size()) {
+        size_t end = cfg.find(',', pos); if (end == std::string::npos) end = cfg.size();
+        std::string item = cfg.substr(pos, end - pos);
+        std::string key = item.substr(0, item.find('='));
+        while (!key.empty() && key[0] == ' ') key.erase(0, 1);
+        if (!item.empty() && key != "gpus" && key != "gpu" && key != "serverID" && key != "serverCount") { if (!out.empty()) out += ","; out += item; }
+        pos = end + 1;
+    }
+    return out;
+}
+
 yrt_device* yrtCreateDevice(const char* parms, size_t numThreads, int threadsPriority, const char* cfg) {
     const std::string c(cfg ? cfg : "");
     const long n = cfg_int(c, "gpus", 1);
@@ -148,13 +169,16 @@ yrt_device* yrtCreateDevice(const char* parms, size_t numThreads, int threadsPri
         int have = 0; cudaGetDeviceCount(&have);
         if (n > have) throw std::runtime_error("device_cuda: cfg gpus=" + std::to_string(n) + " but only " + std::to_string(have) + " CUDA device(s) are visible");
         const long first = cfg_int(c, "gpu", 0);
+        if (first < 0 || first + n > have) throw std::runtime_error("device_cuda: cfg gpu=" + std::to_string(first) + ",gpus=" + std::to_string(n) + " exceeds the " + std::to_string(have) + " visible CUDA device(s)");
+        const std::string rest = cfg_without_member_keys(c);
         std::unique_ptr<yrt_device> g(new yrt_device());
         // the members' CUDA contexts are created concurrently (about 1.5 s each)
         std::vector<yrt_device*> ms((size_t)n, nullptr); std::vector<std::string> err((size_t)n); std::vector<std::thread> th;
         for (long i = 0; i < n; i++)
             th.emplace_back([&, i] {
-                const std::string mc = c + ",gpus=1,gpu=" + std::to_string(first + i) + ",serverID=" + std::to_string(i) + ",serverCount=" + std::to_string(n);
-                ms[(size_t)i] = yrtCreateDevice_core(parms, numThreads, threadsPriority, mc.c_str());     // later keys override earlier ones
+                const std::string mc = "gpus=1,gpu=" + std::to_string(first + i) + ",serverID=" + std::to_string(i) + ",serverCount=" + std::to_string(n) +
+                                       (rest.empty() ? "" : "," + rest);
+                ms[(size_t)i] = yrtCreateDevice_core(parms, numThreads, threadsPriority, mc.c_str());
                 if (!ms[(size_t)i]) err[(size_t)i] = yrtGetLastError_core();
             });
         for (auto& t : th) t.join();
@@ -164,6 +188,13 @@ yrt_device* yrtCreateDevice(const char* parms, size_t numThreads, int threadsPri
                 throw std::runtime_error(err[(size_t)i]);
             }
         g->members = ms;
+        // frames are assembled on member 0 over NVLink: peer access from GPU 0 to the others, and no per-member host copies
+        cudaSetDevice(ms[0]->gpu);
+        for (long i = 1; i < n; i++) {
+            int can = 0; cudaDeviceCanAccessPeer(&can, ms[0]->gpu, ms[(size_t)i]->gpu);
+            if (can) { const cudaError_t e = cudaDeviceEnablePeerAccess(ms[(size_t)i]->gpu, 0); if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError(); else cudaGetLastError(); }
+        }
+        for (yrt_device* m : ms) m->readback = false;
         return g.release();
     } catch (const std::exception& e) { fail(e); return nullptr; }
 }
@@ -196,10 +227,44 @@ yrt_handle yrtNewFrameBuffer(yrt_device* dev, const char* type, size_t width, si
     for (size_t i = 0; i < g->depth; i++) {
         void* p = ptrs ? ptrs[i] : nullptr; bool own = false;
         const size_t bytes = g->strideBytes * height;
-        if (!p) { p = calloc(1, bytes != 0 ? bytes : 1); own = true; }
+        if (!p) { YRT_CK(cudaHostAlloc(&p, bytes != 0 ? bytes : 1, cudaHostAllocPortable)); memset(p, 0, bytes); own = true; }
         g->host.push_back(p); g->owned.push_back(own);
     }
     return h;
+}
+
+// raster row y of the assembled frame <- buffer row 4 * ((y >> 2) / n) + (y & 3) of member (y >> 2) % n  (api/swapchain.h:57-70)
+__global__ void k_interleave_bands(const uint32_t* __restrict__ staging, size_t memberWords, int n, int height, int strideWords, uint32_t* __restrict__ full) {
+    const size_t total = (size_t)height * strideWords;
+    for (size_t w = (size_t)blockIdx.x * blockDim.x + threadIdx.x; w < total; w += (size_t)gridDim.x * blockDim.x) {
+        const int y = (int)(w / strideWords), x = (int)(w % strideWords);
+        const int member = (y >> 2) % n, row = 4 * ((y >> 2) / n) + (y & 3);
+        full[w] = staging[(size_t)member * memberWords + (size_t)row * strideWords + x];
+    }
+}
+
+// The members' bands -> the full frame on member 0, GPU to GPU: one cudaMemcpyPeerAsync per member over NVLink, one interleave kernel.
+// The members have finished rendering (yrtRenderFrame / yrtxRenderCubeMap return after their streams are idle). Caller holds dev->mutex.
+static const unsigned char* assemble_on_member0(yrt_device* dev, Handle* g) {
+    const size_t n = dev->members.size();
+    yrt_device* m0 = dev->members[0];
+    m0->bind();
+    const size_t maxRows = 4 * ((((g->height + 3) >> 2) + n - 1) / n);
+    g->memberBytes = maxRows * g->strideBytes; g->gpu0 = m0->gpu;
+    if (!g->staging) { YRT_CK(cudaMalloc((void**)&g->staging, std::max<size_t>(16, n * g->memberBytes))); YRT_CK(cudaMalloc((void**)&g->full, std::max<size_t>(16, g->height * g->strideBytes))); }
+    for (size_t i = 0; i < n; i++) {
+        void* src = nullptr; size_t bytes = 0, stride = 0;
+        if (yrtxFrameBufferDevice_core(dev->members[i], g->m[i], &src, &bytes, &stride) != YRT_OK) throw std::runtime_error(yrtGetLastError_core());
+        m0->bind();
+        size_t rows = 0; for (size_t y = 0; y < g->height; y++) if ((((y >> 2) + n - i) % n) == 0) rows++;
+        YRT_CK(cudaMemcpyPeerAsync(g->staging + i * g->memberBytes, m0->gpu, src, dev->members[i]->gpu, rows * g->strideBytes, m0->stream));
+        g->peerCopies++;
+    }
+    const size_t words = g->height * g->strideBytes / 4;
+    k_interleave_bands<<<(unsigned)std::min<size_t>(4096, (words + 255) / 256 + 1), 256, 0, m0->stream>>>((const uint32_t*)g->staging, g->memberBytes / 4, (int)n, (int)g->height,
+                                                                                                          (int)(g->strideBytes / 4), (uint32_t*)g->full);
+    YRT_CK(cudaGetLastError());
+    return g->full;
 }
 
 void* yrtMapFrameBuffer(yrt_device* dev, yrt_handle fb, int bufID) {
@@ -207,18 +272,14 @@ void* yrtMapFrameBuffer(yrt_device* dev, yrt_handle fb, int bufID) {
         Handle* g = gh(fb);
         if (!g->isFrameBuffer) throw std::runtime_error("invalid framebuffer handle");
         std::lock_guard<std::mutex> lock(dev->mutex);
-        const size_t buf = bufID < 0 ? g->cur : (size_t)bufID % g->depth, n = dev->members.size();
+        const size_t buf = bufID < 0 ? g->cur : (size_t)bufID % g->depth;
         unsigned char* out = (unsigned char*)g->host[buf];
-        // every member copies its compacted bands to its host buffer; the rows are re-interleaved into the caller's frame
-        const yrt_status rc = each_parallel(dev, [&](yrt_device* m, int i) -> yrt_status {
-            const unsigned char* src = (const unsigned char*)yrtMapFrameBuffer_core(m, g->m[(size_t)i], bufID);
-            if (!src) return YRT_ERROR;
-            size_t row = 0;
-            for (size_t y = 0; y < g->height; y++)
-                if ((((y >> 2) + n - (size_t)i) % n) == 0) { memcpy(out + y * g->strideBytes, src + row * g->strideBytes, g->strideBytes); row++; }
-            return yrtUnmapFrameBuffer_core(m, g->m[(size_t)i], bufID);
-        });
-        return rc == YRT_OK ? out : nullptr;
+        const unsigned char* full = assemble_on_member0(dev, g);
+        yrt_device* m0 = dev->members[0];
+        YRT_CK(cudaMemcpyAsync(out, full, g->height * g->strideBytes, cudaMemcpyDeviceToHost, m0->stream));    // the ONE host copy of the frame
+        YRT_CK(cudaStreamSynchronize(m0->stream));
+        g->hostCopies++;
+        return out;
     } catch (const std::exception& e) { fail(e); return nullptr; }
 }
 yrt_status yrtUnmapFrameBuffer(yrt_device*, yrt_handle fb, int) { try { gh(fb); return YRT_OK; } catch (const std::exception& e) { return fail(e); } }
@@ -319,9 +380,20 @@ yrt_status yrtxPrimaryRays(yrt_device* dev, yrt_handle r, yrt_handle c, yrt_hand
 yrt_status yrtxSampleTable(yrt_device* dev, yrt_handle r, yrt_handle s, int it, int* sets, int* spp, int* n1, int* n2, float* table) {
     try { return yrtxSampleTable_core(m0(dev), un(r, 0), un(s, 0), it, sets, spp, n1, n2, table); } catch (const std::exception& e) { return fail(e); }
 }
-yrt_status yrtxFrameBufferDevice(yrt_device*, yrt_handle, void**, size_t*, size_t*) {
-    yrt::g_lastError = "device_cuda: a group device has no single device frame (map the frame buffer instead)"; return YRT_ERROR;
+// the assembled frame on member 0 (bands gathered over NVLink); valid until the next render into this frame buffer
+yrt_status yrtxFrameBufferDevice(yrt_device* dev, yrt_handle fb, void** devPtr, size_t* bytes, size_t* strideBytes) {
+    try {
+        Handle* g = gh(fb);
+        if (!g->isFrameBuffer) throw std::runtime_error("invalid framebuffer handle");
+        std::lock_guard<std::mutex> lock(dev->mutex);
+        const unsigned char* full = assemble_on_member0(dev, g);
+        YRT_CK(cudaStreamSynchronize(dev->members[0]->stream));
+        if (devPtr) *devPtr = (void*)full; if (bytes) *bytes = g->height * g->strideBytes; if (strideBytes) *strideBytes = g->strideBytes;
+        return YRT_OK;
+    } catch (const std::exception& e) { return fail(e); }
 }
+// a group's frames reach the host through yrtMapFrameBuffer only (assembled on member 0 first): the members never copy their bands out
+yrt_status yrtxSetReadback(yrt_device* dev, int) { for (yrt_device* m : dev->members) m->readback = false; return YRT_OK; }
 yrt_status yrtxReadImage(yrt_device* dev, yrt_handle img, int* w, int* h, int* f, void* px) {
     try { return yrtxReadImage_core(m0(dev), un(img, 0), w, h, f, px); } catch (const std::exception& e) { return fail(e); }
 }
@@ -334,10 +406,11 @@ yrt_status yrtxStripAddFace(yrt_device* dev, yrt_handle fb, int face, int waterm
     try {
         Handle* g = gh(fb);
         if (g->format != 2) throw std::runtime_error("device_cuda: the strip takes RGB8 frames");
-        const unsigned char* px = (const unsigned char*)grp::yrtMapFrameBuffer(dev, fb, -1);
-        if (!px) return YRT_ERROR;
-        std::lock_guard<std::mutex> lock(m0(dev)->mutex); m0(dev)->bind();
-        yrt::strip_add_face_host(m0(dev), px, g->strideBytes, g->width, g->height, face, watermark);
+        // bands -> member 0 over NVLink -> strip segment: the frame never touches the host
+        std::lock_guard<std::mutex> lock(dev->mutex);
+        const unsigned char* full = assemble_on_member0(dev, g);
+        std::lock_guard<std::mutex> lock0(m0(dev)->mutex); m0(dev)->bind();
+        yrt::strip_add_face_device(m0(dev), full, g->strideBytes, g->width, g->height, face, watermark);
         return YRT_OK;
     } catch (const std::exception& e) { return fail(e); }
 }

@@ -510,7 +510,9 @@ yrt_handle yrtNewData(yrt_device* dev, const char* type, size_t bytes, const voi
     GUARD_H(const std::string t = lower(type);
             auto d = std::make_shared<DataObj>(); d->bytes = bytes;
             if (t == "immutable") {                                    // api/data.h:33-38 (copy)
-                d->ptr = (char*)malloc(bytes ? bytes : 1); if (bytes && data) memcpy(d->ptr, data, bytes);
+                d->ptr = (char*)malloc(bytes ? bytes : 1);
+                if (!d->ptr) throw std::runtime_error("memory allocation failed");
+                if (bytes && data) memcpy(d->ptr, data, bytes);
             } else if (t == "immutable_managed") d->ptr = (char*)data;  // takes ownership (freed with the handle)
             else throw std::runtime_error("unknown data buffer type: " + std::string(type ? type : ""));
             auto* h = new DataHandle(); h->type = t; h->inst = d; return h;)
@@ -522,6 +524,7 @@ yrt_handle yrtNewDataFromFile(yrt_device* dev, const char* type, const char* fil
             FILE* f = fopen(file ? file : "", "rb");
             if (!f) throw std::runtime_error("cannot open file " + std::string(file ? file : ""));
             auto d = std::make_shared<DataObj>(); d->bytes = bytes; d->ptr = (char*)malloc(bytes ? bytes : 1);
+            if (!d->ptr) { fclose(f); throw std::runtime_error("memory allocation failed"); }
             fseek(f, (long)offset, SEEK_SET);
             const size_t got = fread(d->ptr, 1, bytes, f); fclose(f);
             if (got != bytes) throw std::runtime_error("error filling data buffer from file");

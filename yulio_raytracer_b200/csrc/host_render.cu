@@ -237,10 +237,12 @@ void scene_commit(yrt_device* dev, SceneHandle* sc) {
     if (patched == 1) {                                        // vertices of a few slots moved: rebuild the BVH over the patched arrays
         lap("patch");
         sc->patchSlots.clear();
-        sc->releaseDevice();
+        // the old BVH is released only once the new one exists; a failed build leaves the scene uncommitted (never dangling pointers)
         BvhBuildInput in{sc->refsBuf.p, sc->numRefs, sc->geoms.p, sc->positions.p, sc->indices.p, sc->normals.p, sc->uvs.p, dev->hostCounters + 8, dev->bvhPloc, dev->splitLeaves, dev->plocRadius};
         BvhResult out{};
-        build_bvh(in, out, st);
+        try { build_bvh(in, out, st); }
+        catch (...) { sc->releaseDevice(); sc->committed = false; sc->structureDirty = true; sc->data.nodes = nullptr; sc->data.tris = nullptr; sc->data.triShade = nullptr; sc->data.numNodes = sc->data.numTris = 0; throw; }
+        sc->releaseDevice();
         lap("bvh");
         sc->nodes = out.nodes; sc->tris = out.tris; sc->triShade = out.triShade; sc->buildMs = out.buildMs; sc->buildLaunches = out.launches; sc->rebuildCount++;
         sc->data.nodes = sc->nodes; sc->data.tris = sc->tris; sc->data.triShade = sc->triShade; sc->data.numNodes = out.numNodes; sc->data.numTris = out.numTris;
@@ -368,11 +370,15 @@ void scene_commit(yrt_device* dev, SceneHandle* sc) {
     sc->numRefs = (uint32_t)refs.size();
 
     lap("upload");
+    sc->committed = false;                                    // until the new structure exists (the arrays above were replaced already)
     sc->releaseDevice();
+    sc->data.nodes = nullptr; sc->data.tris = nullptr; sc->data.triShade = nullptr; sc->data.numNodes = sc->data.numTris = 0;
     BvhBuildInput in{dRefs.p, (uint32_t)refs.size(), sc->geoms.p, sc->positions.p, sc->indices.p, sc->normals.p, sc->uvs.p, dev->hostCounters + 8, dev->bvhPloc, dev->splitLeaves, dev->plocRadius};
     BvhResult out{};
+    sc->structureDirty = true;                                // a throw below leaves a scene that re-flattens on the next commit
     build_bvh(in, out, st);
     YRT_CK(cudaStreamSynchronize(st));
+    sc->structureDirty = false;
     lap("bvh");
     sc->nodes = out.nodes; sc->tris = out.tris; sc->triShade = out.triShade; sc->buildMs = out.buildMs; sc->buildLaunches = out.launches; sc->rebuildCount++;
 

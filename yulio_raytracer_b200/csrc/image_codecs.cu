@@ -93,11 +93,15 @@ static bool read_file(const char* file, std::vector<unsigned char>& out) {
 // interleaved RGB (top-down) -> RGBA8, rows flipped; the byte passes through Color4 and back exactly as in jpeg.cpp:55-62
 // (b * (1/255) then clamp * 255 truncated: the identity for every byte, checked in tests)
 __global__ void k_rgb_to_rgba_flip(const unsigned char* __restrict__ rgb, int pitch, int w, int h, uchar4* __restrict__ out) {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
     if (x >= w) return;
-    const unsigned char* p = rgb + (size_t)y * pitch + 3 * x;
-    out[(size_t)(h - 1 - y) * w + x] = make_uchar4(p[0], p[1], p[2], 255);
+    for (int y = blockIdx.y; y < h; y += gridDim.y) {                // grid.y is capped at 65535: taller images take several rows per block
+        const unsigned char* p = rgb + (size_t)y * pitch + 3 * x;
+        out[(size_t)(h - 1 - y) * w + x] = make_uchar4(p[0], p[1], p[2], 255);
+    }
 }
+static unsigned rows_grid(size_t h) { return (unsigned)(h < 1 ? 1 : (h > 65535 ? 65535 : h)); }
+struct DevFree { void operator()(void* p) const { if (p) cudaFree(p); } };      // device scratch released on every exit path
 
 std::shared_ptr<ImageObj> decode_jpeg_file(const char* file) {
     std::vector<unsigned char> data;
@@ -108,19 +112,21 @@ std::shared_ptr<ImageObj> decode_jpeg_file(const char* file) {
         NJ_CK(nj.GetImageInfo(nj.handle, data.data(), data.size(), &comps, &css, widths, heights));
         const int w = widths[0], h = heights[0];
         if (w <= 0 || h <= 0) throw std::runtime_error("improper dimensions");
+        unsigned char* rgbRaw = nullptr; YRT_CK(cudaMalloc((void**)&rgbRaw, (size_t)w * h * 3));
+        std::unique_ptr<unsigned char, DevFree> rgb(rgbRaw);
         nvjpegJpegState_t state; NJ_CK(nj.JpegStateCreate(nj.handle, &state));
-        unsigned char* rgb = nullptr; YRT_CK(cudaMalloc((void**)&rgb, (size_t)w * h * 3));
-        nvjpegImage_t dst; memset(&dst, 0, sizeof(dst)); dst.channel[0] = rgb; dst.pitch[0] = (size_t)w * 3;
+        nvjpegImage_t dst; memset(&dst, 0, sizeof(dst)); dst.channel[0] = rgb.get(); dst.pitch[0] = (size_t)w * 3;
         const nvjpegStatus_t s = nj.Decode(nj.handle, state, data.data(), data.size(), NVJPEG_OUTPUT_RGBI, &dst, nullptr);
         nj.JpegStateDestroy(state);
-        if (s != NVJPEG_STATUS_SUCCESS) { cudaFree(rgb); throw std::runtime_error("nvjpegDecode failed with status " + std::to_string((int)s)); }
+        if (s != NVJPEG_STATUS_SUCCESS) throw std::runtime_error("nvjpegDecode failed with status " + std::to_string((int)s));
+        YRT_CK(cudaStreamSynchronize(nullptr));                       // the decode ran on the legacy stream: surface its errors here
         auto img = std::make_shared<ImageObj>();
         img->width = w; img->height = h; img->format = TEX_RGBA8;
-        YRT_CK(cudaMalloc(&img->devPixels, (size_t)w * h * 4));
-        k_rgb_to_rgba_flip<<<dim3((w + 127) / 128, h), 128>>>(rgb, w * 3, w, h, (uchar4*)img->devPixels);
+        YRT_CK(cudaMalloc(&img->devPixels, (size_t)w * h * 4));       // owned (and released) by the ImageObj
+        k_rgb_to_rgba_flip<<<dim3((w + 127) / 128, rows_grid((size_t)h)), 128>>>(rgb.get(), w * 3, w, h, (uchar4*)img->devPixels);
+        YRT_CK(cudaGetLastError());
         img->storage.resize((size_t)w * h * 4);                       // host mirror: HDRI importance tables and backplates read texels on the host
         YRT_CK(cudaMemcpy(img->storage.data(), img->devPixels, img->storage.size(), cudaMemcpyDeviceToHost));
-        cudaFree(rgb);
         img->pixels = img->storage.data();
         return img;
     } catch (const std::exception& e) { printf("cannot read file %s: %s\n", file, e.what()); return nullptr; }
@@ -228,21 +234,23 @@ static int strip_segment(int cubeFaceIndex) {
 // reference loads it) centred on the face: blended = (1 - a) * ic + a * wc on Color4 lanes, stored as (uchar)(clamp(c) * 255)
 __global__ void k_strip_face(const unsigned char* __restrict__ fb, int fbStride, int w, int h, unsigned char* __restrict__ strip, int stripStride, int xOfs,
                              const uchar4* __restrict__ wm, int wmW, int wmH, int wmX0, int wmY0) {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
     if (x >= w) return;
-    const unsigned char* p = fb + (size_t)y * fbStride + 3 * x;
-    float c[3] = {(float)p[0], (float)p[1], (float)p[2]};
-    unsigned char o[3] = {p[0], p[1], p[2]};
-    if (wm) {
-        const int wx = x - wmX0, wy = y - wmY0;
-        if (wx >= 0 && wx < wmW && wy >= 0 && wy < wmH) {
-            const uchar4 t = wm[(size_t)wy * wmW + wx];
-            const float k = 1.f / 255.f, a = t.w * k, wc[3] = {t.x * k, t.y * k, t.z * k};
-            for (int i = 0; i < 3; i++) { const float b = (1.f - a) * (c[i] * k) + a * wc[i]; o[i] = (unsigned char)(rclamp(b) * 255.0f); }
+    for (int y = blockIdx.y; y < h; y += gridDim.y) {
+        const unsigned char* p = fb + (size_t)y * fbStride + 3 * x;
+        float c[3] = {(float)p[0], (float)p[1], (float)p[2]};
+        unsigned char o[3] = {p[0], p[1], p[2]};
+        if (wm) {
+            const int wx = x - wmX0, wy = y - wmY0;
+            if (wx >= 0 && wx < wmW && wy >= 0 && wy < wmH) {
+                const uchar4 t = wm[(size_t)wy * wmW + wx];
+                const float k = 1.f / 255.f, a = t.w * k, wc[3] = {t.x * k, t.y * k, t.z * k};
+                for (int i = 0; i < 3; i++) { const float b = (1.f - a) * (c[i] * k) + a * wc[i]; o[i] = (unsigned char)(rclamp(b) * 255.0f); }
+            }
         }
+        unsigned char* q = strip + (size_t)y * stripStride + 3 * (xOfs + x);
+        q[0] = o[0]; q[1] = o[1]; q[2] = o[2];
     }
-    unsigned char* q = strip + (size_t)y * stripStride + 3 * (xOfs + x);
-    q[0] = o[0]; q[1] = o[1]; q[2] = o[2];
 }
 
 void strip_begin(yrt_device* dev, size_t faceW, size_t faceH) {
@@ -269,39 +277,27 @@ void strip_set_watermark(yrt_device* dev, const char* pngFile) {
     YRT_CK(cudaMemcpy(s.wm, img->storage.data(), img->storage.size(), cudaMemcpyHostToDevice));
 }
 
+void strip_add_face_device(yrt_device* dev, const unsigned char* devRgb, size_t strideBytes, size_t w, size_t h, int cubeFaceIndex, int watermark);
 void strip_add_face(yrt_device* dev, FrameBufferHandle* fb, int cubeFaceIndex, int watermark) {
+    if (fb->format != 2) throw std::runtime_error("device_cuda: the strip takes RGB8 frames of the size given to yrtxStripBegin");
+    strip_add_face_device(dev, (const unsigned char*)fb->devPacked, fb->strideBytes, fb->width, fb->height, cubeFaceIndex, watermark);
+}
+// the same for any RGB8 frame resident on this device (a group device assembles its members' bands on member 0, group_api.cu)
+void strip_add_face_device(yrt_device* dev, const unsigned char* devRgb, size_t strideBytes, size_t w, size_t h, int cubeFaceIndex, int watermark) {
     CubeStrip& s = dev->strip;
     if (!s.dev) throw std::runtime_error("device_cuda: yrtxStripBegin was not called");
-    if (fb->format != 2 || fb->width != s.w || fb->height != s.h) throw std::runtime_error("device_cuda: the strip takes RGB8 frames of the size given to yrtxStripBegin");
+    if (w != s.w || h != s.h) throw std::runtime_error("device_cuda: the strip takes RGB8 frames of the size given to yrtxStripBegin");
+    struct { const void* devPacked; size_t strideBytes; } fbv{devRgb, strideBytes}; auto* fb = &fbv;
     const int seg = strip_segment(cubeFaceIndex);
     const bool wm = watermark && s.wm && (((cubeFaceIndex % 12) + 12) % 6) < 4;             // front, right, back, left only (renderer.cpp:637)
     // xDst = x + (W - w) * .5f truncated (renderer.cpp:642-643)
     const int x0 = (int)(0 + ((float)s.w - (float)s.wmW) * .5f), y0 = (int)(0 + ((float)s.h - (float)s.wmH) * .5f);
-    k_strip_face<<<dim3((unsigned)((s.w + 127) / 128), (unsigned)s.h), 128, 0, dev->stream>>>((const unsigned char*)fb->devPacked, (int)fb->strideBytes, (int)s.w, (int)s.h,
+    k_strip_face<<<dim3((unsigned)((s.w + 127) / 128), rows_grid(s.h)), 128, 0, dev->stream>>>((const unsigned char*)fb->devPacked, (int)fb->strideBytes, (int)s.w, (int)s.h,
                                                                                                 s.dev, (int)(12 * s.w * 3), seg * (int)s.w, wm ? s.wm : nullptr, s.wmW, s.wmH, x0, y0);
     YRT_CK(cudaGetLastError());
     s.facesAdded++;
 }
 
-// the same for a frame that is in host memory (a group device collects its members' bands on the host, group_api.cu)
-void strip_add_face_host(yrt_device* dev, const unsigned char* rgb, size_t strideBytes, size_t w, size_t h, int cubeFaceIndex, int watermark) {
-    CubeStrip& s = dev->strip;
-    if (!s.dev) throw std::runtime_error("device_cuda: yrtxStripBegin was not called");
-    if (w != s.w || h != s.h) throw std::runtime_error("device_cuda: the strip takes RGB8 frames of the size given to yrtxStripBegin");
-    unsigned char* tmp = nullptr;
-    const size_t frameBytes = strideBytes * h;
-    YRT_CK(cudaMallocAsync((void**)&tmp, frameBytes != 0 ? frameBytes : 1, dev->stream));
-    YRT_CK(cudaMemcpyAsync(tmp, rgb, strideBytes * h, cudaMemcpyHostToDevice, dev->stream));
-    const int seg = strip_segment(cubeFaceIndex);
-    const bool wm = watermark && s.wm && (((cubeFaceIndex % 12) + 12) % 6) < 4;
-    const int x0 = (int)(0 + ((float)s.w - (float)s.wmW) * .5f), y0 = (int)(0 + ((float)s.h - (float)s.wmH) * .5f);
-    k_strip_face<<<dim3((unsigned)((s.w + 127) / 128), (unsigned)s.h), 128, 0, dev->stream>>>(tmp, (int)strideBytes, (int)s.w, (int)s.h, s.dev, (int)(12 * s.w * 3),
-                                                                                                seg * (int)s.w, wm ? s.wm : nullptr, s.wmW, s.wmH, x0, y0);
-    YRT_CK(cudaGetLastError());
-    YRT_CK(cudaFreeAsync(tmp, dev->stream));
-    YRT_CK(cudaStreamSynchronize(dev->stream));                      // `rgb` belongs to the caller
-    s.facesAdded++;
-}
 
 void strip_read(yrt_device* dev, void* rgb) {
     CubeStrip& s = dev->strip;

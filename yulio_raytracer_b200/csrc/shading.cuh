@@ -34,8 +34,12 @@ YRT_D Col4 tex_get(const TextureRec& t, float px, float py) {
         const float u = s1 * t.width - .5f, v = t1 * t.height - .5f;
         const int x = iclamp(int(floorf(u)), 0, t.width - 2), y = iclamp(int(floorf(v)), 0, t.height - 2);
         const float ur = u - x, vr = v - y, uo = 1.f - ur, vo = 1.f - vr;
-        c = c4add(c4mul(c4add(c4mul(texel(t, x, y), uo), c4mul(texel(t, x + 1, y), ur)), vo),
-                  c4mul(c4add(c4mul(texel(t, x, y + 1), uo), c4mul(texel(t, x + 1, y + 1), ur)), vr));
+        // pin P5: a 1-pixel-wide / -tall image (the 1x1 white fallback of a missing texture, singleray_device.cpp:250, and the sample
+        // scene's own 1x1 JPEGs) makes the reference read texel x+1 / y+1 past the allocation; the neighbour index is clamped instead
+        // (the variant left commented out in Bilinear.h:36-37). Any image of 2 or more pixels per axis is unaffected.
+        const int x1 = x + 1 > t.width - 1 ? x : x + 1, y1 = y + 1 > t.height - 1 ? y : y + 1;
+        c = c4add(c4mul(c4add(c4mul(texel(t, x, y), uo), c4mul(texel(t, x1, y), ur)), vo),
+                  c4mul(c4add(c4mul(texel(t, x, y1), uo), c4mul(texel(t, x1, y1), ur)), vr));
     } else {
         const int si = (int)(s1 * float(t.width)), ti = (int)(t1 * float(t.height));
         c = texel(t, iclamp(si, 0, t.width - 1), iclamp(ti, 0, t.height - 1));
