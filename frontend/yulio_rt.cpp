@@ -44,6 +44,8 @@ struct StripHooks {
     int (*setWatermark)(void*, const char*) = nullptr;
     int (*addFace)(void*, void*, int, int) = nullptr;
     int (*encode)(void*, int, int, const char*) = nullptr;
+    // yrtxRenderCubeMap: the 12 cameras of a viewpoint as one render call (include/yrt_device.h)
+    int (*renderCubeMap)(void*, void*, void* const*, size_t, void*, void*, void* const*, int) = nullptr;
     const char* (*lastError)() = nullptr;
     bool ok() const { return native && begin && addFace && encode; }
 };
@@ -80,6 +82,7 @@ Device* Device::rtCreateDevice(const char* type, size_t numThreads, int threadsP
         g_hooks.setWatermark = (int (*)(void*, const char*))dlsym(lib, "yrtxStripSetWatermark");
         g_hooks.addFace = (int (*)(void*, void*, int, int))dlsym(lib, "yrtxStripAddFace");
         g_hooks.encode = (int (*)(void*, int, int, const char*))dlsym(lib, "yrtxStripEncodeJPEG");
+        g_hooks.renderCubeMap = (int (*)(void*, void*, void* const*, size_t, void*, void*, void* const*, int))dlsym(lib, "yrtxRenderCubeMap");
         g_hooks.lastError = (const char* (*)())dlsym(lib, "yrtGetLastError");
     }
     return dev;
@@ -106,7 +109,8 @@ static StatusTracker g_status;
 static std::atomic<bool> g_running{false}, g_stop{false}, g_keep{false};
 static std::thread g_worker;
 
-static void rendererStatus(const RendererStatus& s) { g_status.stageProgress(s.progress); }   // rsc, renderer.cpp:231-233
+static std::atomic<int> g_stageSpan{1};            // stages (cube faces) covered by the render call in flight
+static void rendererStatus(const RendererStatus& s) { g_status.stageProgress(s.progress * float(g_stageSpan.load())); }   // rsc, renderer.cpp:231-233
 
 struct Session {                                   // the g_* globals of renderer.cpp:243-300, per StartRT call
     Device* device = nullptr;
@@ -150,6 +154,48 @@ static void renderCubeMaps(Session& S) {
             if (g_hooks.setWatermark(g_hooks.native, file.c_str()) != 0) printf("yulio_rt: no watermark (%s)\n", g_hooks.lastError ? g_hooks.lastError() : file.c_str());
         }
     } else if (S.p.waterMark) printf("yulio_rt: the watermark is applied by device_cuda's strip path only\n");
+    // device_cuda: the 12 stereo cube cameras of a viewpoint share their origin (ColladaLoader.cpp:470-505), so the camera-aligned
+    // primitives turn once per viewpoint and all 12 faces are rendered by ONE call, yrtxRenderCubeMap, as one wavefront; the frames go
+    // from their frame buffers into the strip on the device. YULIO_RT_PER_FACE=1 keeps the reference's literal per-face loop below.
+    const bool batched = gpuStrip && g_hooks.renderCubeMap && S.cameras.size() % 12 == 0 && !getenv("YULIO_RT_PER_FACE");
+    if (batched) {
+        std::vector<Handle<Device::RTFrameBuffer>> fbs;
+        fbs.push_back(S.frameBuffer);
+        for (int f = 1; f < 12; f++) fbs.push_back(dev->rtNewFrameBuffer("RGB8", W, H, 1));
+        auto hook = [&](int rc) { if (rc != 0) throw std::runtime_error(g_hooks.lastError ? g_hooks.lastError() : "device_cuda hook failed"); };
+        for (size_t v = 0; v + 12 <= S.cameras.size() && !g_stop; v += 12) {
+            g_status.setStage((int)v); g_stageSpan = 12;
+            Vector3f camPos;
+            dev->rtGetFloat3(S.cameras[v], "origin", camPos.x, camPos.y, camPos.z);
+            for (size_t j = 0; j < S.prims.size(); ++j) dev->rtUpdatePrimitive(scene, j, S.prims[j], camPos, camUp);
+            dev->rtCommit(scene);
+            void* cams[12]; void* bufs[12];
+            for (int f = 0; f < 12; f++) {
+                if (S.p.toeIn) { dev->rtSetBool1(S.cameras[v + f], "toeIn", true); dev->rtCommit(S.cameras[v + f]); }
+                cams[f] = (void*)(Device::RTCamera)S.cameras[v + f]; bufs[f] = (void*)(Device::RTFrameBuffer)fbs[f];
+            }
+            hook(g_hooks.renderCubeMap(g_hooks.native, (void*)(Device::RTRenderer)S.renderer, cams, 12, (void*)(Device::RTScene)scene,
+                                       (void*)(Device::RTToneMapper)S.tonemapper, bufs, 0));
+            g_stageSpan = 1;
+            if (g_stop) { if (!g_keep) for (const auto& f : saved) remove(f.c_str()); break; }
+            std::string cameraName;
+            dev->rtGetString(S.cameras[v], "name", cameraName);
+            hook(g_hooks.begin(g_hooks.native, W, H));
+            for (int f = 0; f < 12; f++) {
+                dev->rtSwapBuffers(fbs[f]);
+                hook(g_hooks.addFace(g_hooks.native, bufs[f], f, S.p.waterMark ? 1 : 0));
+                if (S.p.debug) {
+                    const std::string file = base + cameraName + "_" + faceNames[f % 6] + (f < 6 ? "left" : "right") + ".jpg";
+                    hook(g_hooks.encode(g_hooks.native, f, S.p.jpegQuality, file.c_str())); saved.push_back(file);
+                }
+            }
+            const std::string file = base + cameraName + ".jpg";
+            hook(g_hooks.encode(g_hooks.native, -1, S.p.jpegQuality, file.c_str())); saved.push_back(file);
+            printf("Generated stereoscopic cube map #%zu in file %s\n", v / 12 + 1, file.c_str());
+        }
+        g_status.setState(g_stop ? Stopped : Done);
+        return;
+    }
     for (size_t i = 0; i < S.cameras.size() && !g_stop; ++i) {
         g_status.setStage((int)i);
         const Handle<Device::RTCamera>& cam = S.cameras[i];

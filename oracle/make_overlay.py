@@ -30,6 +30,8 @@ dependent; DESIGN.md "Parity contract" lists them):
      1/sqrt(x) the reference itself uses in its non-SSE branch (math.h:65,69) [SURVEY F5]
   P4 renderers/integratorrenderer.cpp: ray counter + timing exported through
      a C hook so bench.py can read Mrays/s without scraping stdout (no behaviour change).
+  P6 renderers/debugrenderer.cpp:116: `cosineSampleHemisphere(rand.getFloat(), rand.getFloat(), Nf)` leaves the order of the two draws
+     to the compiler (unspecified in C++; gcc and MSVC differ in practice): pinned to u first, then v.
   P5 textures/Bilinear.h:31-34: texels x+1 / y+1 are read past the allocation for a 1-pixel-wide / -tall image (the 1x1
      white fallback of a missing texture, and the sample scene's own 1x1 JPEGs): the neighbour index is clamped, which is
      the variant the reference left commented out two lines below (Bilinear.h:36-37). Images >= 2 px per axis are unaffected.
@@ -134,6 +136,12 @@ def main():
     patch("devices/device_singleray/integrators/pathtraceintegrator.cpp",
           '#include "integrators/pathtraceintegrator.h"',
           '#include "integrators/pathtraceintegrator.h"\n#include "yrt_oracle_pins.h"')
+
+    # ---- P6 debug renderer: order of the two random numbers of a diffuse bounce ------------------
+    patch("devices/device_singleray/renderers/debugrenderer.cpp",
+          "new (&ray) Ray(ray.org+0.999f*ray.tfar*ray.dir,cosineSampleHemisphere(rand.getFloat(),rand.getFloat(),Nf),4.0f*float(ulp)/**hit.error*/);",
+          "const float yrt_u = rand.getFloat(); const float yrt_v = rand.getFloat(); /* PIN P6 */\n"
+          "\t\t  new (&ray) Ray(ray.org+0.999f*ray.tfar*ray.dir,cosineSampleHemisphere(yrt_u,yrt_v,Nf),4.0f*float(ulp)/**hit.error*/);")
 
     # ---- P4 ray counter / timing hook ------------------------------------------
     patch("devices/device_singleray/renderers/integratorrenderer.cpp",

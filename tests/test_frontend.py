@@ -162,3 +162,21 @@ def test_cube_map_cuda_matches_reference_backend(tmp_path):
     assert j.shape == a.shape
     from tests.test_formats import _libjpeg_psnr, _psnr
     assert _psnr(j, a) >= _libjpeg_psnr(a, 90, str(tmp_path / "ref.jpg")) - 1.5     # jpegQuality 90, 4:2:0: as good as libjpeg on this image
+
+
+@pytest.mark.gpu
+def test_cube_map_call_equals_the_per_face_loop(tmp_path):
+    """The front end renders a viewpoint with ONE yrtxRenderCubeMap call on device_cuda; YULIO_RT_PER_FACE=1 keeps the reference's literal
+    loop (12 x update / commit / rtRenderFrame). Same frames -> byte-identical JPEG strips, incl. a scene with a camera-aligned billboard
+    and two viewpoints."""
+    need_frontend()
+    d1, d2 = tmp_path / "batched", tmp_path / "perface"
+    views = (("A", (0, 60, 0)), ("B", (-90, 70, 40)))
+    dae1 = dae_scene.write_scene(str(d1), "room", views=views)
+    dae2 = dae_scene.write_scene(str(d2), "room", views=views)
+    r1 = run_rt_test(dae1, 48, 8, 6)
+    r2 = run_rt_test(dae2, 48, 8, 6, extra_env={"YULIO_RT_PER_FACE": "1"})
+    assert r1.returncode == 0 and r2.returncode == 0, r1.stdout + r1.stderr + r2.stdout + r2.stderr
+    for v in "AB":
+        a, b = open(str(d1 / f"room_{v}.jpg"), "rb").read(), open(str(d2 / f"room_{v}.jpg"), "rb").read()
+        assert len(a) > 1000 and a == b, f"viewpoint {v}: strips differ"

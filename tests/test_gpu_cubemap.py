@@ -71,3 +71,25 @@ def test_cube_map_debug_renderer_and_rgb8(cuda_dev):
         d.render_cube_map(r, cams, s.scene, s.tonemapper, fbs)
         for k, fb in enumerate(fbs):
             assert np.array_equal(d.read_framebuffer(fb, "RGB8", 24, 24), ref[k])
+
+
+def test_two_chunk_lanes_render_the_same_frame():
+    """A call of >= 2^22 paths is cut into chunks that run on two streams with their own wavefront state (cfg lanes, default 2):
+    bit-identical to one lane, whatever the chunk size."""
+    from yulio_raytracer_b200 import Device
+    ref = None
+    for cfg in ("lanes=1", "lanes=2", "lanes=2,chunk=700000"):
+        d = Device.cuda(cfg=cfg)
+        s = scenes.atrium(d, 192, 160, 256, 6, face=5, detail=4, tex_size=32)          # 7.9 M paths
+        cams = scenes.cube_cameras(d, s, faces=[5, 10])
+        fbs = [d.rtNewFrameBuffer("RGB_FLOAT32", 192, 160, 1) for _ in cams]
+        scenes.render_cube_map_batched(d, s, cams, fbs)
+        st = d.frame_stats()
+        imgs = [d.read_framebuffer(fb, "RGB_FLOAT32", 192, 160) for fb in fbs]
+        if ref is None:
+            ref = (imgs, st.rays_closest, st.rays_shadow)
+        else:
+            assert (st.rays_closest, st.rays_shadow) == ref[1:], cfg
+            for a, b in zip(imgs, ref[0]):
+                assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), cfg
+        d.close()

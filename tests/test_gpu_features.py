@@ -140,3 +140,54 @@ def test_one_pixel_textures(cuda_dev, oracle_dev):
     a = _both(cuda_dev, oracle_dev, build)[0]
     b = _both(cuda_dev, oracle_dev, build)[0]
     assert np.array_equal(a, b), "frames with 1-pixel textures must be reproducible"
+
+
+@pytest.mark.parametrize("depth,spp", [(2, 1), (4, 2)])
+def test_debug_renderer_with_diffuse_bounces(cuda_dev, oracle_dev, depth, spp):
+    """renderers/debugrenderer.cpp:104-121 with maxDepth > 1: per-tile Random(tile * 1024) drawn in pixel / sample / bounce order (pin P6:
+    u before v). The ID colour of the last hit must match the oracle's; a last-bit difference of sinf / cosf can move a bounce ray across
+    a triangle edge, so up to 1 % of the pixels may show a neighbouring primitive."""
+    imgs = []
+    for d in (cuda_dev, oracle_dev):
+        s = scenes.cornell(d, 64, 48, 1, 1, fmt="RGB8")
+        r = d.rtNewRenderer("debug"); d.rtSetInt1(r, "maxDepth", depth); d.rtSetInt1(r, "sampler.spp", spp); d.rtCommit(r)
+        d.rtRenderFrame(r, s.camera, s.scene, s.tonemapper, s.framebuffer, 0)
+        imgs.append(d.read_framebuffer(s.framebuffer, "RGB8", 64, 48))
+    differ = (imgs[0] != imgs[1]).any(axis=-1).mean()
+    assert differ <= 0.01, f"{differ:.2%} of the pixels differ"
+    assert len(np.unique(imgs[1].reshape(-1, 3), axis=0)) > 5
+
+
+def test_tangent_arrays_and_bump_map(cuda_dev, oracle_dev):
+    """Per-vertex tangent_x / tangent_y arrays (trianglemesh_full.cpp:252-270, read by BrushedMetal's anisotropic lobe) and the Obj
+    material's map_Bump (materials/obj.h:52-56: Ns = normalize(b.x Tx + b.y Ty + b.z Ns))."""
+    rng = np.random.default_rng(11)
+    bump = np.clip(rng.normal(128, 40, (16, 16, 3)), 0, 255).astype(np.uint8); bump[..., 2] = 230
+
+    def build(d):
+        prims = []
+        # a tilted quad carrying tangent arrays, brushed metal
+        p, n, u, t = scenes.grid_quad((150, 20, 350), (260, 0, -60), (0, 240, 40), 3, 3)
+        mesh = d.rtNewShape("trianglemesh")
+        keep = []
+        for key, ty, arr, stride in (("positions", "float3", p, 12), ("normals", "float3", n, 12), ("texcoords", "float2", u, 8), ("indices", "int3", t, 12),
+                                     ("tangent_x", "float3", np.tile(np.array([[1.0, 0.2, 0.1]], np.float32), (len(p), 1)) * (1 + p[:, :1] / 500), 12),
+                                     ("tangent_y", "float3", np.tile(np.array([[-0.1, 1.0, 0.3]], np.float32), (len(p), 1)), 12)):
+            a = np.ascontiguousarray(arr, np.int32 if ty == "int3" else np.float32)
+            h = d.rtNewData("immutable", a); keep.append(h)
+            d.rtSetArray(mesh, key, ty, h, len(a), stride, 0)
+        d.rtCommit(mesh)
+        for h in keep:
+            d.rtDecRef(h)
+        prims.append(d.rtNewShapePrimitive(mesh, scenes.material(d, "BrushedMetal", reflectance=(.8, .8, .9), eta=(1.4, 1.2, 1.1), k=(5.0, 4.6, 4.2), roughnessX=.02, roughnessY=.3), None))
+        # a bump-mapped Obj floor patch
+        tex, _ = scenes.texture(d, bump)
+        m = d.rtNewMaterial("obj")
+        d.rtSetFloat3(m, "Kd", .7, .7, .6); d.rtSetFloat3(m, "Ks", .3, .3, .3); d.rtSetFloat1(m, "Ns", 20.0); d.rtSetTexture(m, "map_Bump", tex)
+        d.rtCommit(m)
+        p2, n2, u2, t2 = scenes.grid_quad((60, 1, 400), (430, 0, 0), (0, 0, -380), 2, 2, (3, 3))
+        prims.append(d.rtNewShapePrimitive(scenes.add_mesh(d, p2, t2, normals=n2, uvs=u2), m, None))
+        prims += scenes.cornell_prims(d) + scenes.quad_light(d, (213, 548.77, 227), (130, 0, 0), (0, 0, 105), (50, 50, 50)) + [scenes.ambient_light(d, (.2, .25, .3))]
+        cam = scenes.pinhole(d, (278, 273, -800), (278, 273, 0), (0, 1, 0), 37.0, W / H)
+        return scenes._bundle(d, prims, cam, scenes.pathtracer(d, 16, 4), W, H)
+    _both(cuda_dev, oracle_dev, build, mean_tol=4e-4)

@@ -169,6 +169,7 @@ struct GeomRec {                 // one per geomID (= one committed shape primit
     uint32_t nrmBase, uvBase;    // into normals / uvs, YRT_NO_ATTR when the mesh has none
     V3 triNg;                    // MESH_TRIANGLE: normalize(cross(v2-v0, v1-v0))  (shapes/triangle.h:43)
     int shadeClass;              // 1..14: hits whose shading follows the same code path (material kind, textured or not, lobe set)
+    uint32_t tanXBase, tanYBase; // into SceneData::tangents (per-vertex tangent_x / tangent_y arrays), YRT_NO_ATTR when the mesh has none
 };
 
 enum MaterialType { MAT_NONE = 0, MAT_MATTE, MAT_OBJ, MAT_UBER, MAT_MATTE_TEXTURED, MAT_DIELECTRIC, MAT_THIN_DIELECTRIC, MAT_MIRROR,
@@ -211,6 +212,7 @@ struct SceneData {
     // shading data
     const GeomRec* geoms;
     const float4* positions; const float4* normals; const float2* uvs; const int4* indices;
+    const float4* tangents;      // per-vertex tangent arrays of the meshes that carry them (GeomRec::tanXBase / tanYBase)
     const MaterialRec* materials; const TextureRec* textures; const LightRec* lights;
     int numGeoms, numLights, numEnvLights, numPrecomputed;
     int envLightIdx[8];

@@ -60,12 +60,12 @@ struct SceneHandle : Handle {
     // Incremental commit (the per-cube-face billboard update, renderer.cpp:551-559, only moves vertices): a slot whose new
     // primitive has the signature of the committed one is patched in place; anything else re-flattens the scene.
     struct SlotLayout { const void* material = nullptr; int type = -1, geomID = -1, illumMask = 0, shadowMask = 0; bool hasLight = false, cull = false, allFinite = false;
-                        size_t nv = 0, nn = 0, nuv = 0, nt = 0; uint32_t vtxBase = 0, nrmBase = 0, uvBase = 0, idxBase = 0; };
+                        size_t nv = 0, nn = 0, nuv = 0, nt = 0; bool hasTangents = false; uint32_t vtxBase = 0, nrmBase = 0, uvBase = 0, idxBase = 0; };
     std::vector<SlotLayout> layout; std::vector<size_t> patchSlots; bool structureDirty = true; uint32_t numRefs = 0;
     std::vector<float4> hostPositions, hostNormals; std::vector<float2> hostUvs; std::vector<int4> hostIndices;
     // ---- committed (device) state
     SceneData data{};                          // pointers below
-    DevBuf<GeomRec> geoms; DevBuf<float4> positions, normals; DevBuf<float2> uvs; DevBuf<int4> indices;
+    DevBuf<GeomRec> geoms; DevBuf<float4> positions, normals, tangents; DevBuf<float2> uvs; DevBuf<int4> indices;
     DevBuf<MaterialRec> materials; DevBuf<TextureRec> textures; DevBuf<LightRec> lights; DevBuf<uint2> refsBuf;
     void* nodes = nullptr; float4* tris = nullptr; float4* triShade = nullptr;
     std::vector<std::shared_ptr<ImageObj>> imagesInUse;   // keeps device pixel storage alive
@@ -135,7 +135,11 @@ struct yrt_device {
     int sortRays = 0; uint32_t sortMin = 1u << 16;   // cfg sort=0|1: re-order bounce queues of at least sortMin rays (sort.cu); measured slower, off
     uint32_t* hostCounters = nullptr;          // pinned: queue lengths read back once per bounce   // cfg refill=,trinum=,triden= (bvh.cuh: TraceTune)
     bool readback = true;                      // copy the frame to the host buffer inside yrtRenderFrame (yrtxSetReadback)
-    yrt::WavefrontStorage wf;
+    // Two chunk lanes: consecutive chunks of a render call run on two streams with their own wavefront state, each kernel launched with
+    // half the CTAs, so that a latency-bound shading kernel of one chunk shares the SMs with an issue-bound traversal kernel of the other
+    // (ncu r2: k_shade issues 44 % of the time, the traversal kernels 77 %) and launch tails overlap. cfg lanes=1 restores one stream.
+    int lanes = 2; cudaStream_t stream1 = nullptr;
+    yrt::WavefrontStorage wf, wf1;
     yrt::FrameTimers timers;
     yrt::DevBuf<float> sampleTable; yrt::TableKey tableKey; int tableSpp = 1, tableN1 = 0, tableN2 = 0, tableRec = 0;
     yrt::PixelFilter filters[3]; bool filterReady[3] = {false, false, false};

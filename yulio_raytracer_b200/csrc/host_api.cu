@@ -125,7 +125,7 @@ static std::shared_ptr<ShapeObj> make_shape(const std::string& type, const Parms
     auto s = std::make_shared<ShapeObj>();
     if (type == "trianglemesh") {                               // shapes/trianglemesh.h:29-41, trianglemesh_full.cpp:21-66
         bool hasP, hasM, hasN, hasTx, hasTy;
-        std::vector<V3> motion, tx, ty;
+        std::vector<V3> motion; std::vector<V3>& tx = s->tangentX; std::vector<V3>& ty = s->tangentY;
         read_v3_array(p, "positions", "wrong position format", s->position, hasP);
         read_v3_array(p, "motions", "wrong motion vector format", motion, hasM);
         read_v3_array(p, "normals", "wrong normal format", s->normal, hasN);
@@ -155,6 +155,8 @@ static std::shared_ptr<ShapeObj> make_shape(const std::string& type, const Parms
         }
         if (!s->normal.empty() && s->normal.size() < s->position.size()) s->normal.resize(s->position.size(), V3(0.f));
         if (!s->texcoord.empty() && s->texcoord.size() < s->position.size()) s->texcoord.resize(s->position.size(), make_float2(0.f, 0.f));
+        if (!tx.empty() && tx.size() < s->position.size()) tx.resize(s->position.size(), V3(0.f));
+        if (!ty.empty() && ty.size() < s->position.size()) ty.resize(s->position.size(), V3(0.f));
         return s;
     }
     if (type == "triangle") {                                   // shapes/triangle.h:33-38
@@ -269,7 +271,6 @@ static std::shared_ptr<MaterialObj> make_material(const std::string& type, const
         m->textures[2] = p.getTexture("map_Ks"); r.c1 = p.getV3("Ks", V3(0.f));
         m->textures[3] = p.getTexture("map_Ns"); r.f[1] = p.getFloat("Ns", 10.0f);
         m->textures[4] = p.getTexture("map_Bump");
-        if (m->textures[4]) throw std::runtime_error("device_cuda: Obj material with map_Bump is not supported");
     } else if (type == "plastic") {                                                                        // plastic.h:31-36
         r.type = MAT_PLASTIC; r.c0 = p.getV3("pigmentColor", V3(1.f)); r.f[0] = p.getFloat("eta", 1.4f); r.f[1] = p.getFloat("roughness", 0.01f); r.f[3] = rcpf(r.f[1]);
     } else if (type == "metal") {                                                                          // metal.h:35-41
@@ -440,6 +441,8 @@ yrt_device* yrtCreateDevice(const char* parms, size_t numThreads, int threadsPri
         dev->gpu = gpu; dev->numSMs = prop.multiProcessorCount;
         YRT_CK(cudaSetDevice(gpu));
         YRT_CK(cudaStreamCreateWithFlags(&dev->stream, cudaStreamNonBlocking));
+        YRT_CK(cudaStreamCreateWithFlags(&dev->stream1, cudaStreamNonBlocking));
+        dev->lanes = (int)cfg_int(cfg, "lanes", 2) >= 2 ? 2 : 1;
         {   // keep freed scratch in the stream-ordered pool instead of returning it to the OS at every synchronisation
             cudaMemPool_t pool; YRT_CK(cudaDeviceGetDefaultMemPool(&pool, gpu));
             uint64_t keep = ~0ull; YRT_CK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
@@ -468,10 +471,10 @@ yrt_device* yrtCreateDevice(const char* parms, size_t numThreads, int threadsPri
 void yrtDestroyDevice(yrt_device* dev) {
     if (!dev) return;
     cudaSetDevice(dev->gpu);
-    cudaStreamSynchronize(dev->stream);
-    dev->wf.release(); dev->timers.release(); dev->sampleTable.release(); strip_release(dev);
+    cudaStreamSynchronize(dev->stream); cudaStreamSynchronize(dev->stream1);
+    dev->wf.release(); dev->wf1.release(); dev->timers.release(); dev->sampleTable.release(); strip_release(dev);
     if (dev->hostCounters) cudaFreeHost(dev->hostCounters);
-    cudaStreamDestroy(dev->stream);
+    cudaStreamDestroy(dev->stream); cudaStreamDestroy(dev->stream1);
     delete dev;
 }
 
@@ -750,6 +753,16 @@ yrt_status yrtxFrameBufferDevice(yrt_device* dev, yrt_handle fb, void** devPtr, 
             if (devPtr) *devPtr = f->devPacked; if (bytes) *bytes = f->bytes(); if (strideBytes) *strideBytes = f->strideBytes)
 }
 yrt_status yrtxSetReadback(yrt_device* dev, int readbackEachFrame) { GUARD_S(dev->readback = readbackEachFrame != 0) }
+yrt_status yrtxSetOption(yrt_device* dev, const char* key, long value) {
+    GUARD_S(const std::string k(key ? key : "");
+            if (k == "lanes") dev->lanes = value >= 2 ? 2 : 1;
+            else if (k == "tracectas") dev->traceCtas = (int)std::max(1l, std::min(16l, value));
+            else if (k == "shadectas") dev->shadeCtas = (int)std::max(1l, std::min(16l, value));
+            else if (k == "syncmin") dev->syncMinPaths = (uint32_t)std::max(0l, value);
+            else if (k == "timers") dev->useTimers = value != 0;
+            else if (k == "verbose") dev->verbose = (int)value;
+            else throw std::runtime_error("device_cuda: unknown option " + k))
+}
 yrt_status yrtxMicrobench(yrt_device* dev, int kind, size_t bytes, double* result) { GUARD_S(const double v = yrt::microbench(dev, kind, bytes); if (result) *result = v) }
 yrt_status yrtxRenderCubeMap(yrt_device* dev, yrt_handle renderer, const yrt_handle* cameras, size_t numFaces, yrt_handle scene, yrt_handle tonemapper,
                              const yrt_handle* frameBuffers, int accumulate) {

@@ -123,6 +123,9 @@ static std::shared_ptr<ShapeObj> transform_shape(const std::shared_ptr<ShapeObj>
         const Lin3 it = lin3_inverse_transposed(xfm.l);
         for (size_t i = 0; i < s->normal.size(); i++) t->normal[i] = xfmVector(it, s->normal[i]);
     }
+    t->tangentX.resize(s->tangentX.size()); t->tangentY.resize(s->tangentY.size());          // xfmVector (trianglemesh_full.cpp:84-87)
+    for (size_t i = 0; i < s->tangentX.size(); i++) t->tangentX[i] = xfmVector(xfm, s->tangentX[i]);
+    for (size_t i = 0; i < s->tangentY.size(); i++) t->tangentY[i] = xfmVector(xfm, s->tangentY[i]);
     return t;
 }
 
@@ -182,6 +185,7 @@ static bool slot_matches(const SceneHandle::SlotLayout& L, const ScenePrim& p) {
     if (!p.shape || p.light || L.hasLight || L.geomID < 0 || !L.allFinite) return false;
     const ShapeObj& s = *p.shape;
     if (s.type != L.type || s.type == MESH_TRIANGLE || p.material.get() != L.material || s.cullBackFaces != L.cull) return false;
+    if (L.hasTangents || !s.tangentX.empty() || !s.tangentY.empty()) return false;          // tangent arrays are re-flattened, not patched
     if (p.illumMask != L.illumMask || p.shadowMask != L.shadowMask) return false;
     if (s.position.size() != L.nv || s.normal.size() != L.nn || s.texcoord.size() != L.nuv || s.triangles.size() != L.nt) return false;
     for (const V3& q : s.position) if (!(std::isfinite(q.x) && std::isfinite(q.y) && std::isfinite(q.z))) return false;
@@ -257,7 +261,7 @@ void scene_commit(yrt_device* dev, SceneHandle* sc) {
     std::vector<float2>& uvs = sc->hostUvs; std::vector<int4>& indices = sc->hostIndices;
     positions.clear(); normals.clear(); uvs.clear(); indices.clear();
     sc->layout.assign(sc->prims.size(), SceneHandle::SlotLayout());
-    std::vector<uint2> refs; std::vector<MaterialRec> materials; std::vector<LightRec> lights;
+    std::vector<uint2> refs; std::vector<MaterialRec> materials; std::vector<LightRec> lights; std::vector<float4> tangents;
     std::map<const MaterialObj*, int> matIndex; std::map<const TextureObj*, int> texIndex;
     sc->hostTextures.clear(); sc->imagesInUse.clear(); sc->hdri.clear(); sc->geomOfSlot.assign(sc->prims.size(), -1);
 
@@ -333,7 +337,7 @@ void scene_commit(yrt_device* dev, SceneHandle* sc) {
         g.type = s.type; g.material = material_index(p->material); g.areaLight = lightIdx;
         g.cull = s.cullBackFaces ? 1 : 0; g.illumMask = p->illumMask; g.shadowMask = p->shadowMask;
         g.vtxBase = (uint32_t)positions.size(); g.idxBase = (uint32_t)indices.size();
-        g.nrmBase = YRT_NO_ATTR; g.uvBase = YRT_NO_ATTR; g.triNg = V3(0.f);
+        g.nrmBase = YRT_NO_ATTR; g.uvBase = YRT_NO_ATTR; g.tanXBase = YRT_NO_ATTR; g.tanYBase = YRT_NO_ATTR; g.triNg = V3(0.f);
         if (s.type == MESH_TRIANGLE) {
             g.triNg = s.triNg;
             const V3 v[3] = {s.v0, s.v1, s.v2};
@@ -346,6 +350,8 @@ void scene_commit(yrt_device* dev, SceneHandle* sc) {
             for (const V3& q : s.position) positions.push_back(make_float4(q.x, q.y, q.z, 0.f));
             if (!s.normal.empty()) { g.nrmBase = (uint32_t)normals.size(); for (const V3& q : s.normal) normals.push_back(make_float4(q.x, q.y, q.z, 0.f)); }
             if (!s.texcoord.empty()) { g.uvBase = (uint32_t)uvs.size(); for (const float2& q : s.texcoord) uvs.push_back(q); }
+            if (!s.tangentX.empty()) { g.tanXBase = (uint32_t)tangents.size(); for (const V3& q : s.tangentX) tangents.push_back(make_float4(q.x, q.y, q.z, 0.f)); }
+            if (!s.tangentY.empty()) { g.tanYBase = (uint32_t)tangents.size(); for (const V3& q : s.tangentY) tangents.push_back(make_float4(q.x, q.y, q.z, 0.f)); }
             for (size_t t = 0; t < s.triangles.size(); t++) {
                 const int4 tri = s.triangles[t];
                 indices.push_back(tri);
@@ -360,11 +366,12 @@ void scene_commit(yrt_device* dev, SceneHandle* sc) {
         L.hasLight = (bool)p->light; L.cull = s.cullBackFaces; L.vtxBase = g.vtxBase; L.nrmBase = g.nrmBase; L.uvBase = g.uvBase; L.idxBase = g.idxBase;
         if (s.type != MESH_TRIANGLE) { L.nv = s.position.size(); L.nn = s.normal.size(); L.nuv = s.texcoord.size(); L.nt = s.triangles.size(); }
         L.allFinite = s.type != MESH_TRIANGLE && refs.size() - refsBefore == s.triangles.size();
+        L.hasTangents = !s.tangentX.empty() || !s.tangentY.empty();
     }
 
     lap("flatten");
     sc->geoms.upload(geoms, st); sc->positions.upload(positions, st); sc->normals.upload(normals, st); sc->uvs.upload(uvs, st);
-    sc->indices.upload(indices, st); sc->materials.upload(materials, st); sc->lights.upload(lights, st);
+    sc->indices.upload(indices, st); sc->materials.upload(materials, st); sc->lights.upload(lights, st); sc->tangents.upload(tangents, st);
     sc->textures.upload(sc->hostTextures, st);
     DevBuf<uint2>& dRefs = sc->refsBuf; dRefs.upload(refs, st);      // kept across commits: no cudaMalloc/cudaFree per cube face
     sc->numRefs = (uint32_t)refs.size();
@@ -383,7 +390,7 @@ void scene_commit(yrt_device* dev, SceneHandle* sc) {
     sc->nodes = out.nodes; sc->tris = out.tris; sc->triShade = out.triShade; sc->buildMs = out.buildMs; sc->buildLaunches = out.launches; sc->rebuildCount++;
 
     d.nodes = sc->nodes; d.tris = sc->tris; d.triShade = sc->triShade; d.numNodes = out.numNodes; d.numTris = out.numTris;
-    d.geoms = sc->geoms.p; d.positions = sc->positions.p; d.normals = sc->normals.p; d.uvs = sc->uvs.p; d.indices = sc->indices.p;
+    d.geoms = sc->geoms.p; d.positions = sc->positions.p; d.normals = sc->normals.p; d.uvs = sc->uvs.p; d.indices = sc->indices.p; d.tangents = sc->tangents.p;
     d.materials = sc->materials.p; d.textures = sc->textures.p; d.lights = sc->lights.p;
     d.numGeoms = (int)geoms.size(); d.numLights = (int)lights.size();
     {   // shading classes for the CTA-local regrouping of k_shade: same material kind / textured-ness / lobe set -> same class
@@ -403,7 +410,8 @@ void scene_commit(yrt_device* dev, SceneHandle* sc) {
         }
     }
     d.hasMedia = 0; for (const MaterialRec& m : materials) d.hasMedia |= m.isMediaInterface;
-    d.hasExtMaterials = 0; for (const MaterialRec& m : materials) d.hasExtMaterials |= m.type >= MAT_PLASTIC ? 1 : 0;
+    // the EXT shading kernel also serves Obj materials with a bump map (they need the tangent frame, materials/obj.h:52-56)
+    d.hasExtMaterials = 0; for (const MaterialRec& m : materials) d.hasExtMaterials |= (m.type >= MAT_PLASTIC || (m.type == MAT_OBJ && m.tex[4] >= 0)) ? 1 : 0;
     sc->data = d;
     scene_bounds(sc);
     sc->committed = true; sc->dirty = false;
@@ -645,28 +653,40 @@ void render_frames(yrt_device* dev, RendererHandle* rh, size_t numFaces, CameraH
     uint64_t capacity = dev->chunkPaths;
     const uint64_t totalPaths = (uint64_t)numPixels * spp;
     if (capacity > totalPaths) capacity = totalPaths;
-    if (capacity > dev->wf.wb.capacity || capacity * nl > dev->wf.wb.shadowCapacity) {
-        // growing: 112 B of path state + 48 B per (path, light) shadow slot; stay within 40 % of what is free right now
-        size_t freeB = 0, totalB = 0; YRT_CK(cudaMemGetInfo(&freeB, &totalB));
-        const uint64_t have = (uint64_t)dev->wf.wb.capacity * 112ull + (uint64_t)dev->wf.wb.shadowCapacity * 48ull;   // already ours
-        const uint64_t budget = (uint64_t)(0.4 * (double)freeB) + have;
-        while (capacity * (112ull + 48ull * nl) > budget && capacity > 65536) capacity >>= 1;
+    // two lanes (device_impl.hpp): a call of at least 2^22 paths is cut into at least two chunks so that both streams have work
+    const int nLanes = (dev->lanes >= 2 && !R.debug && !dev->sortRays && totalPaths >= (1ull << 22)) ? 2 : 1;
+    if (nLanes == 2 && capacity > (totalPaths + 1) / 2) capacity = (totalPaths + 1) / 2;
+    WavefrontStorage* const W[2] = {&dev->wf, &dev->wf1};
+    const cudaStream_t LS[2] = {dev->stream, dev->stream1};
+    {
+        bool grow = false;
+        for (int l = 0; l < nLanes; l++) grow |= capacity > W[l]->wb.capacity || capacity * nl > W[l]->wb.shadowCapacity;
+        if (grow) {
+            // growing: 112 B of path state + 48 B per (path, light) shadow slot per lane; stay within 40 % of what is free right now
+            size_t freeB = 0, totalB = 0; YRT_CK(cudaMemGetInfo(&freeB, &totalB));
+            uint64_t have = 0;
+            for (int l = 0; l < nLanes; l++) have += (uint64_t)W[l]->wb.capacity * 112ull + (uint64_t)W[l]->wb.shadowCapacity * 48ull;   // already ours
+            const uint64_t budget = (uint64_t)(0.4 * (double)freeB) + have;
+            while (nLanes * capacity * (112ull + 48ull * nl) > budget && capacity > 65536) capacity >>= 1;
+        }
     }
     while (capacity * nl > 0xfff00000ull && capacity > 65536) capacity >>= 1;          // 32-bit shadow-slot indices
     if (capacity < (uint64_t)spp) capacity = spp;
-    const uint32_t pixelsPerChunk = (uint32_t)(capacity / spp);
+    const uint32_t pixelsPerChunk = (uint32_t)((capacity + spp - 1) / spp);
     capacity = (uint64_t)pixelsPerChunk * spp;
-    dev->wf.ensure((uint32_t)capacity, (uint32_t)(capacity * nl), facePixels);
-    const WavefrontBuffers& wb = dev->wf.wb;
+    for (int l = 0; l < nLanes; l++) W[l]->ensure((uint32_t)capacity, (uint32_t)(capacity * nl), facePixels);
 
     hostLap("setup");
-    LaunchCfg lcTrace{dev->numSMs * dev->traceCtas, 128, st}, lcStream{dev->numSMs * 8, 256, st}, lcShade{dev->numSMs * dev->shadeCtas, 128, st};
+    const int traceCtas = std::max(1, dev->traceCtas / nLanes), shadeCtas = std::max(1, dev->shadeCtas / nLanes), streamCtas = 8 / nLanes;
     FrameTimers& tm = dev->timers; tm.reset();
     const bool timers = dev->useTimers != 0;
     uint64_t launches = 0, closestLaunches = 0, shadowLaunches = 0, shadeLaunches = 0;
-    YRT_CK(cudaMemsetAsync(wb.stats, 0, 8 * sizeof(unsigned long long), st));
     cudaEvent_t evStart = tm.get(), evStop = tm.get();
     YRT_CK(cudaEventRecord(evStart, st));
+    for (int l = 0; l < nLanes; l++) {
+        if (l > 0) YRT_CK(cudaStreamWaitEvent(LS[l], evStart, 0));          // the timed span starts on the device's first stream
+        YRT_CK(cudaMemsetAsync(W[l]->wb.stats, 0, 8 * sizeof(unsigned long long), LS[l]));
+    }
 
     FilmParams fp; memset(&fp, 0, sizeof(fp)); fp.format = fb->format; fp.fbStrideBytes = (int)fb->strideBytes;
     for (size_t f = 0; f < numFaces; f++) { fp.face[f].accum = fbs[f]->accum; fp.face[f].fb = fbs[f]->devPacked; }
@@ -674,65 +694,74 @@ void render_frames(yrt_device* dev, RendererHandle* rh, size_t numFaces, CameraH
 
     bool stopped = false;
     if (R.debug) {
-        if (R.maxDepth > 1) throw std::runtime_error("device_cuda: the debug renderer supports maxDepth = 1 only");
-        launch_debug(fc, cams, wb, fp, (uint32_t)numPixels, lcStream); launches++;
+        launch_debug(fc, cams, W[0]->wb, fp, (uint32_t)numPixels, LaunchCfg{dev->numSMs * 8, 256, st}); launches++;
     } else if (numPixels) {
-        launch_pixel_sets(fc, wb.pixelSet, fs.sets, lcStream); launches++;
-        if (fc.integ.maxDepth <= 0) YRT_CK(cudaMemsetAsync(wb.Lacc, 0, (size_t)capacity * sizeof(float4), st));   // no bounce writes the radiance
+        for (int l = 0; l < nLanes; l++) {
+            launch_pixel_sets(fc, W[l]->wb.pixelSet, fs.sets, LaunchCfg{dev->numSMs * streamCtas, 256, LS[l]}); launches++;
+            if (fc.integ.maxDepth <= 0) YRT_CK(cudaMemsetAsync(W[l]->wb.Lacc, 0, (size_t)capacity * sizeof(float4), LS[l]));   // no bounce writes the radiance
+        }
         std::vector<cudaEvent_t> chunkDone;
         size_t chunkIdx = 0;
         for (size_t pixelBegin = 0; pixelBegin < numPixels; pixelBegin += pixelsPerChunk, chunkIdx++) {
-            // keep two chunks in flight so that stopFlag / statusCallback stay responsive (integratorrenderer.cpp:125,178)
-            if (chunkIdx >= 2) {
-                YRT_CK(cudaEventSynchronize(chunkDone[chunkIdx - 2]));
-                if (statusFn) { status.progress = float(pixelBegin - pixelsPerChunk) / float(numPixels); statusFn(&status); }
+            const int lane = (int)(chunkIdx % (size_t)nLanes);
+            const cudaStream_t ls = LS[lane];
+            const WavefrontBuffers& wb = W[lane]->wb;
+            const LaunchCfg lcTrace{dev->numSMs * traceCtas, 128, ls}, lcStream{dev->numSMs * streamCtas, 256, ls}, lcShade{dev->numSMs * shadeCtas, 128, ls};
+            // keep two chunks per lane in flight so that stopFlag / statusCallback stay responsive (integratorrenderer.cpp:125,178)
+            if (chunkIdx >= (size_t)(2 * nLanes)) {
+                YRT_CK(cudaEventSynchronize(chunkDone[chunkIdx - 2 * nLanes]));
+                if (statusFn) { status.progress = float(pixelBegin - (size_t)(2 * nLanes - 1) * pixelsPerChunk) / float(numPixels); statusFn(&status); }
             }
             if (stopRequested()) { stopped = true; break; }
             const uint32_t np = (uint32_t)std::min<size_t>(pixelsPerChunk, numPixels - pixelBegin);
-            if (timers) tm.begin(TK_RAYGEN_FILM, st);
+            if (timers) tm.begin(TK_RAYGEN_FILM, ls);
             launch_raygen(fc, cams, wb, (uint32_t)pixelBegin, np, lcStream); launches++;
-            if (timers) tm.end(st);
+            if (timers) tm.end(ls);
             int q = 0;
             uint32_t alive = np * (uint32_t)spp;                 // length of the current queue, known on the host
             for (int depth = 0; depth < fc.integ.maxDepth && alive; depth++, q ^= 1) {
                 // bounce queues are re-ordered by origin cell + direction octant (sort.cu); the sorted ids live in queueS
                 WavefrontBuffers wq = wb;
                 if (depth > 0 && dev->sortRays && alive >= dev->sortMin) {
-                    if (timers) tm.begin(TK_SORT, st);
+                    if (timers) tm.begin(TK_SORT, ls);
                     launch_sort_keys(fc, wb, q, alive, lcStream); launches++;
-                    sort_queue(wb, q, alive, dev->wf.sortTemp, dev->wf.sortTempBytes, st); launches += 4;
-                    if (timers) tm.end(st);
+                    sort_queue(wb, q, alive, W[lane]->sortTemp, W[lane]->sortTempBytes, ls); launches += 4;
+                    if (timers) tm.end(ls);
                     (q ? wq.queueB : wq.queueA) = wb.queueS;
                 }
-                if (timers) tm.begin(TK_CLOSEST, st);
+                if (timers) tm.begin(TK_CLOSEST, ls);
                 launch_trace_closest(fc, wq, q, lcTrace); launches++; closestLaunches++;
-                if (timers) { tm.end(st); tm.begin(TK_SHADE, st); }
+                if (timers) { tm.end(ls); tm.begin(TK_SHADE, ls); }
                 launch_shade(fc, wq, q, (uint32_t)pixelBegin, depth, lcShade); launches++; shadeLaunches++;
-                if (timers) tm.end(st);
+                if (timers) tm.end(ls);
                 // queue lengths of the next bounce: one small read-back per bounce buys the early exit and the sort size. Below
                 // syncMinPaths the round trip costs more than the (short, self-terminating) launches it could save: `alive` then
-                // stays an upper bound and the remaining bounces are enqueued without waiting.
-                const bool readCounters = alive >= dev->syncMinPaths || (dev->sortRays && alive >= dev->sortMin);
+                // stays an upper bound and the remaining bounces are enqueued without waiting. With two lanes the host never waits
+                // inside a chunk (it would stall the other lane's enqueue): every bounce is enqueued, empty ones end at once.
+                const bool readCounters = (nLanes == 1 && alive >= dev->syncMinPaths) || (dev->sortRays && alive >= dev->sortMin);
                 cudaEvent_t evCnt = nullptr;
                 if (readCounters) {
-                    YRT_CK(cudaMemcpyAsync(dev->hostCounters, wb.counters, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-                    evCnt = tm.get(); YRT_CK(cudaEventRecord(evCnt, st));
+                    YRT_CK(cudaMemcpyAsync(dev->hostCounters, wb.counters, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, ls));
+                    evCnt = tm.get(); YRT_CK(cudaEventRecord(evCnt, ls));
                 }
                 if (fc.scene.numLights > 0) {
-                    if (timers) tm.begin(TK_SHADOW, st);
+                    if (timers) tm.begin(TK_SHADOW, ls);
                     launch_trace_shadow(fc, wq, lcTrace); launches++; shadowLaunches++;
-                    if (timers) { tm.end(st); tm.begin(TK_RESOLVE, st); }
+                    if (timers) { tm.end(ls); tm.begin(TK_RESOLVE, ls); }
                 }
-                else if (timers) tm.begin(TK_RESOLVE, st);
+                else if (timers) tm.begin(TK_RESOLVE, ls);
                 launch_resolve(fc, wq, q, lcStream); launches += 2;
-                if (timers) tm.end(st);
+                if (timers) tm.end(ls);
                 if (readCounters) { YRT_CK(cudaEventSynchronize(evCnt)); alive = dev->hostCounters[q ^ 1]; }
             }
-            if (timers) tm.begin(TK_RAYGEN_FILM, st);
+            if (timers) tm.begin(TK_RAYGEN_FILM, ls);
             launch_film(fc, wb, fp, (uint32_t)pixelBegin, np, lcStream); launches++;
-            if (timers) tm.end(st);
-            cudaEvent_t e = tm.get(); YRT_CK(cudaEventRecord(e, st)); chunkDone.push_back(e);
+            if (timers) tm.end(ls);
+            cudaEvent_t e = tm.get(); YRT_CK(cudaEventRecord(e, ls)); chunkDone.push_back(e);
         }
+    }
+    for (int l = 1; l < nLanes; l++) {                          // the span ends when every lane is done
+        cudaEvent_t e = tm.get(); YRT_CK(cudaEventRecord(e, LS[l])); YRT_CK(cudaStreamWaitEvent(st, e, 0));
     }
     YRT_CK(cudaEventRecord(evStop, st));
     hostLap("enqueued");
@@ -744,10 +773,11 @@ void render_frames(yrt_device* dev, RendererHandle* rh, size_t numFaces, CameraH
             d2h += b->bytes(); b->pendingBuf = -1;
         } else b->pendingBuf = (int)b->cur;
     }
-    unsigned long long hstats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    YRT_CK(cudaMemcpyAsync(hstats, wb.stats, sizeof(hstats), cudaMemcpyDeviceToHost, st));
+    unsigned long long hstats[8] = {0, 0, 0, 0, 0, 0, 0, 0}, lstats[2][8];
+    for (int l = 0; l < nLanes; l++) YRT_CK(cudaMemcpyAsync(lstats[l], W[l]->wb.stats, sizeof(lstats[l]), cudaMemcpyDeviceToHost, st));   // after the lanes joined `st`
     YRT_CK(cudaStreamSynchronize(st));
     YRT_CK(cudaGetLastError());
+    for (int l = 0; l < nLanes; l++) for (int k = 0; k < 8; k++) { if (k == 7) hstats[k] |= lstats[l][k]; else hstats[k] += lstats[l][k]; }
     hostLap("synced");
 
     yrtx_frame_stats& S = dev->stats;

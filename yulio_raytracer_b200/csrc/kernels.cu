@@ -582,7 +582,65 @@ __global__ void __launch_bounds__(128) k_debug(FrameConst fc, const __grid_const
     }
     if (rays) atomicAdd(&wb.stats[0], rays);
 }
+// The same renderer with maxDepth > 1 (debugrenderer.cpp:104-121): after every hit but the last a diffuse bounce leaves the hit point,
+// ray = (org + 0.999 t dir, cosineSampleHemisphere(u, v, Nf), tnear 4 ulp), with u, v from ONE Random per 16x16 tile seeded tile * 1024 and
+// drawn in pixel / sample / bounce order — so a pixel's numbers depend on how many bounces the pixels before it in its tile took. One
+// thread walks one tile in that order (a debugging aid: correctness first). u is drawn before v (pin P6: the reference leaves the order
+// of its two getFloat() arguments to the compiler). The pixel shows the ID colour of the last hit, or white once a ray escapes.
+__global__ void __launch_bounds__(64) k_debug_bounces(FrameConst fc, const __grid_constant__ FrameCameras cams, const __grid_constant__ FilmParams fp, WavefrontBuffers wb) {
+    const SceneData& sc = fc.scene;
+    const int numTilesX = (fc.width + 15) / 16, numTilesY = (fc.height + 15) / 16;
+    const int job = blockIdx.x * blockDim.x + threadIdx.x;
+    if (job >= numTilesX * numTilesY * fc.numFaces) return;
+    const int face = job / (numTilesX * numTilesY), tile = job % (numTilesX * numTilesY);
+    const int x0 = (tile % numTilesX) * 16, y0 = (tile / numTilesX) * 16;
+    DevLcg rng; rng.init(tile * 1024);
+    unsigned long long rays = 0; bool overflow = false;
+    for (int dy = 0; dy < 16; dy++) {
+        const int y = y0 + dy;
+        if (y >= fc.height || (((y >> 2) - fc.serverID) % fc.serverCount) != 0) continue;
+        const int by = 4 * ((y >> 2) / fc.serverCount) + (y & 3);
+        const float fy = float(y) * fc.rcpHeight;
+        for (int dx = 0; dx < 16; dx++) {
+            const int x = x0 + dx;
+            if (x >= fc.width) continue;
+            const float fx = float(x) * fc.rcpWidth;
+            for (int i = 0; i < fc.integ.spp; i++) {
+                V3 org, dir; camera_ray(cams.cam[face], fx, fy, 0.5f, 0.5f, org, dir);
+                float tnear = 0.f; HitRec h; h.geomID = -1; h.primID = -1;
+                for (int depth = 0; depth < fc.integ.maxDepth; depth++) {
+                    TraceCounters cnt = {0, 0, 0};
+                    trace_ray<false, false>((const uint4*)sc.nodes, sc.tris, sc.numNodes, org, dir, tnear, INFINITY, h, &cnt); rays++;
+                    overflow |= cnt.overflow != 0;
+                    if (h.geomID < 0) break;
+                    if (depth + 1 < fc.integ.maxDepth) {
+                        V3 Nf = normalize(h.Ng);
+                        if (dot(-dir, Nf) < 0.f) Nf = -Nf;
+                        const float u = rmin(float(rng.next()) / 2147483647.0f, 1.0f - YRT_ULP), v = rmin(float(rng.next()) / 2147483647.0f, 1.0f - YRT_ULP);
+                        const V3 nd = cosine_sample_hemisphere(u, v, Nf).v;
+                        org = org + 0.999f * h.t * dir; dir = nd; tnear = 4.0f * YRT_ULP;
+                    }
+                }
+                Col c(1.f);
+                if (h.geomID >= 0) {
+                    const int id = h.geomID + h.primID;
+                    c = Col(float((3434553u * ((unsigned)(id + 3243))) % 255u) / 255.0f,
+                            float((7342453u * ((unsigned)(id + 8237))) % 255u) / 255.0f,
+                            float((9234454u * ((unsigned)(id + 2343))) % 255u) / 255.0f);
+                }
+                pack_pixel(fp, fp.face[face].fb, x, by, c);
+            }
+        }
+    }
+    if (rays) atomicAdd(&wb.stats[0], rays);
+    if (overflow) atomicOr(&wb.stats[7], 1ull);
+}
 void launch_debug(const FrameConst& fc, const FrameCameras& cams, const WavefrontBuffers& wb, const FilmParams& fp, uint32_t numPixels, LaunchCfg lc) {
+    if (fc.integ.maxDepth > 1) {
+        const int jobs = ((fc.width + 15) / 16) * ((fc.height + 15) / 16) * fc.numFaces;
+        k_debug_bounces<<<(jobs + 63) / 64, 64, 0, lc.stream>>>(fc, cams, fp, wb);
+        return;
+    }
     k_debug<<<lc.blocks, 128, 0, lc.stream>>>(fc, cams, fp, wb, numPixels);
 }
 

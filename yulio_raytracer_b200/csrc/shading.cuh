@@ -54,8 +54,9 @@ struct DG { V3 P, Ng, Ns; float s, t, error; int material, areaLight, illumMask,
 // TriangleMeshFull::postIntersect      shapes/trianglemesh_full.cpp:207-275
 // TriangleMeshWithNormals::postIntersect shapes/trianglemesh_normals.cpp:140-162
 // Triangle::postIntersect              shapes/triangle.h:84-93
-// Tx/Ty (trianglemesh_full.cpp:252-270, trianglemesh_normals.cpp:154-155) are produced by the EXT instantiation only: BrushedMetal is
-// the one material that reads them. Meshes with tangent arrays are not supported (the arrays are ignored).
+// Tx/Ty (trianglemesh_full.cpp:252-270, trianglemesh_normals.cpp:154-155) are produced by the EXT instantiation only: BrushedMetal and
+// a bump-mapped Obj are the materials that read them. Per-vertex tangent arrays ("tangent_x" / "tangent_y") are interpolated unnormalised
+// like the reference does (:253-256, :263-266); without them the tangents come from the positions and texture coordinates.
 template <bool EXT>
 YRT_D void post_intersect(const SceneData& sc, V3 org, V3 dir, float t, float u, float v, int triIdx, DG& dg) {
     // one 80-byte record per leaf-order triangle (bvh_build.cu: write_triangle) replaces geometry record -> indices -> 3 vertices
@@ -85,10 +86,22 @@ YRT_D void post_intersect(const SceneData& sc, V3 org, V3 dir, float t, float u,
         else {
             float dsdu = 1.f, dtdu = 0.f, dsdv = 0.f, dtdv = 1.f;
             if (flags & 2u) { dsdu = r3.w - r1.w; dtdu = r4.x - r2.w; dsdv = r4.y - r1.w; dtdv = r4.z - r2.w; }
-            const V3 dPds = normalize(dPdu * dtdv - dPdv * dtdu);
-            dg.Tx = normalize(dPds - dot(dPds, dg.Ns) * dg.Ns);
-            const V3 dPdt = normalize(dPdv * dsdu - dPdu * dsdv);
-            dg.Ty = normalize(dPdt - dot(dPdt, dg.Ns) * dg.Ns);
+            int4 vi = make_int4(0, 0, 0, 0);
+            if (g.tanXBase != YRT_NO_ATTR || g.tanYBase != YRT_NO_ATTR) vi = sc.indices[g.idxBase + (uint32_t)__float_as_int(r4.w)];
+            if (g.tanXBase != YRT_NO_ATTR) {
+                const float4 a = sc.tangents[g.tanXBase + vi.x], b = sc.tangents[g.tanXBase + vi.y], c = sc.tangents[g.tanXBase + vi.z];
+                dg.Tx = w * V3(a.x, a.y, a.z) + u * V3(b.x, b.y, b.z) + v * V3(c.x, c.y, c.z);
+            } else {
+                const V3 dPds = normalize(dPdu * dtdv - dPdv * dtdu);
+                dg.Tx = normalize(dPds - dot(dPds, dg.Ns) * dg.Ns);
+            }
+            if (g.tanYBase != YRT_NO_ATTR) {
+                const float4 a = sc.tangents[g.tanYBase + vi.x], b = sc.tangents[g.tanYBase + vi.y], c = sc.tangents[g.tanYBase + vi.z];
+                dg.Ty = w * V3(a.x, a.y, a.z) + u * V3(b.x, b.y, b.z) + v * V3(c.x, c.y, c.z);
+            } else {
+                const V3 dPdt = normalize(dPdv * dsdu - dPdu * dsdv);
+                dg.Ty = normalize(dPdt - dot(dPdt, dg.Ns) * dg.Ns);
+            }
         }
     }
     dg.error = rmax(fabsf(t), reduce_max(vabs(dg.P)));
@@ -416,7 +429,7 @@ YRT_D Col lobes_sample(const LobesT<EXT>& L, V3 wo, const DG& dg, Sample3& wiOut
 // Matte matte.h:35-37; Obj obj.h:50-69; Uber Uber.h:34-69; MatteTextured matte_textured.h:39-41;
 // Dielectric dielectric.h:57-69; ThinDielectric thindielectric.h:44-60; Mirror mirror.h:36-38
 template <bool EXT>
-YRT_D void material_shade(const SceneData& sc, const MaterialRec& m, const DG& dg, Col mediumT, float mediumEta, LobesT<EXT>& L) {
+YRT_D void material_shade(const SceneData& sc, const MaterialRec& m, DG& dg, Col mediumT, float mediumEta, LobesT<EXT>& L) {
     L.n = 0;
     switch (m.type) {
     case MAT_MATTE: add_lobe(L, LOBE_LAMBERTIAN, BR_DIFFUSE_REFLECTION, m.c0); break;
@@ -425,6 +438,11 @@ YRT_D void material_shade(const SceneData& sc, const MaterialRec& m, const DG& d
         if (m.tex[0] >= 0) { const Col4 c = tex_get(sc.textures[m.tex[0]], m.dsx * dg.s + m.s0x, m.dsy * dg.t + m.s0y); add_lobe(L, LOBE_LAMBERTIAN, BR_DIFFUSE_REFLECTION, Col(c.r, c.g, c.b)); }
         break;
     case MAT_OBJ: {
+        if (EXT && m.tex[4] >= 0) {                                                       // bump map bends the shading normal (obj.h:52-56)
+            const Col4 bump = tex_get(sc.textures[m.tex[4]], dg.s, dg.t);
+            const V3 b(2.0f * bump.r - 1.0f, 2.0f * bump.g - 1.0f, 2.0f * bump.b - 1.0f);
+            dg.Ns = normalize(b.x * dg.Tx + b.y * dg.Ty + b.z * dg.Ns);
+        }
         float d = m.f[0]; if (m.tex[0] >= 0) d *= tex_get(sc.textures[m.tex[0]], dg.s, dg.t).r;
         if (d < 1.0f) add_lobe(L, LOBE_TRANSMISSION, BR_SPECULAR_TRANSMISSION, Col(1.0f - d));
         Col Kd = d * m.c0; if (m.tex[1] >= 0) { const Col4 c = tex_get(sc.textures[m.tex[1]], dg.s, dg.t); Kd *= Col(c.r, c.g, c.b); }

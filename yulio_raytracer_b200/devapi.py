@@ -81,6 +81,7 @@ _OPTIONAL = {
     "yrtxSampleTable": (C.c_int, [H, H, C.c_int] + [C.POINTER(C.c_int)] * 4 + [C.c_void_p]),
     "yrtxFrameBufferDevice": (C.c_int, [H, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
     "yrtxSetReadback": (C.c_int, [C.c_int]),
+    "yrtxSetOption": (C.c_int, [_P, C.c_long]),
     "yrtxMicrobench": (C.c_int, [C.c_int, C.c_size_t, C.POINTER(C.c_double)]),
     "yrtxRenderCubeMap": (C.c_int, [H, C.c_void_p, C.c_size_t, H, H, C.c_void_p, C.c_int]),
     "yrtxReadImage": (C.c_int, [H] + [C.POINTER(C.c_int)] * 3 + [C.c_void_p]),
@@ -294,6 +295,10 @@ class Device:
     # ---- render calls (device.h:322-329) ---------------------------------------------
     def rtRenderFrame(self, renderer, camera, scene, tonemapper, framebuffer, accumulate=0):
         self._s("yrtRenderFrame", renderer, camera, scene, tonemapper, framebuffer, int(accumulate))
+
+    def set_option(self, key: str, value: int):
+        """yrtxSetOption: change an integer cfg key ("lanes", "tracectas", "shadectas", "syncmin", "timers", "verbose") on a live device."""
+        self._s("yrtxSetOption", _b(key), int(value))
 
     def microbench(self, kind: int, nbytes: int = 0) -> float:
         """yrtxMicrobench: 0 FP32 FMA TFLOP/s, 1 read GB/s over an nbytes working set (L1 bypassed), 2 G warp-instructions/s."""
