@@ -30,7 +30,7 @@ def main():
     inc = ["-I" + OVL, "-I" + os.path.join(OVL, "common"), "-I" + os.path.join(OVL, "devices"), "-I" + HERE,
            "-I" + os.path.join(ASSIMP, "include")]
     base = ["g++", "-std=c++14", "-O2", "-msse4.2", "-fPIC", "-fpermissive", "-w", "-DNDEBUG", "-pthread"] + inc
-    jobs = [os.path.join(OVL, s) for s in REF_SOURCES] + [os.path.join(HERE, "yulio_rt.cpp"), os.path.join(REPO, "oracle", "oracle_stubs.cpp")]
+    jobs = [os.path.join(OVL, s) for s in REF_SOURCES] + [os.path.join(HERE, "yulio_rt.cpp"), os.path.join(HERE, "codec_stubs.cpp")]
 
     def cc(src):
         obj = os.path.join(OBJ, os.path.relpath(src, REPO).replace("/", "_") + ".o")

@@ -66,6 +66,8 @@ struct Scene {
     std::vector<Node> nodes;
     std::vector<TriRef> refs;
     std::vector<float> tri;        // 9 floats per ref (time step 0), gathered for locality
+    std::vector<float> triD;       // motion blur: 9 floats per ref, vertex(time step 1) - vertex(time step 0); empty if no mesh moves
+    std::vector<uint8_t> moving;   // per ref: its mesh has two time steps
     bool committed = false;
     ~Scene() { for (auto* m : meshes) delete m; }
 };
@@ -191,12 +193,20 @@ static void commitScene(Scene* s) {
         b.build(0, 0, prims.size());
     }
     s->refs.resize(prims.size()); s->tri.resize(prims.size() * 9);
+    bool anyMotion = false;
+    for (auto* m : s->meshes) anyMotion |= m->numTimeSteps > 1;
+    s->triD.clear(); s->moving.clear();
+    if (anyMotion) { s->triD.assign(prims.size() * 9, 0.f); s->moving.assign(prims.size(), 0); }
     for (size_t i = 0; i < prims.size(); i++) {
         s->refs[i] = prims[i].ref;
         Mesh* m = s->meshes[prims[i].ref.geom];
         for (int c = 0; c < 3; c++) {
             const int32_t vi = m->idx[3 * (size_t)prims[i].ref.prim + c];
             for (int k = 0; k < 3; k++) s->tri[9 * i + 3 * c + k] = m->vtx[0][4 * (size_t)vi + k];
+            if (m->numTimeSteps > 1) {                          // contract: vertex(time) = v0 + time * (v1 - v0), mul then add
+                s->moving[i] = 1;
+                for (int k = 0; k < 3; k++) s->triD[9 * i + 3 * c + k] = m->vtx[1][4 * (size_t)vi + k] - m->vtx[0][4 * (size_t)vi + k];
+            }
         }
     }
     s->committed = true;
@@ -279,6 +289,12 @@ static void traverse(Scene* s, RTCRay& ray) {
         }
         for (uint32_t i = n.left; i < n.left + n.count; i++) {
             const float* q = &s->tri[9 * (size_t)i];
+            float moved[9];
+            if (!s->moving.empty() && s->moving[i]) {           // linear vertex motion over the shutter interval (rtcore_ray.h: RTCRay::time)
+                const float* d = &s->triD[9 * (size_t)i];
+                for (int k = 0; k < 9; k++) { const float step = ray.time * d[k]; moved[k] = q[k] + step; }
+                q = moved;
+            }
             Cand c; nt++;
             if (!triTest(O, D, {q[0], q[1], q[2]}, {q[3], q[4], q[5]}, {q[6], q[7], q[8]}, c)) continue;
             if (!(c.t > tnear)) continue;

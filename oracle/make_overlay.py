@@ -30,6 +30,8 @@ dependent; DESIGN.md "Parity contract" lists them):
      1/sqrt(x) the reference itself uses in its non-SSE branch (math.h:65,69) [SURVEY F5]
   P4 renderers/integratorrenderer.cpp: ray counter + timing exported through
      a C hook so bench.py can read Mrays/s without scraping stdout (no behaviour change).
+  P7 shapes/disk.h:53-57: the apex vertex (index n) gets no normal / texture coordinate, so shading a disk reads element n of arrays
+     of n elements: the apex is given the rim's values, normal (0,0,1) and texcoord (0,0).
   P6 renderers/debugrenderer.cpp:116: `cosineSampleHemisphere(rand.getFloat(), rand.getFloat(), Nf)` leaves the order of the two draws
      to the compiler (unspecified in C++; gcc and MSVC differ in practice): pinned to u first, then v.
   P5 textures/Bilinear.h:31-34: texels x+1 / y+1 are read past the allocation for a 1-pixel-wide / -tall image (the 1x1
@@ -142,6 +144,11 @@ def main():
           "new (&ray) Ray(ray.org+0.999f*ray.tfar*ray.dir,cosineSampleHemisphere(rand.getFloat(),rand.getFloat(),Nf),4.0f*float(ulp)/**hit.error*/);",
           "const float yrt_u = rand.getFloat(); const float yrt_v = rand.getFloat(); /* PIN P6 */\n"
           "\t\t  new (&ray) Ray(ray.org+0.999f*ray.tfar*ray.dir,cosineSampleHemisphere(yrt_u,yrt_v,Nf),4.0f*float(ulp)/**hit.error*/);")
+
+    # ---- P7 disk apex attributes ------------------------------------------------------------------
+    patch("devices/device_singleray/shapes/disk.h",
+          "position.push_back(P+Vector3f(0,0,h));",
+          "position.push_back(P+Vector3f(0,0,h)); normal.push_back(Vector3f(0.0f,0.0f,1.0f)); texcoord.push_back(Vec2f(0.0f,0.0f)); /* PIN P7 */")
 
     # ---- P4 ray counter / timing hook ------------------------------------------
     patch("devices/device_singleray/renderers/integratorrenderer.cpp",

@@ -191,3 +191,49 @@ def test_tangent_arrays_and_bump_map(cuda_dev, oracle_dev):
         cam = scenes.pinhole(d, (278, 273, -800), (278, 273, 0), (0, 1, 0), 37.0, W / H)
         return scenes._bundle(d, prims, cam, scenes.pathtracer(d, 16, 4), W, H)
     _both(cuda_dev, oracle_dev, build, mean_tol=4e-4)
+
+
+def _motion_scene(d, spp=16, depth=3):
+    """models/sphere_motion.xml in miniature: a static and a moving sphere (dPdt), a quad whose far edge drops over the shutter interval
+    ("motions" array, under a transform), the quad light and a dome light."""
+    prims = []
+    for P, dPdt, mat in (((150, 100, 280), (0, 0, 0), scenes.material(d, "matte", reflectance=(.7, .2, .2))),
+                         ((400, 100, 330), (-90, 0, -60), scenes.material(d, "MetallicPaint", shadeColor=(.1, .5, .2), glitterColor=(.8, .8, .6), glitterSpread=.3, eta=1.45))):
+        s = d.rtNewShape("sphere")
+        d.rtSetFloat3(s, "P", *P); d.rtSetFloat3(s, "dPdt", *dPdt); d.rtSetFloat1(s, "r", 90.0)
+        d.rtSetInt1(s, "numTheta", 14); d.rtSetInt1(s, "numPhi", 14)
+        d.rtCommit(s)
+        prims.append(d.rtNewShapePrimitive(s, mat, None))
+    mesh = d.rtNewShape("trianglemesh")
+    arrays = (("positions", "float3", [(-120, 0, -120), (120, 180, -120), (120, 180, 120), (-120, 0, 120)]),
+              ("motions", "float3", [(0, 0, 0), (0, -70, 0), (0, -70, 0), (0, 0, 0)]),
+              ("normals", "float3", [(0, 1, 0)] * 4), ("texcoords", "float2", [(0, 0), (1, 0), (1, 1), (0, 1)]), ("indices", "int3", [(0, 1, 2), (2, 3, 0)]))
+    keep = []
+    for key, ty, vals in arrays:
+        a = np.ascontiguousarray(vals, np.int32 if ty == "int3" else np.float32)
+        h = d.rtNewData("immutable", a); keep.append(h)
+        d.rtSetArray(mesh, key, ty, h, len(a), a.shape[1] * 4, 0)
+    d.rtCommit(mesh)
+    for h in keep:
+        d.rtDecRef(h)
+    xfm = np.array([0, 0, 1, 0, 1, 0, -1, 0, 0, 300, 0, 150], np.float32)               # rotated and translated: motion vectors turn with it
+    prims.append(d.rtNewShapePrimitive(mesh, scenes.material(d, "matte", reflectance=(.3, .4, .8)), xfm))
+    fp, fn, fu, ft = scenes.grid_quad((-400, 0, 900), (1400, 0, 0), (0, 0, -1300), 2, 2)
+    prims.append(d.rtNewShapePrimitive(scenes.add_mesh(d, fp, ft, normals=fn, uvs=fu), scenes.material(d, "matte", reflectance=(.6, .6, .6)), None))
+    prims += scenes.quad_light(d, (213, 548.77, 227), (130, 0, 0), (0, 0, 105), (50, 50, 50)) + [scenes.ambient_light(d, (.2, .25, .3))]
+    cam = scenes.pinhole(d, (278, 273, -800), (278, 150, 0), (0, 1, 0), 37.0, W / H)
+    return scenes._bundle(d, prims, cam, scenes.pathtracer(d, spp, depth, tmax_shadow=400.0), W, H)
+
+
+def test_motion_blur(cuda_dev, oracle_dev):
+    """Linear vertex motion over the shutter interval (trianglemesh_full.cpp:29-32,104-110,150-164; sphere.h:62): the ray's time comes from the
+    sample (integratorrenderer.cpp:160), travels with the path and its shadow rays, moving triangles are interpolated per ray."""
+    imgs = _both(cuda_dev, oracle_dev, _motion_scene, mean_tol=4e-4)
+    # the frame does not depend on the scheduling or the BVH builder
+    from yulio_raytracer_b200 import Device
+    for cfg in ("bvh=0,chunk=1000", "lanes=2,refill=1,trinum=1,triden=4"):
+        d = Device.cuda(cfg=cfg)
+        s = _motion_scene(d)
+        d.rtRenderFrame(s.renderer, s.camera, s.scene, s.tonemapper, s.framebuffer, 0)
+        assert np.array_equal(d.read_framebuffer(s.framebuffer, "RGB_FLOAT32", W, H).view(np.uint32), imgs[0].view(np.uint32)), cfg
+        d.close()

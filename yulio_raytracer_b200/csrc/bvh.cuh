@@ -25,6 +25,7 @@ struct __align__(16) Node8 {
 static_assert(sizeof(Node8) == 80, "Node8 must be 80 bytes");
 
 #define YRT_TRI_FLAG_CULL 1u
+#define YRT_TRI_FLAG_MOTION 2u       // the triangle's vertices move linearly over the shutter interval: p(time) = p + time * d (SceneData::triMotion)
 #define YRT_STACK_SIZE 96
 #ifndef YRT_BOX_PAD
 #define YRT_BOX_PAD 9.5367431640625e-07f     // 2^-20
@@ -265,8 +266,11 @@ YRT_D bool trace_ray(const uint4* __restrict__ nodes, const float4* __restrict__
 
 struct TraceTune { int refillMin; int triNum; int triDen; };   // refill when >= refillMin slots idle; triangle phase when triNum*nT >= triDen*nN
 
-template <bool ANY, bool COUNT, class IO>
-YRT_D void trace_stream(const uint4* __restrict__ nodes, const float4* __restrict__ tris, uint32_t numNodes,
+// MOTION (scenes with moving meshes only): every ray carries its time (IO::time), a triangle flagged YRT_TRI_FLAG_MOTION is moved to
+// p + time * d before the test — a multiply and an add per component, as the oracle's shim does (embree2_shim.cpp) — for the test, the
+// cull filter and the tie-break alike. Static triangles and static scenes run the code they always ran.
+template <bool ANY, bool COUNT, bool MOTION, class IO>
+YRT_D void trace_stream(const uint4* __restrict__ nodes, const float4* __restrict__ tris, const float4* __restrict__ triMotion, uint32_t numNodes,
                         uint32_t n, uint32_t* __restrict__ workCounter, IO io, TraceCounters& cnt, const TraceTune tune) {
     __shared__ uint2 smStack[YRT_SM_STACK * YRT_TRACE_THREADS];
     uint2 lstack[YRT_STACK_SIZE - YRT_SM_STACK];
@@ -281,7 +285,7 @@ YRT_D void trace_stream(const uint4* __restrict__ nodes, const float4* __restric
 
     bool active = false, occluded = false;
     RayPre r; r.O = V3(0.f); r.D = V3(0.f); r.idir = V3(0.f); r.octinv = 0;
-    float tnear = 0.f, tbest = 0.f, bt = 0.f, bu = 0.f, bv = 0.f;
+    float tnear = 0.f, tbest = 0.f, bt = 0.f, bu = 0.f, bv = 0.f, time = 0.f;
     uint32_t bestTri = YRT_NO_TRI, tag = 0;
     uint2 G = make_uint2(0u, 0u), T = make_uint2(0u, 0u);
     int sp = 0;
@@ -305,6 +309,7 @@ YRT_D void trace_stream(const uint4* __restrict__ nodes, const float4* __restric
                 if (!active && my < avail) {
                     V3 O, D; float tfar;
                     tag = io.load(sliceNext + my, O, D, tnear, tfar);
+                    if (MOTION) time = io.time(tag);
                     r = ray_prepare(O, D);
                     tbest = tfar; bt = tfar; bu = 0.f; bv = 0.f; bestTri = YRT_NO_TRI; occluded = false; sp = 0;
                     T = make_uint2(0u, 0u);
@@ -335,8 +340,14 @@ YRT_D void trace_stream(const uint4* __restrict__ nodes, const float4* __restric
                 const float4* tp = tris + 3ull * triIdx;
                 const float4 a = bvh_ld(tp, pol), b = bvh_ld(tp + 1, pol), c = bvh_ld(tp + 2, pol);
                 if (COUNT) cnt.tris++;
+                V3 p0(a.x, a.y, a.z), p1(b.x, b.y, b.z), p2(c.x, c.y, c.z);
+                if (MOTION && (__float_as_uint(c.w) & YRT_TRI_FLAG_MOTION)) {
+                    const float4* mp = triMotion + 3ull * triIdx;
+                    const float4 d0 = __ldg(mp), d1 = __ldg(mp + 1), d2 = __ldg(mp + 2);
+                    p0 = p0 + time * V3(d0.x, d0.y, d0.z); p1 = p1 + time * V3(d1.x, d1.y, d1.z); p2 = p2 + time * V3(d2.x, d2.y, d2.z);
+                }
                 float t, u, v, den; V3 Ng;
-                if (tri_test(r.O, r.D, V3(a.x, a.y, a.z), V3(b.x, b.y, b.z), V3(c.x, c.y, c.z), t, u, v, Ng, den) && t > tnear) {
+                if (tri_test(r.O, r.D, p0, p1, p2, t, u, v, Ng, den) && t > tnear) {
                     bool closer = t < tbest;
                     if (!ANY && !closer && bestTri != YRT_NO_TRI && t == tbest) {      // tie: (geomID, primID) ascending
                         const int g = __float_as_int(a.w), p = __float_as_int(b.w);
@@ -356,7 +367,7 @@ YRT_D void trace_stream(const uint4* __restrict__ nodes, const float4* __restric
                 if (T.y) {                                       // postpone the pending triangles
                     if (sp < YRT_SM_STACK) smStack[sp * YRT_TRACE_THREADS + threadIdx.x] = T;
                     else if (sp < YRT_STACK_SIZE) lstack[sp - YRT_SM_STACK] = T;
-                    if (sp < YRT_STACK_SIZE) sp++; else cnt.overflow = 1u;
+                    if (sp < YRT_STACK_SIZE) sp++; else io.overflow();     // reported (wb.stats[7] -> the call fails): never a silent drop
                     T.y = 0u;
                 }
                 const uint32_t bit = 31u - __clz(G.y);
@@ -366,7 +377,7 @@ YRT_D void trace_stream(const uint4* __restrict__ nodes, const float4* __restric
                 if (G.y & 0xff000000u) {
                     if (sp < YRT_SM_STACK) smStack[sp * YRT_TRACE_THREADS + threadIdx.x] = G;
                     else if (sp < YRT_STACK_SIZE) lstack[sp - YRT_SM_STACK] = G;
-                    if (sp < YRT_STACK_SIZE) sp++; else cnt.overflow = 1u;
+                    if (sp < YRT_STACK_SIZE) sp++; else io.overflow();
                 }
                 const uint4* np = nodes + 5ull * nodeIdx;
                 const uint4 n0 = bvh_ld(np, pol), n1 = bvh_ld(np + 1, pol), n2 = bvh_ld(np + 2, pol), n3 = bvh_ld(np + 3, pol), n4 = bvh_ld(np + 4, pol);

@@ -22,6 +22,7 @@
 #include <stdexcept>
 #include <string>
 #include <vector>
+#include <nvtx3/nvToolsExt.h>
 
 #include "bvh.cuh"
 #include "device_internal.hpp"
@@ -41,7 +42,7 @@ __global__ void k_init_bounds(uint32_t* sb) {
 }
 
 __global__ void k_tri_bounds(const uint2* __restrict__ refs, uint32_t n, const GeomRec* __restrict__ geoms,
-                             const float4* __restrict__ positions, const int4* __restrict__ indices,
+                             const float4* __restrict__ positions, const int4* __restrict__ indices, const float4* __restrict__ motions,
                              float4* __restrict__ boxLo, float4* __restrict__ boxHi, uint32_t* __restrict__ sceneBounds) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
@@ -53,6 +54,14 @@ __global__ void k_tri_bounds(const uint2* __restrict__ refs, uint32_t n, const G
         lo[0] = fminf(a.x, fminf(b.x, c.x)); hi[0] = fmaxf(a.x, fmaxf(b.x, c.x));
         lo[1] = fminf(a.y, fminf(b.y, c.y)); hi[1] = fmaxf(a.y, fmaxf(b.y, c.y));
         lo[2] = fminf(a.z, fminf(b.z, c.z)); hi[2] = fmaxf(a.z, fmaxf(b.z, c.z));
+        if (motions && g.motBase != YRT_NO_ATTR) {               // a moving triangle is bounded over the whole shutter interval: both end positions
+            const int vi[3] = {t.x, t.y, t.z}; const float4 p[3] = {a, b, c};
+            for (int k = 0; k < 3; k++) {
+                const float4 m = motions[g.motBase + vi[k]];
+                const float e[3] = {p[k].x + m.x, p[k].y + m.y, p[k].z + m.z};
+                for (int ax = 0; ax < 3; ax++) { lo[ax] = fminf(lo[ax], e[ax]); hi[ax] = fmaxf(hi[ax], e[ax]); }
+            }
+        }
         boxLo[i] = make_float4(lo[0], lo[1], lo[2], 0.f);
         boxHi[i] = make_float4(hi[0], hi[1], hi[2], 0.f);
     }
@@ -304,6 +313,7 @@ struct CollapseArgs {
     Lbvh t; int n;
     const uint32_t* sortedIdx;
     const uint2* refs; const GeomRec* geoms; const float4* positions; const int4* indices; const float4* normals; const float2* uvs;
+    const float4* motions; float4* triMotion;
     Node8* nodes; float4* tris; float4* triShade;
     uint32_t* counters;          // [0] node counter, [1] triangle counter, [2] next-level task count
     const uint2* tasksIn; uint2* tasksOut; uint32_t numTasks; int splitLeaves;
@@ -340,7 +350,17 @@ __device__ void write_triangle(const CollapseArgs& a, uint32_t sortedPos, uint32
     float4* o = a.tris + 3ull * outIdx;
     o[0] = make_float4(p0.x, p0.y, p0.z, __int_as_float((int)r.x));
     o[1] = make_float4(p1.x, p1.y, p1.z, __int_as_float((int)r.y));
-    o[2] = make_float4(p2.x, p2.y, p2.z, __uint_as_float(g.cull ? YRT_TRI_FLAG_CULL : 0u));
+    const bool moving = a.motions && g.motBase != YRT_NO_ATTR;
+    o[2] = make_float4(p2.x, p2.y, p2.z, __uint_as_float((g.cull ? YRT_TRI_FLAG_CULL : 0u) | (moving ? YRT_TRI_FLAG_MOTION : 0u)));
+    if (a.triMotion) {                                          // d = vertex(t = 1) - vertex(t = 0) with vertex(t = 1) = p + motion rounded first,
+        float4* mo = a.triMotion + 3ull * outIdx;               // exactly what the reference hands to the second vertex buffer (trianglemesh_full.cpp:157-160)
+        const int vi[3] = {t.x, t.y, t.z}; const float4 pv[3] = {p0, p1, p2};
+        for (int k = 0; k < 3; k++) {
+            float4 d = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (moving) { const float4 m = a.motions[g.motBase + vi[k]]; d = make_float4((pv[k].x + m.x) - pv[k].x, (pv[k].y + m.y) - pv[k].y, (pv[k].z + m.z) - pv[k].z, 0.f); }
+            mo[k] = d;
+        }
+    }
     const V3 q0(p0.x, p0.y, p0.z), q1(p1.x, p1.y, p1.z), q2(p2.x, p2.y, p2.z);
     V3 Ng = g.type == MESH_TRIANGLE ? g.triNg : normalize(cross(q0 - q1, q2 - q0));
     uint32_t flags = (uint32_t)r.x << 2;
@@ -499,9 +519,11 @@ template <typename T> static T* dalloc(size_t n) {
 static void dfree(void* p) { if (p) { g_scratch->forget(p); cudaFreeAsync(p, g_scratch->stream); } }
 
 void build_bvh(const BvhBuildInput& in, BvhResult& out, cudaStream_t stream) {
-    out.nodes = nullptr; out.tris = nullptr; out.triShade = nullptr; out.numNodes = 0; out.numTris = 0; out.buildMs = 0.f; out.launches = 0;
+    out.nodes = nullptr; out.tris = nullptr; out.triShade = nullptr; out.triMotion = nullptr; out.numNodes = 0; out.numTris = 0; out.buildMs = 0.f; out.launches = 0;
     const uint32_t n = in.numRefs;
     if (n == 0) return;
+    nvtxRangePushA("device_cuda: BVH8 build");
+    struct Pop { ~Pop() { nvtxRangePop(); } } nvtxPop;
     BuildScratch scratch(stream); g_scratch = &scratch;
     CK(cudaEventCreate(&scratch.e0)); CK(cudaEventCreate(&scratch.e1));
     const cudaEvent_t e0 = scratch.e0, e1 = scratch.e1;
@@ -513,7 +535,7 @@ void build_bvh(const BvhBuildInput& in, BvhResult& out, cudaStream_t stream) {
     uint64_t* keys = dalloc<uint64_t>(n); uint64_t* keysSorted = dalloc<uint64_t>(n);
     uint32_t* vals = dalloc<uint32_t>(n); uint32_t* sortedIdx = dalloc<uint32_t>(n);
     k_init_bounds<<<1, 32, 0, stream>>>(sceneBounds);
-    k_tri_bounds<<<G, B, 0, stream>>>(in.refs, n, in.geoms, in.positions, in.indices, boxLo, boxHi, sceneBounds);
+    k_tri_bounds<<<G, B, 0, stream>>>(in.refs, n, in.geoms, in.positions, in.indices, in.motions, boxLo, boxHi, sceneBounds);
     k_morton<<<G, B, 0, stream>>>(boxLo, boxHi, n, sceneBounds, keys, vals);
     out.launches += 3;
     size_t tmpBytes = 0;
@@ -572,6 +594,7 @@ void build_bvh(const BvhBuildInput& in, BvhResult& out, cudaStream_t stream) {
     // worst case one BVH8 node per BVH2 internal node; shrunk to the exact size afterwards
     Node8* nodesTmp = dalloc<Node8>((size_t)ni + 1);
     float4* tris = dalloc<float4>(3ull * n); float4* triShade = dalloc<float4>(5ull * n);
+    float4* triMotion = in.motions ? dalloc<float4>(3ull * n) : nullptr;
     uint32_t* counters = dalloc<uint32_t>(4);
     uint2* tasksA = dalloc<uint2>(ni + 1); uint2* tasksB = dalloc<uint2>(ni + 1);
     const uint32_t initCounters[4] = {1u, 0u, 0u, 0u};
@@ -582,6 +605,7 @@ void build_bvh(const BvhBuildInput& in, BvhResult& out, cudaStream_t stream) {
     CollapseArgs ca;
     ca.t = t; ca.n = (int)n; ca.sortedIdx = sortedIdx;
     ca.refs = in.refs; ca.geoms = in.geoms; ca.positions = in.positions; ca.indices = in.indices; ca.normals = in.normals; ca.uvs = in.uvs;
+    ca.motions = in.motions; ca.triMotion = triMotion;
     ca.nodes = nodesTmp; ca.tris = tris; ca.triShade = triShade; ca.counters = counters; ca.splitLeaves = in.splitLeaves;
     uint32_t numTasks = 1; uint2* tin = tasksA; uint2* tout = tasksB;
     uint32_t hostCounters[4];
@@ -602,8 +626,8 @@ void build_bvh(const BvhBuildInput& in, BvhResult& out, cudaStream_t stream) {
     CK(cudaEventRecord(e1, stream));
     CK(cudaStreamSynchronize(stream));
     CK(cudaEventElapsedTime(&out.buildMs, e0, e1));
-    out.nodes = nodes; out.tris = tris; out.triShade = triShade;
-    scratch.forget(nodes); scratch.forget(tris); scratch.forget(triShade);      // the results outlive the build (SceneHandle::releaseDevice)
+    out.nodes = nodes; out.tris = tris; out.triShade = triShade; out.triMotion = triMotion;
+    scratch.forget(nodes); scratch.forget(tris); scratch.forget(triShade); if (triMotion) scratch.forget(triMotion);      // the results outlive the build (SceneHandle::releaseDevice)
 
     dfree(nodesTmp); dfree(counters); dfree(tasksA); dfree(tasksB);
     dfree(t.left); dfree(t.right); dfree(t.parent); dfree(t.count);

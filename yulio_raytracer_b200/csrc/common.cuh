@@ -169,6 +169,7 @@ struct GeomRec {                 // one per geomID (= one committed shape primit
     uint32_t nrmBase, uvBase;    // into normals / uvs, YRT_NO_ATTR when the mesh has none
     V3 triNg;                    // MESH_TRIANGLE: normalize(cross(v2-v0, v1-v0))  (shapes/triangle.h:43)
     int shadeClass;              // 1..14: hits whose shading follows the same code path (material kind, textured or not, lobe set)
+    uint32_t motBase;            // into SceneData::motions (per-vertex motion vectors, "motions" / sphere "dPdt"), YRT_NO_ATTR when static
     uint32_t tanXBase, tanYBase; // into SceneData::tangents (per-vertex tangent_x / tangent_y arrays), YRT_NO_ATTR when the mesh has none
 };
 
@@ -208,10 +209,13 @@ struct SceneData {
     const void* nodes;           // BVH8 nodes, 80 B each (bvh.cuh)
     const float4* tris;          // 3 x float4 per triangle in leaf order (p0|geomID, p1|primID, p2|cull)
     const float4* triShade;      // 5 x float4 per triangle in leaf order: what postIntersect needs (bvh_build.cu: write_triangle)
+    const float4* triMotion;     // motion blur: 3 x float4 per triangle in leaf order, vertex(t = 1) - vertex(t = 0); NULL when nothing moves
+    int hasMotion;               // some mesh carries motion vectors: rays carry their time, moving triangles are interpolated per ray
     uint32_t numNodes, numTris;
     // shading data
     const GeomRec* geoms;
     const float4* positions; const float4* normals; const float2* uvs; const int4* indices;
+    const float4* motions;       // per-vertex motion vectors of the moving meshes (GeomRec::motBase)
     const float4* tangents;      // per-vertex tangent arrays of the meshes that carry them (GeomRec::tanXBase / tanYBase)
     const MaterialRec* materials; const TextureRec* textures; const LightRec* lights;
     int numGeoms, numLights, numEnvLights, numPrecomputed;

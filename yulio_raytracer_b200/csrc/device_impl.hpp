@@ -65,9 +65,9 @@ struct SceneHandle : Handle {
     std::vector<float4> hostPositions, hostNormals; std::vector<float2> hostUvs; std::vector<int4> hostIndices;
     // ---- committed (device) state
     SceneData data{};                          // pointers below
-    DevBuf<GeomRec> geoms; DevBuf<float4> positions, normals, tangents; DevBuf<float2> uvs; DevBuf<int4> indices;
+    DevBuf<GeomRec> geoms; DevBuf<float4> positions, normals, tangents, motions; DevBuf<float2> uvs; DevBuf<int4> indices;
     DevBuf<MaterialRec> materials; DevBuf<TextureRec> textures; DevBuf<LightRec> lights; DevBuf<uint2> refsBuf;
-    void* nodes = nullptr; float4* tris = nullptr; float4* triShade = nullptr;
+    void* nodes = nullptr; float4* tris = nullptr; float4* triShade = nullptr; float4* triMotion = nullptr;
     std::vector<std::shared_ptr<ImageObj>> imagesInUse;   // keeps device pixel storage alive
     std::vector<std::shared_ptr<ImageObj>> extraImages;   // images addressable by FrameConst (backplate) appended lazily
     std::vector<TextureRec> hostTextures;
@@ -135,10 +135,12 @@ struct yrt_device {
     int sortRays = 0; uint32_t sortMin = 1u << 16;   // cfg sort=0|1: re-order bounce queues of at least sortMin rays (sort.cu); measured slower, off
     uint32_t* hostCounters = nullptr;          // pinned: queue lengths read back once per bounce   // cfg refill=,trinum=,triden= (bvh.cuh: TraceTune)
     bool readback = true;                      // copy the frame to the host buffer inside yrtRenderFrame (yrtxSetReadback)
-    // Two chunk lanes: consecutive chunks of a render call run on two streams with their own wavefront state, each kernel launched with
-    // half the CTAs, so that a latency-bound shading kernel of one chunk shares the SMs with an issue-bound traversal kernel of the other
-    // (ncu r2: k_shade issues 44 % of the time, the traversal kernels 77 %) and launch tails overlap. cfg lanes=1 restores one stream.
-    int lanes = 2; cudaStream_t stream1 = nullptr;
+    // Two chunk lanes (cfg lanes=2, off by default): consecutive chunks of a render call run on two streams with their own wavefront
+    // state, each kernel launched with half the CTAs, so that a latency-bound shading kernel of one chunk shares the SMs with an
+    // issue-bound traversal kernel of the other (ncu r2: k_shade issues 44 % of the time, the traversal kernels 77 %). Measured r2
+    // (profiles/README.md): 3-6 % SLOWER on C2 / C3 / C4 for every CTA split tried — co-resident kernels take each other's L1 and
+    // warp slots and neither gains issue slots — so one lane stays the default; the frames are bit-identical either way.
+    int lanes = 1; cudaStream_t stream1 = nullptr;
     yrt::WavefrontStorage wf, wf1;
     yrt::FrameTimers timers;
     yrt::DevBuf<float> sampleTable; yrt::TableKey tableKey; int tableSpp = 1, tableN1 = 0, tableN2 = 0, tableRec = 0;

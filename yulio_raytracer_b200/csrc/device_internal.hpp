@@ -17,13 +17,14 @@ struct BvhBuildInput {
     const int4* indices;          // device
     const float4* normals;        // device (shading normals, GeomRec::nrmBase)
     const float2* uvs;            // device (texture coordinates, GeomRec::uvBase)
+    const float4* motions;        // device (motion vectors, GeomRec::motBase), NULL when the scene has no moving mesh
     uint32_t* hostWord;           // pinned host word for the builder's read-backs (owned by the device)
     int ploc = 1;                 // 1: PLOC hierarchy (default), 0: Karras LBVH
     int splitLeaves = 1;          // BVH8 collapse: use free child slots to split leaf children of 2-3 triangles
     int plocRadius = 8;           // PLOC neighbour search radius (positions to either side)
 };
 struct BvhResult {
-    void* nodes; float4* tris; float4* triShade; uint32_t numNodes, numTris; float buildMs; uint32_t launches;
+    void* nodes; float4* tris; float4* triShade; float4* triMotion; uint32_t numNodes, numTris; float buildMs; uint32_t launches;
 };
 void build_bvh(const BvhBuildInput& in, BvhResult& out, cudaStream_t stream);
 

@@ -125,7 +125,7 @@ static std::shared_ptr<ShapeObj> make_shape(const std::string& type, const Parms
     auto s = std::make_shared<ShapeObj>();
     if (type == "trianglemesh") {                               // shapes/trianglemesh.h:29-41, trianglemesh_full.cpp:21-66
         bool hasP, hasM, hasN, hasTx, hasTy;
-        std::vector<V3> motion; std::vector<V3>& tx = s->tangentX; std::vector<V3>& ty = s->tangentY;
+        std::vector<V3>& motion = s->motion; std::vector<V3>& tx = s->tangentX; std::vector<V3>& ty = s->tangentY;
         read_v3_array(p, "positions", "wrong position format", s->position, hasP);
         read_v3_array(p, "motions", "wrong motion vector format", motion, hasM);
         read_v3_array(p, "normals", "wrong normal format", s->normal, hasN);
@@ -145,7 +145,6 @@ static std::shared_ptr<ShapeObj> make_shape(const std::string& type, const Parms
             s->triangles.resize(v->size);
             for (size_t i = 0; i < v->size; i++) { int t[3]; memcpy(t, v->elem(i), 12); s->triangles[i] = make_int4(t[0], t[1], t[2], 0); }
         }
-        if (!motion.empty()) throw std::runtime_error("device_cuda: motion blur (\"motions\") is not supported");
         s->cullBackFaces = p.getBool("cullBackFaces", false);
         const bool withNormals = hasP && !hasM && hasN && !hasTx && !hasTy && !hasUV;
         s->type = withNormals ? MESH_NORMALS : MESH_FULL;
@@ -155,6 +154,7 @@ static std::shared_ptr<ShapeObj> make_shape(const std::string& type, const Parms
         }
         if (!s->normal.empty() && s->normal.size() < s->position.size()) s->normal.resize(s->position.size(), V3(0.f));
         if (!s->texcoord.empty() && s->texcoord.size() < s->position.size()) s->texcoord.resize(s->position.size(), make_float2(0.f, 0.f));
+        if (!motion.empty() && motion.size() < s->position.size()) motion.resize(s->position.size(), V3(0.f));
         if (!tx.empty() && tx.size() < s->position.size()) tx.resize(s->position.size(), V3(0.f));
         if (!ty.empty() && ty.size() < s->position.size()) ty.resize(s->position.size(), V3(0.f));
         return s;
@@ -169,7 +169,6 @@ static std::shared_ptr<ShapeObj> make_shape(const std::string& type, const Parms
         const V3 P = p.getV3("P"), dPdt = p.getV3("dPdt");
         const float r = p.getFloat("r");
         const size_t numTheta = (size_t)p.getInt("numTheta"), numPhi = (size_t)p.getInt("numPhi");
-        if (dPdt != V3(0.f)) throw std::runtime_error("device_cuda: motion blur (\"dPdt\") is not supported");
         auto eval = [](float theta, float phi) { return V3(sinf(theta) * cosf(phi), cosf(theta), sinf(theta) * sinf(phi)); };
         for (size_t theta = 0; theta <= numTheta; theta++) {
             const float rcpNumTheta = rcpf(float(numTheta));
@@ -180,6 +179,7 @@ static std::shared_ptr<ShapeObj> make_shape(const std::string& type, const Parms
                 const V3 dpdv = eval(theta * YRT_PI * rcpNumTheta, (phi + 0.001f) * 2.0f * YRT_PI * rcpNumPhi) - pt;
                 pt = r * pt + P;
                 s->position.push_back(pt);
+                if (dPdt != V3(0.f)) s->motion.push_back(dPdt);                      // sphere.h:62
                 s->normal.push_back(normalize(cross(dpdv, dpdu)));
                 s->texcoord.push_back(make_float2(phi * rcpNumPhi, theta * rcpNumTheta));
             }
@@ -205,7 +205,9 @@ static std::shared_ptr<ShapeObj> make_shape(const std::string& type, const Parms
         s->texcoord.push_back(make_float2(0.0f, 0.0f));
     }
     s->position.push_back(P + V3(0, 0, h));
-    s->normal.push_back(V3(0.f)); s->texcoord.push_back(make_float2(0.f, 0.f));   // the reference reads past the end here
+    // pin P7: the reference gives the apex no normal / texture coordinate and reads element n of arrays of n (disk.h:53-57); the apex gets
+    // the rim's values, (0,0,1) and (0,0), here and in the oracle overlay
+    s->normal.push_back(V3(0.0f, 0.0f, 1.0f)); s->texcoord.push_back(make_float2(0.f, 0.f));
     for (size_t phi = 0; phi < n; phi++) {
         const size_t p0 = n, p1 = (phi + 0) % n, p2 = (phi + 1) % n;
         switch (phi % 3) {
@@ -442,7 +444,7 @@ yrt_device* yrtCreateDevice(const char* parms, size_t numThreads, int threadsPri
         YRT_CK(cudaSetDevice(gpu));
         YRT_CK(cudaStreamCreateWithFlags(&dev->stream, cudaStreamNonBlocking));
         YRT_CK(cudaStreamCreateWithFlags(&dev->stream1, cudaStreamNonBlocking));
-        dev->lanes = (int)cfg_int(cfg, "lanes", 2) >= 2 ? 2 : 1;
+        dev->lanes = (int)cfg_int(cfg, "lanes", 1) >= 2 ? 2 : 1;
         {   // keep freed scratch in the stream-ordered pool instead of returning it to the OS at every synchronisation
             cudaMemPool_t pool; YRT_CK(cudaDeviceGetDefaultMemPool(&pool, gpu));
             uint64_t keep = ~0ull; YRT_CK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));

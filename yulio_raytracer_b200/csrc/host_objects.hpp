@@ -37,7 +37,7 @@ struct MaterialObj {
 
 struct ShapeObj {
     int type = MESH_FULL;              // MeshType
-    std::vector<V3> position, normal, tangentX, tangentY; std::vector<float2> texcoord; std::vector<int4> triangles;
+    std::vector<V3> position, normal, tangentX, tangentY, motion; std::vector<float2> texcoord; std::vector<int4> triangles;   // motion: per-vertex displacement over the shutter interval ("motions", sphere "dPdt")
     bool cullBackFaces = false;
     V3 v0, v1, v2, triNg;              // MESH_TRIANGLE
     bool triNgValid = false;           // the Parms constructor of Triangle leaves Ng unset (shapes/triangle.h:33-38)

@@ -14,6 +14,8 @@
 #include <cstdlib>
 #include <map>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "device_impl.hpp"
 #include "host_math.hpp"
 
@@ -102,7 +104,8 @@ static void image_upload(ImageObj& img, cudaStream_t s) {
 SceneHandle::~SceneHandle() { releaseDevice(); }
 void SceneHandle::releaseDevice() {
     if (nodes) cudaFreeAsync(nodes, nullptr); if (tris) cudaFreeAsync(tris, nullptr); if (triShade) cudaFreeAsync(triShade, nullptr);   // allocated from the stream-ordered pool (bvh_build.cu)
-    nodes = nullptr; tris = nullptr; triShade = nullptr;
+    if (triMotion) cudaFreeAsync(triMotion, nullptr);
+    nodes = nullptr; tris = nullptr; triShade = nullptr; triMotion = nullptr;
 }
 
 // Shape::transform  shapes/trianglemesh_full.cpp:68-90, trianglemesh_normals.cpp:42-56, triangle.h:47-49
@@ -123,6 +126,8 @@ static std::shared_ptr<ShapeObj> transform_shape(const std::shared_ptr<ShapeObj>
         const Lin3 it = lin3_inverse_transposed(xfm.l);
         for (size_t i = 0; i < s->normal.size(); i++) t->normal[i] = xfmVector(it, s->normal[i]);
     }
+    t->motion.resize(s->motion.size());                                                      // xfmVector (trianglemesh_full.cpp:80-81)
+    for (size_t i = 0; i < s->motion.size(); i++) t->motion[i] = xfmVector(xfm, s->motion[i]);
     t->tangentX.resize(s->tangentX.size()); t->tangentY.resize(s->tangentY.size());          // xfmVector (trianglemesh_full.cpp:84-87)
     for (size_t i = 0; i < s->tangentX.size(); i++) t->tangentX[i] = xfmVector(xfm, s->tangentX[i]);
     for (size_t i = 0; i < s->tangentY.size(); i++) t->tangentY[i] = xfmVector(xfm, s->tangentY[i]);
@@ -185,7 +190,7 @@ static bool slot_matches(const SceneHandle::SlotLayout& L, const ScenePrim& p) {
     if (!p.shape || p.light || L.hasLight || L.geomID < 0 || !L.allFinite) return false;
     const ShapeObj& s = *p.shape;
     if (s.type != L.type || s.type == MESH_TRIANGLE || p.material.get() != L.material || s.cullBackFaces != L.cull) return false;
-    if (L.hasTangents || !s.tangentX.empty() || !s.tangentY.empty()) return false;          // tangent arrays are re-flattened, not patched
+    if (L.hasTangents || !s.tangentX.empty() || !s.tangentY.empty() || !s.motion.empty()) return false;   // tangent / motion arrays are re-flattened, not patched
     if (p.illumMask != L.illumMask || p.shadowMask != L.shadowMask) return false;
     if (s.position.size() != L.nv || s.normal.size() != L.nn || s.texcoord.size() != L.nuv || s.triangles.size() != L.nt) return false;
     for (const V3& q : s.position) if (!(std::isfinite(q.x) && std::isfinite(q.y) && std::isfinite(q.z))) return false;
@@ -225,7 +230,10 @@ static int scene_patch(yrt_device* dev, SceneHandle* sc) {
     return moved ? 1 : 2;
 }
 
+struct NvtxRange { explicit NvtxRange(const char* name) { nvtxRangePushA(name); } ~NvtxRange() { nvtxRangePop(); } };   // timeline ranges (nsys / ncu --nvtx)
+
 void scene_commit(yrt_device* dev, SceneHandle* sc) {
+    NvtxRange nvtxCommit("device_cuda: rtCommit(scene)");
     sc->commitCount++;
     // The reference rebuilds the Embree scene on every commit (scene_flat.h:87-112); the result only
     // depends on the slots, so an unchanged scene keeps its BVH unless cfg rebuild=1 asks for the reference's cost.
@@ -242,14 +250,15 @@ void scene_commit(yrt_device* dev, SceneHandle* sc) {
         lap("patch");
         sc->patchSlots.clear();
         // the old BVH is released only once the new one exists; a failed build leaves the scene uncommitted (never dangling pointers)
-        BvhBuildInput in{sc->refsBuf.p, sc->numRefs, sc->geoms.p, sc->positions.p, sc->indices.p, sc->normals.p, sc->uvs.p, dev->hostCounters + 8, dev->bvhPloc, dev->splitLeaves, dev->plocRadius};
+        BvhBuildInput in{sc->refsBuf.p, sc->numRefs, sc->geoms.p, sc->positions.p, sc->indices.p, sc->normals.p, sc->uvs.p, sc->data.hasMotion ? sc->motions.p : nullptr,
+                         dev->hostCounters + 8, dev->bvhPloc, dev->splitLeaves, dev->plocRadius};
         BvhResult out{};
         try { build_bvh(in, out, st); }
-        catch (...) { sc->releaseDevice(); sc->committed = false; sc->structureDirty = true; sc->data.nodes = nullptr; sc->data.tris = nullptr; sc->data.triShade = nullptr; sc->data.numNodes = sc->data.numTris = 0; throw; }
+        catch (...) { sc->releaseDevice(); sc->committed = false; sc->structureDirty = true; sc->data.nodes = nullptr; sc->data.tris = nullptr; sc->data.triShade = nullptr; sc->data.triMotion = nullptr; sc->data.numNodes = sc->data.numTris = 0; throw; }
         sc->releaseDevice();
         lap("bvh");
-        sc->nodes = out.nodes; sc->tris = out.tris; sc->triShade = out.triShade; sc->buildMs = out.buildMs; sc->buildLaunches = out.launches; sc->rebuildCount++;
-        sc->data.nodes = sc->nodes; sc->data.tris = sc->tris; sc->data.triShade = sc->triShade; sc->data.numNodes = out.numNodes; sc->data.numTris = out.numTris;
+        sc->nodes = out.nodes; sc->tris = out.tris; sc->triShade = out.triShade; sc->triMotion = out.triMotion; sc->buildMs = out.buildMs; sc->buildLaunches = out.launches; sc->rebuildCount++;
+        sc->data.nodes = sc->nodes; sc->data.tris = sc->tris; sc->data.triShade = sc->triShade; sc->data.triMotion = sc->triMotion; sc->data.numNodes = out.numNodes; sc->data.numTris = out.numTris;
         if (dev->sortRays) scene_bounds(sc);
         sc->dirty = false;
         dev->stats.build_ms = out.buildMs; dev->stats.num_triangles = out.numTris; dev->stats.num_nodes = out.numNodes; dev->stats.bvh_builds = sc->rebuildCount;
@@ -261,7 +270,7 @@ void scene_commit(yrt_device* dev, SceneHandle* sc) {
     std::vector<float2>& uvs = sc->hostUvs; std::vector<int4>& indices = sc->hostIndices;
     positions.clear(); normals.clear(); uvs.clear(); indices.clear();
     sc->layout.assign(sc->prims.size(), SceneHandle::SlotLayout());
-    std::vector<uint2> refs; std::vector<MaterialRec> materials; std::vector<LightRec> lights; std::vector<float4> tangents;
+    std::vector<uint2> refs; std::vector<MaterialRec> materials; std::vector<LightRec> lights; std::vector<float4> tangents, motions;
     std::map<const MaterialObj*, int> matIndex; std::map<const TextureObj*, int> texIndex;
     sc->hostTextures.clear(); sc->imagesInUse.clear(); sc->hdri.clear(); sc->geomOfSlot.assign(sc->prims.size(), -1);
 
@@ -337,7 +346,7 @@ void scene_commit(yrt_device* dev, SceneHandle* sc) {
         g.type = s.type; g.material = material_index(p->material); g.areaLight = lightIdx;
         g.cull = s.cullBackFaces ? 1 : 0; g.illumMask = p->illumMask; g.shadowMask = p->shadowMask;
         g.vtxBase = (uint32_t)positions.size(); g.idxBase = (uint32_t)indices.size();
-        g.nrmBase = YRT_NO_ATTR; g.uvBase = YRT_NO_ATTR; g.tanXBase = YRT_NO_ATTR; g.tanYBase = YRT_NO_ATTR; g.triNg = V3(0.f);
+        g.nrmBase = YRT_NO_ATTR; g.uvBase = YRT_NO_ATTR; g.tanXBase = YRT_NO_ATTR; g.tanYBase = YRT_NO_ATTR; g.motBase = YRT_NO_ATTR; g.triNg = V3(0.f);
         if (s.type == MESH_TRIANGLE) {
             g.triNg = s.triNg;
             const V3 v[3] = {s.v0, s.v1, s.v2};
@@ -350,6 +359,7 @@ void scene_commit(yrt_device* dev, SceneHandle* sc) {
             for (const V3& q : s.position) positions.push_back(make_float4(q.x, q.y, q.z, 0.f));
             if (!s.normal.empty()) { g.nrmBase = (uint32_t)normals.size(); for (const V3& q : s.normal) normals.push_back(make_float4(q.x, q.y, q.z, 0.f)); }
             if (!s.texcoord.empty()) { g.uvBase = (uint32_t)uvs.size(); for (const float2& q : s.texcoord) uvs.push_back(q); }
+            if (!s.motion.empty()) { g.motBase = (uint32_t)motions.size(); for (const V3& q : s.motion) motions.push_back(make_float4(q.x, q.y, q.z, 0.f)); }
             if (!s.tangentX.empty()) { g.tanXBase = (uint32_t)tangents.size(); for (const V3& q : s.tangentX) tangents.push_back(make_float4(q.x, q.y, q.z, 0.f)); }
             if (!s.tangentY.empty()) { g.tanYBase = (uint32_t)tangents.size(); for (const V3& q : s.tangentY) tangents.push_back(make_float4(q.x, q.y, q.z, 0.f)); }
             for (size_t t = 0; t < s.triangles.size(); t++) {
@@ -366,12 +376,12 @@ void scene_commit(yrt_device* dev, SceneHandle* sc) {
         L.hasLight = (bool)p->light; L.cull = s.cullBackFaces; L.vtxBase = g.vtxBase; L.nrmBase = g.nrmBase; L.uvBase = g.uvBase; L.idxBase = g.idxBase;
         if (s.type != MESH_TRIANGLE) { L.nv = s.position.size(); L.nn = s.normal.size(); L.nuv = s.texcoord.size(); L.nt = s.triangles.size(); }
         L.allFinite = s.type != MESH_TRIANGLE && refs.size() - refsBefore == s.triangles.size();
-        L.hasTangents = !s.tangentX.empty() || !s.tangentY.empty();
+        L.hasTangents = !s.tangentX.empty() || !s.tangentY.empty() || !s.motion.empty();
     }
 
     lap("flatten");
     sc->geoms.upload(geoms, st); sc->positions.upload(positions, st); sc->normals.upload(normals, st); sc->uvs.upload(uvs, st);
-    sc->indices.upload(indices, st); sc->materials.upload(materials, st); sc->lights.upload(lights, st); sc->tangents.upload(tangents, st);
+    sc->indices.upload(indices, st); sc->materials.upload(materials, st); sc->lights.upload(lights, st); sc->tangents.upload(tangents, st); sc->motions.upload(motions, st);
     sc->textures.upload(sc->hostTextures, st);
     DevBuf<uint2>& dRefs = sc->refsBuf; dRefs.upload(refs, st);      // kept across commits: no cudaMalloc/cudaFree per cube face
     sc->numRefs = (uint32_t)refs.size();
@@ -380,16 +390,18 @@ void scene_commit(yrt_device* dev, SceneHandle* sc) {
     sc->committed = false;                                    // until the new structure exists (the arrays above were replaced already)
     sc->releaseDevice();
     sc->data.nodes = nullptr; sc->data.tris = nullptr; sc->data.triShade = nullptr; sc->data.numNodes = sc->data.numTris = 0;
-    BvhBuildInput in{dRefs.p, (uint32_t)refs.size(), sc->geoms.p, sc->positions.p, sc->indices.p, sc->normals.p, sc->uvs.p, dev->hostCounters + 8, dev->bvhPloc, dev->splitLeaves, dev->plocRadius};
+    BvhBuildInput in{dRefs.p, (uint32_t)refs.size(), sc->geoms.p, sc->positions.p, sc->indices.p, sc->normals.p, sc->uvs.p, motions.empty() ? nullptr : sc->motions.p,
+                     dev->hostCounters + 8, dev->bvhPloc, dev->splitLeaves, dev->plocRadius};
     BvhResult out{};
     sc->structureDirty = true;                                // a throw below leaves a scene that re-flattens on the next commit
     build_bvh(in, out, st);
     YRT_CK(cudaStreamSynchronize(st));
     sc->structureDirty = false;
     lap("bvh");
-    sc->nodes = out.nodes; sc->tris = out.tris; sc->triShade = out.triShade; sc->buildMs = out.buildMs; sc->buildLaunches = out.launches; sc->rebuildCount++;
+    sc->nodes = out.nodes; sc->tris = out.tris; sc->triShade = out.triShade; sc->triMotion = out.triMotion; sc->buildMs = out.buildMs; sc->buildLaunches = out.launches; sc->rebuildCount++;
 
-    d.nodes = sc->nodes; d.tris = sc->tris; d.triShade = sc->triShade; d.numNodes = out.numNodes; d.numTris = out.numTris;
+    d.nodes = sc->nodes; d.tris = sc->tris; d.triShade = sc->triShade; d.triMotion = sc->triMotion; d.hasMotion = motions.empty() ? 0 : 1; d.motions = sc->motions.p;
+    d.numNodes = out.numNodes; d.numTris = out.numTris;
     d.geoms = sc->geoms.p; d.positions = sc->positions.p; d.normals = sc->normals.p; d.uvs = sc->uvs.p; d.indices = sc->indices.p; d.tangents = sc->tangents.p;
     d.materials = sc->materials.p; d.textures = sc->textures.p; d.lights = sc->lights.p;
     d.numGeoms = (int)geoms.size(); d.numLights = (int)lights.size();
@@ -603,6 +615,7 @@ struct StatusRec { int state; float progress; };               // RendererStatus
 // all faces are rendered as one wavefront (device_internal.hpp: FrameConst::numFaces).
 void render_frames(yrt_device* dev, RendererHandle* rh, size_t numFaces, CameraHandle* const* chs, SceneHandle* sc, ToneMapperHandle* th,
                    FrameBufferHandle* const* fbs, int accumulate) {
+    NvtxRange nvtxFrame(numFaces > 1 ? "device_cuda: yrtxRenderCubeMap" : "device_cuda: rtRenderFrame");
     const auto tHost0 = std::chrono::steady_clock::now();
     auto hostLap = [&](const char* what) { if (dev->verbose >= 3) printf("  host %-10s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tHost0).count()); };
     if (!rh->inst) throw std::runtime_error("invalid renderer value");
@@ -714,12 +727,14 @@ void render_frames(yrt_device* dev, RendererHandle* rh, size_t numFaces, CameraH
             }
             if (stopRequested()) { stopped = true; break; }
             const uint32_t np = (uint32_t)std::min<size_t>(pixelsPerChunk, numPixels - pixelBegin);
+            NvtxRange nvtxChunk(lane ? "wavefront chunk (lane 1): enqueue" : "wavefront chunk (lane 0): enqueue");
             if (timers) tm.begin(TK_RAYGEN_FILM, ls);
             launch_raygen(fc, cams, wb, (uint32_t)pixelBegin, np, lcStream); launches++;
             if (timers) tm.end(ls);
             int q = 0;
             uint32_t alive = np * (uint32_t)spp;                 // length of the current queue, known on the host
             for (int depth = 0; depth < fc.integ.maxDepth && alive; depth++, q ^= 1) {
+                NvtxRange nvtxBounce("bounce: closest / shade / shadow / resolve");
                 // bounce queues are re-ordered by origin cell + direction octant (sort.cu); the sorted ids live in queueS
                 WavefrontBuffers wq = wb;
                 if (depth > 0 && dev->sortRays && alive >= dev->sortMin) {

@@ -94,6 +94,7 @@ __global__ void __launch_bounds__(256) k_raygen(FrameConst fc, const __grid_cons
         V3 org, dir; camera_ray(cams.cam[c.face], fx, fy, rec[3], rec[4], org, dir);
         wb.rayO[pid] = make_float4(org.x, org.y, org.z, 0.f);
         wb.rayD[pid] = make_float4(dir.x, dir.y, dir.z, INFINITY);
+        if (fc.scene.hasMotion) wb.hitA[pid] = make_float4(rec[2], 0.f, 0.f, 0.f);     // the ray's time (integratorrenderer.cpp:160) for the traversal
         // throughput (1, unbent), radiance (0) and medium (vacuum) of a fresh path are implied: k_shade(depth 0) does not read them
         wb.queueA[pid] = pid;
     }
@@ -134,6 +135,9 @@ struct ClosestIO {
         YRT_ST_STREAM(&wb.hitA[pid], make_float4(t, u, v, __int_as_float(tri == YRT_NO_TRI ? -1 : (int)tri)));
     }
     __device__ __forceinline__ void store_any(uint32_t, bool) const {}
+    // motion blur: the path's time travels in the hit record's first lane until the traversal overwrites it (k_raygen / k_shade put it there)
+    __device__ __forceinline__ float time(uint32_t pid) const { return wb.hitA[pid].x; }
+    __device__ __forceinline__ void overflow() const { atomicOr(&wb.stats[7], 1ull); }     // traversal stack exhausted: the render call throws
 };
 struct ShadowIO {
     WavefrontBuffers wb;
@@ -144,9 +148,12 @@ struct ShadowIO {
     }
     __device__ __forceinline__ void store_hit(uint32_t, float, float, float, uint32_t, const float4*) const {}
     __device__ __forceinline__ void store_any(uint32_t i, bool occluded) const { wb.shC[i].w = occluded ? 1.f : 0.f; }
+    // motion blur: a shadow ray's time arrives in the lane the occlusion flag is written to
+    __device__ __forceinline__ float time(uint32_t i) const { return wb.shC[i].w; }
+    __device__ __forceinline__ void overflow() const { atomicOr(&wb.stats[7], 1ull); }
 };
 struct UserIO {
-    const float4* __restrict__ rays; float4* __restrict__ hits;
+    const float4* __restrict__ rays; float4* __restrict__ hits; unsigned long long* errFlags;
     __device__ __forceinline__ uint32_t load(uint32_t i, V3& O, V3& D, float& tnear, float& tfar) const {
         const float4 o = __ldg(&rays[2ull * i]), d = __ldg(&rays[2ull * i + 1]);
         O = f4v(o); D = f4v(d); tnear = o.w; tfar = d.w;
@@ -164,6 +171,8 @@ struct UserIO {
     __device__ __forceinline__ void store_any(uint32_t i, bool occluded) const {
         float4 a = hits[2ull * i]; a.w = __int_as_float(occluded ? 0 : -1); hits[2ull * i] = a;
     }
+    __device__ __forceinline__ float time(uint32_t) const { return 0.f; }     // the API's ray record has no time: shutter open (t = 0)
+    __device__ __forceinline__ void overflow() const { if (errFlags) atomicOr(errFlags, 1ull); }
 };
 
 // ---- A/B baseline: one ray per thread for the life of the thread (bvh.cuh: trace_ray), cfg trav=0 ------------
@@ -184,57 +193,60 @@ __global__ void __launch_bounds__(YRT_TRACE_THREADS) k_trace_simple(SceneData sc
 #ifndef YRT_CLOSEST_MINBLOCKS
 #define YRT_CLOSEST_MINBLOCKS 8
 #endif
-template <bool COUNT>
+template <bool COUNT, bool MOTION>
 __global__ void __launch_bounds__(YRT_TRACE_THREADS, YRT_CLOSEST_MINBLOCKS) k_trace_closest(SceneData sc, WavefrontBuffers wb, int queueSel) {
     const uint32_t n = wb.counters[queueSel];
     TraceCounters cnt = {0, 0, 0};
     ClosestIO io{wb, queueSel ? wb.queueB : wb.queueA};
-    trace_stream<false, COUNT>((const uint4*)sc.nodes, sc.tris, sc.numNodes, n, &wb.counters[4], io, cnt, TraceTune{sc.tuneRefillMin, sc.tuneTriNum, sc.tuneTriDen});
+    trace_stream<false, COUNT, MOTION>((const uint4*)sc.nodes, sc.tris, sc.triMotion, sc.numNodes, n, &wb.counters[4], io, cnt, TraceTune{sc.tuneRefillMin, sc.tuneTriNum, sc.tuneTriDen});
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&wb.stats[0], (unsigned long long)n);
-    if (cnt.overflow) atomicOr(&wb.stats[7], 1ull);
     if (COUNT) { atomicAdd(&wb.stats[2], (unsigned long long)cnt.nodes); atomicAdd(&wb.stats[3], (unsigned long long)cnt.tris); }
 }
 __global__ void k_count_closest(WavefrontBuffers wb, int queueSel) { atomicAdd(&wb.stats[0], (unsigned long long)wb.counters[queueSel]); }
 void launch_trace_closest(const FrameConst& fc, const WavefrontBuffers& wb, int queueSel, LaunchCfg lc) {
-    if (fc.scene.tuneSimple) {
+    if (fc.scene.tuneSimple && !fc.scene.hasMotion) {
         ClosestIO io{wb, queueSel ? wb.queueB : wb.queueA};
         k_trace_simple<false><<<lc.blocks, YRT_TRACE_THREADS, 0, lc.stream>>>(fc.scene, io, &wb.counters[queueSel], 0u, &wb.stats[7]);
         k_count_closest<<<1, 1, 0, lc.stream>>>(wb, queueSel);
         return;
     }
-    if (fc.countStats) k_trace_closest<true><<<lc.blocks, YRT_TRACE_THREADS, 0, lc.stream>>>(fc.scene, wb, queueSel);
-    else k_trace_closest<false><<<lc.blocks, YRT_TRACE_THREADS, 0, lc.stream>>>(fc.scene, wb, queueSel);
+    if (fc.scene.hasMotion) {
+        if (fc.countStats) k_trace_closest<true, true><<<lc.blocks, YRT_TRACE_THREADS, 0, lc.stream>>>(fc.scene, wb, queueSel);
+        else k_trace_closest<false, true><<<lc.blocks, YRT_TRACE_THREADS, 0, lc.stream>>>(fc.scene, wb, queueSel);
+    } else if (fc.countStats) k_trace_closest<true, false><<<lc.blocks, YRT_TRACE_THREADS, 0, lc.stream>>>(fc.scene, wb, queueSel);
+    else k_trace_closest<false, false><<<lc.blocks, YRT_TRACE_THREADS, 0, lc.stream>>>(fc.scene, wb, queueSel);
 }
 
-template <bool COUNT>
+template <bool COUNT, bool MOTION>
 __global__ void __launch_bounds__(YRT_TRACE_THREADS) k_trace_shadow(SceneData sc, WavefrontBuffers wb) {
     const uint32_t n = wb.counters[2];
     TraceCounters cnt = {0, 0, 0};
     ShadowIO io{wb};
-    trace_stream<true, COUNT>((const uint4*)sc.nodes, sc.tris, sc.numNodes, n, &wb.counters[5], io, cnt, TraceTune{sc.tuneRefillMin, sc.tuneTriNum, sc.tuneTriDen});
-    if (cnt.overflow) atomicOr(&wb.stats[7], 1ull);
+    trace_stream<true, COUNT, MOTION>((const uint4*)sc.nodes, sc.tris, sc.triMotion, sc.numNodes, n, &wb.counters[5], io, cnt, TraceTune{sc.tuneRefillMin, sc.tuneTriNum, sc.tuneTriDen});
     if (COUNT) { atomicAdd(&wb.stats[4], (unsigned long long)cnt.nodes); atomicAdd(&wb.stats[5], (unsigned long long)cnt.tris); }
 }
 void launch_trace_shadow(const FrameConst& fc, const WavefrontBuffers& wb, LaunchCfg lc) {
-    if (fc.scene.tuneSimple) { ShadowIO io{wb}; k_trace_simple<true><<<lc.blocks, YRT_TRACE_THREADS, 0, lc.stream>>>(fc.scene, io, &wb.counters[2], 0u, &wb.stats[7]); return; }
-    if (fc.countStats) k_trace_shadow<true><<<lc.blocks, YRT_TRACE_THREADS, 0, lc.stream>>>(fc.scene, wb);
-    else k_trace_shadow<false><<<lc.blocks, YRT_TRACE_THREADS, 0, lc.stream>>>(fc.scene, wb);
+    if (fc.scene.tuneSimple && !fc.scene.hasMotion) { ShadowIO io{wb}; k_trace_simple<true><<<lc.blocks, YRT_TRACE_THREADS, 0, lc.stream>>>(fc.scene, io, &wb.counters[2], 0u, &wb.stats[7]); return; }
+    if (fc.scene.hasMotion) {
+        if (fc.countStats) k_trace_shadow<true, true><<<lc.blocks, YRT_TRACE_THREADS, 0, lc.stream>>>(fc.scene, wb);
+        else k_trace_shadow<false, true><<<lc.blocks, YRT_TRACE_THREADS, 0, lc.stream>>>(fc.scene, wb);
+    } else if (fc.countStats) k_trace_shadow<true, false><<<lc.blocks, YRT_TRACE_THREADS, 0, lc.stream>>>(fc.scene, wb);
+    else k_trace_shadow<false, false><<<lc.blocks, YRT_TRACE_THREADS, 0, lc.stream>>>(fc.scene, wb);
 }
 
 template <bool ANY, bool COUNT>
 __global__ void __launch_bounds__(YRT_TRACE_THREADS) k_trace_user(SceneData sc, const float4* __restrict__ rays, float4* __restrict__ hits, uint32_t n,
                                                                   uint32_t* workCounter, unsigned long long* stats) {
     TraceCounters cnt = {0, 0, 0};
-    UserIO io{rays, hits};
-    trace_stream<ANY, COUNT>((const uint4*)sc.nodes, sc.tris, sc.numNodes, n, workCounter, io, cnt, TraceTune{sc.tuneRefillMin, sc.tuneTriNum, sc.tuneTriDen});
-    if (cnt.overflow && stats) atomicOr(&stats[7], 1ull);
+    UserIO io{rays, hits, stats ? stats + 7 : nullptr};
+    trace_stream<ANY, COUNT, false>((const uint4*)sc.nodes, sc.tris, nullptr, sc.numNodes, n, workCounter, io, cnt, TraceTune{sc.tuneRefillMin, sc.tuneTriNum, sc.tuneTriDen});
     if (COUNT && stats) { atomicAdd(&stats[2], (unsigned long long)cnt.nodes); atomicAdd(&stats[3], (unsigned long long)cnt.tris); }
 }
 void launch_trace_user(const SceneData& sc, const float* rays, float* hits, size_t n, int closest, int countStats,
                        unsigned long long* stats, uint32_t* workCounter, LaunchCfg lc) {
     const float4* r = (const float4*)rays; float4* h = (float4*)hits; const uint32_t m = (uint32_t)n;
     if (sc.tuneSimple) {
-        UserIO io{r, h};
+        UserIO io{r, h, stats ? stats + 7 : nullptr};
         if (closest) k_trace_simple<false><<<lc.blocks, YRT_TRACE_THREADS, 0, lc.stream>>>(sc, io, nullptr, m, stats + 7);
         else k_trace_simple<true><<<lc.blocks, YRT_TRACE_THREADS, 0, lc.stream>>>(sc, io, nullptr, m, stats + 7);
         return;
@@ -371,7 +383,7 @@ __global__ void __launch_bounds__(YRT_SHADE_THREADS, EXT ? 4 : YRT_SHADE_MINBLOC
                     for (int e = 0; e < sc.numEnvLights; e++) L += thr * env_Le(sc, sc.lights[sc.envLightIdx[e]], wo);
                 }
             } else {
-                post_intersect<EXT>(sc, org, dir, hA.x, hA.y, hA.z, triIdx, dg);
+                post_intersect<EXT>(sc, org, dir, hA.x, hA.y, hA.z, triIdx, sc.hasMotion ? rec[2] : 0.f, dg);
                 bool backfacing = false;
                 if (dot(dg.Ng, dir) > 0.f) { backfacing = true; dg.Ng = -dg.Ng; dg.Ns = -dg.Ns; }   // :95-98
                 if (dg.material >= 0) material_shade<EXT>(sc, sc.materials[dg.material], dg, Col(m4.x, m4.y, m4.z), m4.w, lobes);
@@ -403,7 +415,7 @@ __global__ void __launch_bounds__(YRT_SHADE_THREADS, EXT ? 4 : YRT_SHADE_MINBLOC
             if (ok) { brdf = lobes_eval(lobes, wo, dg, ls.wi, BR_DIFFUSE); ok = !(brdf == Col(0.f)); }
             if (!ok) {
                 wb.shO[slot] = make_float4(0.f, 0.f, 0.f, 1.f); wb.shD[slot] = make_float4(0.f, 0.f, 1.f, -1.f);
-                wb.shC[slot] = make_float4(0.f, 0.f, 0.f, 1.f);
+                wb.shC[slot] = make_float4(0.f, 0.f, 0.f, 1.f);   // empty interval: retired as "not occluded" -> w = 0 with a zero contribution
                 continue;
             }
             // dome-light shadow-ray length (pathtraceintegrator.cpp:147-158) with the stated pins P1/P2
@@ -421,7 +433,7 @@ __global__ void __launch_bounds__(YRT_SHADE_THREADS, EXT ? 4 : YRT_SHADE_MINBLOC
             const Col contrib = thr * lL * brdf * rcpf(ls.pdf);
             wb.shO[slot] = make_float4(dg.P.x, dg.P.y, dg.P.z, eps);
             wb.shD[slot] = make_float4(ls.wi.x, ls.wi.y, ls.wi.z, tMax - eps);
-            wb.shC[slot] = make_float4(contrib.x, contrib.y, contrib.z, 1.f);
+            wb.shC[slot] = make_float4(contrib.x, contrib.y, contrib.z, sc.hasMotion ? rec[2] : 1.f);   // w: the ray's time in, the occlusion flag out
             shadowRays++;
         }
         if (nl) wb.shadowPid[base / nl] = pid;                // slots are claimed in groups of numLights: base is a multiple of nl
@@ -460,6 +472,7 @@ __global__ void __launch_bounds__(YRT_SHADE_THREADS, EXT ? 4 : YRT_SHADE_MINBLOC
                     wb.rayD[pid] = make_float4(smp.v.x, smp.v.y, smp.v.z, INFINITY);
                     wb.thr[pid] = make_float4(nthr.x, nthr.y, nthr.z, __uint_as_float(nflags << 16));
                     if (sc.hasMedia) wb.medium[pid] = m4;
+                    if (sc.hasMotion) wb.hitA[pid] = make_float4(rec[2], 0.f, 0.f, 0.f);      // lastRay.time rides on (pathtraceintegrator.cpp:210)
                     if (reduce_max(nthr) < ig.minContribution) cont = false;     // loop-top test of the next bounce (:66)
                 }
             }

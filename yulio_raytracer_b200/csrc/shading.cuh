@@ -58,7 +58,7 @@ struct DG { V3 P, Ng, Ns; float s, t, error; int material, areaLight, illumMask,
 // a bump-mapped Obj are the materials that read them. Per-vertex tangent arrays ("tangent_x" / "tangent_y") are interpolated unnormalised
 // like the reference does (:253-256, :263-266); without them the tangents come from the positions and texture coordinates.
 template <bool EXT>
-YRT_D void post_intersect(const SceneData& sc, V3 org, V3 dir, float t, float u, float v, int triIdx, DG& dg) {
+YRT_D void post_intersect(const SceneData& sc, V3 org, V3 dir, float t, float u, float v, int triIdx, float time, DG& dg) {
     // one 80-byte record per leaf-order triangle (bvh_build.cu: write_triangle) replaces geometry record -> indices -> 3 vertices
     const float4* h = sc.triShade + 5ull * (uint32_t)triIdx;
     const float4 r0 = __ldg(h), r1 = __ldg(h + 1), r2 = __ldg(h + 2), r3 = __ldg(h + 3), r4 = __ldg(h + 4);
@@ -68,6 +68,20 @@ YRT_D void post_intersect(const SceneData& sc, V3 org, V3 dir, float t, float u,
     dg.P = org + t * dir;
     dg.Ng = V3(r0.x, r0.y, r0.z);                               // normalize(ray.Ng), or Triangle::Ng for a triangle shape
     if (EXT) { dg.Tx = V3(0.f); dg.Ty = V3(0.f); }
+    // a moving triangle (trianglemesh_full.cpp:211-215): ray.Ng came from the vertices at the ray's time, so does the geometric normal here
+    V3 m0(0.f), m1(0.f), m2(0.f); bool moving = false;
+    if (sc.hasMotion) {
+        const float4* tp = sc.tris + 3ull * (uint32_t)triIdx;
+        const float4 q2 = __ldg(tp + 2);
+        if (__float_as_uint(q2.w) & 2u) {                       // YRT_TRI_FLAG_MOTION
+            moving = true;
+            const float4 q0 = __ldg(tp), q1 = __ldg(tp + 1);
+            const float4* mp = sc.triMotion + 3ull * (uint32_t)triIdx;
+            const float4 d0 = __ldg(mp), d1 = __ldg(mp + 1), d2 = __ldg(mp + 2);
+            m0 = V3(q0.x, q0.y, q0.z) + time * V3(d0.x, d0.y, d0.z); m1 = V3(q1.x, q1.y, q1.z) + time * V3(d1.x, d1.y, d1.z); m2 = V3(q2.x, q2.y, q2.z) + time * V3(d2.x, d2.y, d2.z);
+            dg.Ng = normalize(cross(m0 - m1, m2 - m0));
+        }
+    }
     const float w = 1.0f - u - v;
     if (flags & 2u) { dg.s = r1.w * w + r3.w * u + r4.y * v; dg.t = r2.w * w + r4.x * u + r4.z * v; }
     else { dg.s = u; dg.t = v; }
@@ -81,7 +95,7 @@ YRT_D void post_intersect(const SceneData& sc, V3 org, V3 dir, float t, float u,
     if (EXT && g.type != MESH_TRIANGLE) {
         const float4* tp = sc.tris + 3ull * (uint32_t)triIdx;
         const float4 q0 = __ldg(tp), q1 = __ldg(tp + 1), q2 = __ldg(tp + 2);
-        const V3 p0(q0.x, q0.y, q0.z), dPdu = V3(q1.x, q1.y, q1.z) - p0, dPdv = V3(q2.x, q2.y, q2.z) - p0;
+        const V3 p0 = moving ? m0 : V3(q0.x, q0.y, q0.z), dPdu = (moving ? m1 : V3(q1.x, q1.y, q1.z)) - p0, dPdv = (moving ? m2 : V3(q2.x, q2.y, q2.z)) - p0;
         if (g.type == MESH_NORMALS) { dg.Tx = dPdu; dg.Ty = dPdv; }
         else {
             float dsdu = 1.f, dtdu = 0.f, dsdv = 0.f, dtdv = 1.f;
