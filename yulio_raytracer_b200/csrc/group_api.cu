@@ -278,7 +278,7 @@ void* yrtMapFrameBuffer(yrt_device* dev, yrt_handle fb, int bufID) {
         yrt_device* m0 = dev->members[0];
         YRT_CK(cudaMemcpyAsync(out, full, g->height * g->strideBytes, cudaMemcpyDeviceToHost, m0->stream));    // the ONE host copy of the frame
         YRT_CK(cudaStreamSynchronize(m0->stream));
-        g->hostCopies++;
+        g->hostCopies++; dev->stats.d2h_bytes += g->height * g->strideBytes;
         return out;
     } catch (const std::exception& e) { fail(e); return nullptr; }
 }
@@ -329,6 +329,7 @@ yrt_status yrtRenderFrame(yrt_device* dev, yrt_handle renderer, yrt_handle camer
     try {
         gh(renderer); gh(camera); gh(scene); gh(tonemapper); gh(fb);
         std::lock_guard<std::mutex> lock(dev->mutex);
+        dev->stats.d2h_bytes = 0;
         return each_parallel(dev, [&](yrt_device* m, int i) {
             return yrtRenderFrame_core(m, un(renderer, i), un(camera, i), un(scene, i), un(tonemapper, i), un(fb, i), accumulate); });
     } catch (const std::exception& e) { return fail(e); }
@@ -341,6 +342,7 @@ yrt_status yrtxRenderCubeMap(yrt_device* dev, yrt_handle renderer, const yrt_han
         gh(renderer); gh(scene); gh(tonemapper);
         for (size_t f = 0; f < numFaces; f++) { gh(cameras[f]); gh(fbs[f]); }
         std::lock_guard<std::mutex> lock(dev->mutex);
+        dev->stats.d2h_bytes = 0;
         return each_parallel(dev, [&](yrt_device* m, int i) {
             yrt_handle c[YRT_MAX_FACES], b[YRT_MAX_FACES];
             for (size_t f = 0; f < numFaces; f++) { c[f] = un(cameras[f], i); b[f] = un(fbs[f], i); }
@@ -368,6 +370,7 @@ yrt_status yrtxGetFrameStats(yrt_device* dev, yrtx_frame_stats* out) {
         a.tri_tests += s.tri_tests; a.closest_launches += s.closest_launches; a.shadow_launches += s.shadow_launches; a.h2d_bytes += s.h2d_bytes; a.d2h_bytes += s.d2h_bytes;
     }
     a.num_gpus = (uint32_t)dev->members.size();
+    a.d2h_bytes += dev->stats.d2h_bytes;               // frames the group itself copied to the host (yrtMapFrameBuffer) since the last render call
     *out = a;
     return YRT_OK;
 }
