@@ -6,6 +6,7 @@
 
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <stdexcept>
 #include <vector>
 
@@ -30,7 +31,20 @@ int main(int argc, char** argv) try {
     std::vector<Device::RTPrimitive> prims;
     const float colors[2][3] = {{0.8f, 0.8f, 0.8f}, {0.8f, 0.1f, 0.1f}};
     for (int m = 0; m < 2; m++) {
-        Device::RTData dp = dev->rtNewData("immutable", 48, pos + 12 * m), di = dev->rtNewData("immutable", sizeof(idx), idx);
+        // the second mesh hands its positions over as "immutable_managed", allocated the way the reference's loaders do it: an interior
+        // pointer from embree::alignedMalloc (xml_loader.cpp:227-267, common/sys/platform.cpp:171-181). The device must release it with the
+        // alignedFree convention — plain free() on this pointer corrupts the heap (glibc aborts) — and must have copied it by then.
+        Device::RTData dp;
+        if (m == 1) {
+            const size_t bytes = 48, align = 64;
+            char* base = (char*)malloc(bytes + align + sizeof(int));
+            char* unaligned = base + sizeof(int);
+            char* aligned = unaligned + align - ((size_t)unaligned & (align - 1));
+            ((int*)aligned)[-1] = (int)((size_t)aligned - (size_t)base);
+            memcpy(aligned, pos + 12, bytes);
+            dp = dev->rtNewData("immutable_managed", bytes, aligned);
+        } else dp = dev->rtNewData("immutable", 48, pos);
+        Device::RTData di = dev->rtNewData("immutable", sizeof(idx), idx);
         Device::RTShape mesh = dev->rtNewShape("trianglemesh");
         dev->rtSetArray(mesh, "positions", "float3", dp, 4, 12, 0);
         dev->rtSetArray(mesh, "indices", "int3", di, 2, 12, 0);
