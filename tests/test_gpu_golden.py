@@ -284,7 +284,7 @@ def test_plugin_boundary_with_a_reference_side_caller():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("cfg", ["chunk=4096", "bvh=0", "splitleaves=0", "syncmin=0", "syncmin=1000000000", "trav=0", "sort=1,sortmin=1",
+@pytest.mark.parametrize("cfg", ["chunk=4096", "bvh=0", "splitleaves=0", "collapse=0", "collapse=1,ctri=20", "collapse=1,ctri=300", "bvh=0,collapse=0", "lanes=2", "syncmin=0", "syncmin=1000000000", "trav=0", "sort=1,sortmin=1",
                                  "refill=1,trinum=1,triden=4", "shadectas=3,tracectas=2"])
 def test_frame_is_independent_of_scheduling_and_acceleration_structure(cuda_dev, cfg):
     """Radiance is accumulated per path in the reference's order and hits are the (t, geomID, primID) minimum, so the frame must be

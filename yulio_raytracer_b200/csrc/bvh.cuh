@@ -163,6 +163,9 @@ struct TraceCounters { uint32_t nodes, tris; uint32_t overflow; };   // overflow
 #ifndef YRT_STREAM_HINTS
 #define YRT_STREAM_HINTS 1
 #endif
+#ifndef YRT_TRI_BATCH
+#define YRT_TRI_BATCH 0
+#endif
 YRT_D uint64_t bvh_policy() {
 #if YRT_BVH_EVICT_LAST
     uint64_t p; asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p)); return p;
@@ -273,6 +276,10 @@ template <bool ANY, bool COUNT, bool MOTION, class IO>
 YRT_D void trace_stream(const uint4* __restrict__ nodes, const float4* __restrict__ tris, const float4* __restrict__ triMotion, uint32_t numNodes,
                         uint32_t n, uint32_t* __restrict__ workCounter, IO io, TraceCounters& cnt, const TraceTune tune) {
     __shared__ uint2 smStack[YRT_SM_STACK * YRT_TRACE_THREADS];
+#if YRT_TRI_BATCH
+    __shared__ uint32_t smTriList[YRT_TRACE_THREADS / 32][32];      // owner lane << 27 | leaf-order triangle index (< 2^27)
+    __shared__ float4 smTriRes[YRT_TRACE_THREADS / 32][32];         // (t, u, v, triangle) of an accepted candidate, t = +inf otherwise
+#endif
     uint2 lstack[YRT_STACK_SIZE - YRT_SM_STACK];
     const unsigned FULL = 0xffffffffu;
     const unsigned lane = threadIdx.x & 31u, ltmask = (1u << lane) - 1u;
@@ -332,6 +339,80 @@ YRT_D void trace_stream(const uint4* __restrict__ nodes, const float4* __restric
         const int nN = __popc(__ballot_sync(FULL, nodeWork)), nT = __popc(__ballot_sync(FULL, triWork));
 
         if (nT != 0 && (nN == 0 || tune.triNum * nT >= tune.triDen * nN)) {
+#if YRT_TRI_BATCH
+            // ---- TRIANGLE phase, batched across the warp's rays --------------------------------------------
+            // The pending triangles of all participating lanes go into a shared-memory work list (prefix sum over the per-lane counts);
+            // the 32 lanes then test 32 list entries at a time, each fetching the owner's ray with shuffles, and write (t, u, v, triangle)
+            // back; every owner finally folds its own entries in list order. A lane with three pending triangles no longer needs three
+            // rounds of this phase with two thirds of the warp idle (ncu r2: the phase ran with 4-9 of 32 lanes). The result does not depend
+            // on the order: acceptance is the (t, geomID, primID) minimum / any accepted hit.
+            {
+                const uint32_t wid = threadIdx.x >> 5;
+                const uint32_t pend = triWork ? T.y : 0u;
+                const uint32_t myCnt = __popc(pend);
+                uint32_t incl = myCnt;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(FULL, incl, o); if (lane >= (uint32_t)o) incl += v; }
+                const uint32_t total = __shfl_sync(FULL, incl, 31), myOff = incl - myCnt;
+                for (uint32_t base = 0; base < total; base += 32u) {              // warp-uniform
+                    {   // owners publish their entries that fall into [base, base + 32)
+                        uint32_t tmp = pend, idx = myOff;
+                        while (tmp) {
+                            const uint32_t bit = 31u - __clz(tmp); tmp &= ~(1u << bit);
+                            if (idx >= base && idx < base + 32u) smTriList[wid][idx - base] = ((T.x + bit) & 0x07ffffffu) | (lane << 27);
+                            idx++;
+                        }
+                    }
+                    __syncwarp();
+                    const bool mine = base + lane < total;
+                    const uint32_t entry = mine ? smTriList[wid][lane] : (lane << 27);
+                    const uint32_t owner = entry >> 27, triIdx = entry & 0x07ffffffu;
+                    const float ox = __shfl_sync(FULL, r.O.x, owner), oy = __shfl_sync(FULL, r.O.y, owner), oz = __shfl_sync(FULL, r.O.z, owner);
+                    const float dx = __shfl_sync(FULL, r.D.x, owner), dy = __shfl_sync(FULL, r.D.y, owner), dz = __shfl_sync(FULL, r.D.z, owner);
+                    const float otn = __shfl_sync(FULL, tnear, owner), otb = __shfl_sync(FULL, tbest, owner);
+                    float otime = 0.f; if (MOTION) otime = __shfl_sync(FULL, time, owner);
+                    float4 res = make_float4(INFINITY, 0.f, 0.f, 0.f);
+                    if (mine) {
+                        const float4* tp = tris + 3ull * triIdx;
+                        const float4 a = bvh_ld(tp, pol), b = bvh_ld(tp + 1, pol), c = bvh_ld(tp + 2, pol);
+                        if (COUNT) cnt.tris++;
+                        V3 p0(a.x, a.y, a.z), p1(b.x, b.y, b.z), p2(c.x, c.y, c.z);
+                        if (MOTION && (__float_as_uint(c.w) & YRT_TRI_FLAG_MOTION)) {
+                            const float4* mp = triMotion + 3ull * triIdx;
+                            const float4 d0 = __ldg(mp), d1 = __ldg(mp + 1), d2 = __ldg(mp + 2);
+                            p0 = p0 + otime * V3(d0.x, d0.y, d0.z); p1 = p1 + otime * V3(d1.x, d1.y, d1.z); p2 = p2 + otime * V3(d2.x, d2.y, d2.z);
+                        }
+                        float t, u, v, den; V3 Ng;
+                        // candidates beyond the owner's current best cannot win (ties, t == best, are decided by the owner)
+                        if (tri_test(V3(ox, oy, oz), V3(dx, dy, dz), p0, p1, p2, t, u, v, Ng, den) && t > otn && (ANY ? t < otb : t <= otb) &&
+                            !((__float_as_uint(c.w) & YRT_TRI_FLAG_CULL) && den <= 0.f)) res = make_float4(t, u, v, __uint_as_float(triIdx));
+                    }
+                    smTriRes[wid][lane] = res;
+                    __syncwarp();
+                    if (myCnt) {                                                   // owners fold their entries of this window, in list order
+                        const uint32_t lo = myOff > base ? myOff : base, hi = (myOff + myCnt < base + 32u) ? myOff + myCnt : base + 32u;
+                        for (uint32_t i = lo; i < hi; i++) {
+                            const float4 q = smTriRes[wid][i - base];
+                            if (!(q.x < INFINITY) || (ANY && occluded)) continue;
+                            const uint32_t qTri = __float_as_uint(q.w);
+                            bool closer = q.x < tbest;
+                            if (!ANY && !closer && bestTri != YRT_NO_TRI && q.x == tbest) {      // tie: (geomID, primID) ascending
+                                const int g = __float_as_int(__ldg(tris + 3ull * qTri).w), pr = __float_as_int(__ldg(tris + 3ull * qTri + 1).w);
+                                const int bg = __float_as_int(__ldg(tris + 3ull * bestTri).w), bp = __float_as_int(__ldg(tris + 3ull * bestTri + 1).w);
+                                closer = (g < bg) || (g == bg && pr < bp);
+                            }
+                            if (ANY) closer = true;                                    // any accepted candidate inside (tnear, tfar] occludes
+                            if (closer) {
+                                tbest = q.x; bt = q.x; bu = q.y; bv = q.z; bestTri = qTri;
+                                if (ANY) { occluded = true; G.y = 0u; sp = 0; }
+                            }
+                        }
+                    }
+                    __syncwarp();
+                }
+                if (triWork) T.y = 0u;
+            }
+#else
             // ---- TRIANGLE phase: one triangle per participating lane -------------------------------------
             if (triWork) {
                 const uint32_t bit = 31u - __clz(T.y);
@@ -361,6 +442,7 @@ YRT_D void trace_stream(const uint4* __restrict__ nodes, const float4* __restric
                     }
                 }
             }
+#endif
         } else if (nN != 0) {
             // ---- NODE phase: one compressed node per participating lane --------------------------------
             if (nodeWork) {

@@ -130,6 +130,7 @@ struct yrt_device {
     int countStats = 0, verbose = 0, alwaysRebuild = 0, useTimers = 1;
     int tuneRefillMin = 8, tuneTriNum = 3, tuneTriDen = 1, tuneSimple = 0;
     int shadeCtas = 6, traceCtas = 8;
+    int bvhCollapseDp = 1; float bvhCTri = 0.6f;              // cfg collapse=0|1, ctri=<percent>: SAH-optimal BVH8 collapse and its triangle cost
     int bvhPloc = 1, plocRadius = 8, splitLeaves = 1;           // cfg bvh=0 selects the Karras LBVH hierarchy (A/B), plocr the PLOC search radius
     uint32_t syncMinPaths = 1u << 20;          // cfg syncmin=: per-bounce queue-length read-back only while at least this many paths are alive
     int sortRays = 0; uint32_t sortMin = 1u << 16;   // cfg sort=0|1: re-order bounce queues of at least sortMin rays (sort.cu); measured slower, off

@@ -22,6 +22,8 @@ struct BvhBuildInput {
     int ploc = 1;                 // 1: PLOC hierarchy (default), 0: Karras LBVH
     int splitLeaves = 1;          // BVH8 collapse: use free child slots to split leaf children of 2-3 triangles
     int plocRadius = 8;           // PLOC neighbour search radius (positions to either side)
+    int dpCollapse = 1;           // BVH8 collapse: 1 = SAH-optimal cut by dynamic programming (k_collapse_dp), 0 = greedy largest-area opening
+    float cTri = 0.6f;            // DP cost of one triangle test relative to one node visit
 };
 struct BvhResult {
     void* nodes; float4* tris; float4* triShade; float4* triMotion; uint32_t numNodes, numTris; float buildMs; uint32_t launches;

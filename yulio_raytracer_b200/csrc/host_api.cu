@@ -462,6 +462,7 @@ yrt_device* yrtCreateDevice(const char* parms, size_t numThreads, int threadsPri
         dev->shadeCtas = (int)cfg_int(cfg, "shadectas", YRT_SHADE_MINBLOCKS); dev->traceCtas = (int)cfg_int(cfg, "tracectas", 8);
         dev->syncMinPaths = (uint32_t)cfg_int(cfg, "syncmin", dev->syncMinPaths);
         dev->bvhPloc = (int)cfg_int(cfg, "bvh", 1); dev->plocRadius = (int)cfg_int(cfg, "plocr", dev->plocRadius); dev->splitLeaves = (int)cfg_int(cfg, "splitleaves", 1);
+        dev->bvhCollapseDp = (int)cfg_int(cfg, "collapse", 1); dev->bvhCTri = 0.01f * (float)cfg_int(cfg, "ctri", 60);
         dev->sortRays = (int)cfg_int(cfg, "sort", 0); dev->sortMin = (uint32_t)cfg_int(cfg, "sortmin", 1l << 16);
         YRT_CK(cudaHostAlloc((void**)&dev->hostCounters, 16 * sizeof(uint32_t), cudaHostAllocDefault));
         if (dev->tuneRefillMin < 1) dev->tuneRefillMin = 1; if (dev->tuneRefillMin > 32) dev->tuneRefillMin = 32;

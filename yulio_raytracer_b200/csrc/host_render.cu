@@ -18,6 +18,7 @@
 
 #include "device_impl.hpp"
 #include "host_math.hpp"
+#include "bvh.cuh"
 
 namespace yrt {
 
@@ -251,7 +252,7 @@ void scene_commit(yrt_device* dev, SceneHandle* sc) {
         sc->patchSlots.clear();
         // the old BVH is released only once the new one exists; a failed build leaves the scene uncommitted (never dangling pointers)
         BvhBuildInput in{sc->refsBuf.p, sc->numRefs, sc->geoms.p, sc->positions.p, sc->indices.p, sc->normals.p, sc->uvs.p, sc->data.hasMotion ? sc->motions.p : nullptr,
-                         dev->hostCounters + 8, dev->bvhPloc, dev->splitLeaves, dev->plocRadius};
+                         dev->hostCounters + 8, dev->bvhPloc, dev->splitLeaves, dev->plocRadius, dev->bvhCollapseDp, dev->bvhCTri};
         BvhResult out{};
         try { build_bvh(in, out, st); }
         catch (...) { sc->releaseDevice(); sc->committed = false; sc->structureDirty = true; sc->data.nodes = nullptr; sc->data.tris = nullptr; sc->data.triShade = nullptr; sc->data.triMotion = nullptr; sc->data.numNodes = sc->data.numTris = 0; throw; }
@@ -391,11 +392,12 @@ void scene_commit(yrt_device* dev, SceneHandle* sc) {
     sc->releaseDevice();
     sc->data.nodes = nullptr; sc->data.tris = nullptr; sc->data.triShade = nullptr; sc->data.numNodes = sc->data.numTris = 0;
     BvhBuildInput in{dRefs.p, (uint32_t)refs.size(), sc->geoms.p, sc->positions.p, sc->indices.p, sc->normals.p, sc->uvs.p, motions.empty() ? nullptr : sc->motions.p,
-                     dev->hostCounters + 8, dev->bvhPloc, dev->splitLeaves, dev->plocRadius};
+                     dev->hostCounters + 8, dev->bvhPloc, dev->splitLeaves, dev->plocRadius, dev->bvhCollapseDp, dev->bvhCTri};
     BvhResult out{};
     sc->structureDirty = true;                                // a throw below leaves a scene that re-flattens on the next commit
     build_bvh(in, out, st);
     YRT_CK(cudaStreamSynchronize(st));
+    if (YRT_TRI_BATCH && out.numTris >= (1u << 27)) throw std::runtime_error("device_cuda: the batched triangle phase addresses 2^27 triangles per scene");
     sc->structureDirty = false;
     lap("bvh");
     sc->nodes = out.nodes; sc->tris = out.tris; sc->triShade = out.triShade; sc->triMotion = out.triMotion; sc->buildMs = out.buildMs; sc->buildLaunches = out.launches; sc->rebuildCount++;

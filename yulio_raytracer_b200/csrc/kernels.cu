@@ -217,8 +217,13 @@ void launch_trace_closest(const FrameConst& fc, const WavefrontBuffers& wb, int 
     else k_trace_closest<false, false><<<lc.blocks, YRT_TRACE_THREADS, 0, lc.stream>>>(fc.scene, wb, queueSel);
 }
 
+#ifdef YRT_SHADOW_MINBLOCKS
+#define YRT_SHADOW_BOUNDS __launch_bounds__(YRT_TRACE_THREADS, YRT_SHADOW_MINBLOCKS)
+#else
+#define YRT_SHADOW_BOUNDS __launch_bounds__(YRT_TRACE_THREADS)      // 64 registers without a bound: 8 CTAs/SM
+#endif
 template <bool COUNT, bool MOTION>
-__global__ void __launch_bounds__(YRT_TRACE_THREADS) k_trace_shadow(SceneData sc, WavefrontBuffers wb) {
+__global__ void YRT_SHADOW_BOUNDS k_trace_shadow(SceneData sc, WavefrontBuffers wb) {
     const uint32_t n = wb.counters[2];
     TraceCounters cnt = {0, 0, 0};
     ShadowIO io{wb};
