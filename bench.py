@@ -354,6 +354,7 @@ def main():
         config["partition"] = f"4-row bands round-robin over {in_process} GPUs of one process (group device), scene replicated"
     dev = Device.cuda(cfg=(f"gpus={in_process}" if in_process > 1 else f"gpu={local_rank},serverID={rank},serverCount={world}") + ("," + args.cfg if args.cfg else ""))
     s = build_workload(dev, args.workload, size, spp, depth, "RGB8")
+    st_build = dev.frame_stats()                           # the scene commit above: the GPU BVH build (Morton sort, PLOC, SAH-optimal BVH8 collapse)
     cams = make_cameras(dev, s, faces)
     fbs = [s.framebuffer] + [dev.rtNewFrameBuffer("RGB8", size, size, 1) for _ in range(len(cams) - 1)]
     stride = (3 * size + 3) // 4 * 4
@@ -547,6 +548,9 @@ def main():
                                   "raygen_film": agg["rf_ms"] / args.steps, "sort": agg["sort_ms"] / args.steps, "gather": agg["gather_ms"] / args.steps},
             "stage_ms_note": "sums of CUDA-event spans per kernel kind; launches are serialised on one stream (cfg lanes=1, the default)",
             "stage_ms_single_lane": ({k: ser[k] for k in ("ms", "closest_ms", "shadow_ms", "shade_ms", "resolve_ms", "rf_ms")} if ser else None),
+            "bvh_build": {"ms": st_build.build_ms, "triangles": int(st_build.num_triangles), "nodes": int(st_build.num_nodes),
+                          "mtris_per_s": (st_build.num_triangles / st_build.build_ms / 1e3) if st_build.build_ms > 0 else None,
+                          "note": "first scene commit of the process (CUDA-event time; includes the growth of the stream-ordered memory pool)"},
             "traversal": nbar, "rays_per_step": rays_total / args.steps, "wall_s_timed_region": wall_dev}
     if not args.no_cpu_baseline and world == 1:
         r = cpu_reference(args.workload, 3, 1)

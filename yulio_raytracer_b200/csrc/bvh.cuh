@@ -267,7 +267,12 @@ YRT_D bool trace_ray(const uint4* __restrict__ nodes, const float4* __restrict__
 #define YRT_REFILL_MIN 8
 #define YRT_NO_TRI 0xffffffffu
 
-struct TraceTune { int refillMin; int triNum; int triDen; };   // refill when >= refillMin slots idle; triangle phase when triNum*nT >= triDen*nN
+// refill when >= refillMin slots idle; triangle phase when triNum*nT >= triDen*nN; prefetch (cfg prefetch=1, off by default): after a node test,
+// pull every hit inner child and the first pending triangle towards L2. Meant for scenes whose BVH exceeds L2 (BASELINE config 5: a dependent chain of
+// ~50 node fetches per ray). Measured r2 (profiles/README.md): slower at every size — 1e6 triangles 7182 -> 1888 Mrays/s, 1e7 2981 -> 2063,
+// 1e8 (5.9 GB of BVH) 978 -> 827, C4 3272 -> 2193: the prefetch instructions cost more than the latency they hide
+struct TraceTune { int refillMin; int triNum; int triDen; int prefetch; };
+YRT_D void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" :: "l"(p)); }
 
 // MOTION (scenes with moving meshes only): every ray carries its time (IO::time), a triangle flagged YRT_TRI_FLAG_MOTION is moved to
 // p + time * d before the test — a multiply and an add per component, as the oracle's shim does (embree2_shim.cpp) — for the test, the
@@ -467,6 +472,16 @@ YRT_D void trace_stream(const uint4* __restrict__ nodes, const float4* __restric
                 const uint32_t hm = node_test(n0, n1, n2, n3, n4, r, tnear, tbest);
                 G = make_uint2(n1.x, (hm & 0xff000000u) | (n0.w >> 24));
                 T = make_uint2(n1.y, hm & 0x00ffffffu);
+                if (tune.prefetch) {
+                    uint32_t m = G.y >> 24;
+                    while (m) {
+                        const uint32_t b2 = 31u - __clz(m); m &= ~(1u << b2);
+                        const uint32_t sl = b2 ^ r.octinv;
+                        const char* cp = (const char*)(nodes + 5ull * (G.x + __popc((G.y & 0xffu) & ~(0xffffffffu << sl))));
+                        prefetch_l2(cp); prefetch_l2(cp + 64);
+                    }
+                    if (T.y) prefetch_l2(tris + 3ull * (T.x + (31u - __clz(T.y))));
+                }
             }
         }
 

@@ -203,7 +203,7 @@ struct LightRec {
 };
 
 struct SceneData {
-    int tuneRefillMin, tuneTriNum, tuneTriDen, tuneSimple;
+    int tuneRefillMin, tuneTriNum, tuneTriDen, tuneSimple, tunePrefetch;
     V3 bboxLo, bboxRcpExtent;    // scene bounds (ray-sort keys): cell = (P - bboxLo) * bboxRcpExtent in [0,1]^3   // traversal scheduling knobs (bvh.cuh: TraceTune)
     // acceleration structure
     const void* nodes;           // BVH8 nodes, 80 B each (bvh.cuh)

@@ -129,6 +129,8 @@ struct yrt_device {
     uint32_t chunkPaths = 1u << 26;      // paths per wavefront pass: whole faces where memory allows (launch tails dominate small chunks)
     int countStats = 0, verbose = 0, alwaysRebuild = 0, useTimers = 1;
     int tuneRefillMin = 8, tuneTriNum = 3, tuneTriDen = 1, tuneSimple = 0;
+    int tunePrefetch = 0;                      // cfg prefetch=0|1 (bvh.cuh: TraceTune; measured slower, off)
+    size_t l2Bytes = 0;
     int shadeCtas = 6, traceCtas = 8;
     int bvhCollapseDp = 1; float bvhCTri = 0.6f;              // cfg collapse=0|1, ctri=<percent>: SAH-optimal BVH8 collapse and its triangle cost
     int bvhPloc = 1, plocRadius = 8, splitLeaves = 1;           // cfg bvh=0 selects the Karras LBVH hierarchy (A/B), plocr the PLOC search radius

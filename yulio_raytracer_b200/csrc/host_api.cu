@@ -440,7 +440,7 @@ yrt_device* yrtCreateDevice(const char* parms, size_t numThreads, int threadsPri
         cudaDeviceProp prop; YRT_CK(cudaGetDeviceProperties(&prop, gpu));
         if (prop.major < 10) throw std::runtime_error(std::string("device_cuda is built for sm_100a only; found ") + prop.name);
         auto* dev = new yrt_device();
-        dev->gpu = gpu; dev->numSMs = prop.multiProcessorCount;
+        dev->gpu = gpu; dev->numSMs = prop.multiProcessorCount; dev->l2Bytes = (size_t)prop.l2CacheSize;
         YRT_CK(cudaSetDevice(gpu));
         YRT_CK(cudaStreamCreateWithFlags(&dev->stream, cudaStreamNonBlocking));
         YRT_CK(cudaStreamCreateWithFlags(&dev->stream1, cudaStreamNonBlocking));
@@ -462,6 +462,7 @@ yrt_device* yrtCreateDevice(const char* parms, size_t numThreads, int threadsPri
         dev->shadeCtas = (int)cfg_int(cfg, "shadectas", YRT_SHADE_MINBLOCKS); dev->traceCtas = (int)cfg_int(cfg, "tracectas", 8);
         dev->syncMinPaths = (uint32_t)cfg_int(cfg, "syncmin", dev->syncMinPaths);
         dev->bvhPloc = (int)cfg_int(cfg, "bvh", 1); dev->plocRadius = (int)cfg_int(cfg, "plocr", dev->plocRadius); dev->splitLeaves = (int)cfg_int(cfg, "splitleaves", 1);
+        dev->tunePrefetch = (int)cfg_int(cfg, "prefetch", 0);
         dev->bvhCollapseDp = (int)cfg_int(cfg, "collapse", 1); dev->bvhCTri = 0.01f * (float)cfg_int(cfg, "ctri", 60);
         dev->sortRays = (int)cfg_int(cfg, "sort", 0); dev->sortMin = (uint32_t)cfg_int(cfg, "sortmin", 1l << 16);
         YRT_CK(cudaHostAlloc((void**)&dev->hostCounters, 16 * sizeof(uint32_t), cudaHostAllocDefault));

@@ -574,6 +574,7 @@ static FrameSetup setup_frame(yrt_device* dev, RendererObj& R, SceneHandle* sc, 
     FrameConst& fc = fs.fc;
     if (sc) fc.scene = sc->data;
     fc.scene.tuneRefillMin = dev->tuneRefillMin; fc.scene.tuneTriNum = dev->tuneTriNum; fc.scene.tuneTriDen = dev->tuneTriDen; fc.scene.tuneSimple = dev->tuneSimple;
+    fc.scene.tunePrefetch = dev->tunePrefetch > 0 ? 1 : 0;
     fc.width = (int)fb->width; fc.height = (int)fb->height; fc.numFaces = numFaces;
     fc.serverID = dev->serverID; fc.serverCount = dev->serverCount < 1 ? 1 : dev->serverCount;
     fc.rcpWidth = rcpf(float(fb->width)); fc.rcpHeight = rcpf(float(fb->height));
@@ -860,6 +861,7 @@ void trace_rays(yrt_device* dev, SceneHandle* sc, size_t n, const float* rays, v
     if (n > 0xfffffff0ull) throw std::runtime_error("device_cuda: yrtxTraceRays is limited to 2^32 - 16 rays per call");
     YRT_CK(cudaMemsetAsync(dev->wf.wb.counters + 6, 0, sizeof(uint32_t), st));
     SceneData sd = sc->data; sd.tuneRefillMin = dev->tuneRefillMin; sd.tuneTriNum = dev->tuneTriNum; sd.tuneTriDen = dev->tuneTriDen; sd.tuneSimple = dev->tuneSimple;
+    sd.tunePrefetch = dev->tunePrefetch > 0 ? 1 : 0;
     launch_trace_user(sd, rp, hp, n, closest, dev->countStats, dev->wf.wb.stats, dev->wf.wb.counters + 6, lc);
     YRT_CK(cudaEventRecord(b, st));
     if (!onDevice) YRT_CK(cudaMemcpyAsync(hits, dHits.p, 32 * n, cudaMemcpyDeviceToHost, st));

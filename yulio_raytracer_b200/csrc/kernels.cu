@@ -198,7 +198,7 @@ __global__ void __launch_bounds__(YRT_TRACE_THREADS, YRT_CLOSEST_MINBLOCKS) k_tr
     const uint32_t n = wb.counters[queueSel];
     TraceCounters cnt = {0, 0, 0};
     ClosestIO io{wb, queueSel ? wb.queueB : wb.queueA};
-    trace_stream<false, COUNT, MOTION>((const uint4*)sc.nodes, sc.tris, sc.triMotion, sc.numNodes, n, &wb.counters[4], io, cnt, TraceTune{sc.tuneRefillMin, sc.tuneTriNum, sc.tuneTriDen});
+    trace_stream<false, COUNT, MOTION>((const uint4*)sc.nodes, sc.tris, sc.triMotion, sc.numNodes, n, &wb.counters[4], io, cnt, TraceTune{sc.tuneRefillMin, sc.tuneTriNum, sc.tuneTriDen, sc.tunePrefetch});
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&wb.stats[0], (unsigned long long)n);
     if (COUNT) { atomicAdd(&wb.stats[2], (unsigned long long)cnt.nodes); atomicAdd(&wb.stats[3], (unsigned long long)cnt.tris); }
 }
@@ -227,7 +227,7 @@ __global__ void YRT_SHADOW_BOUNDS k_trace_shadow(SceneData sc, WavefrontBuffers 
     const uint32_t n = wb.counters[2];
     TraceCounters cnt = {0, 0, 0};
     ShadowIO io{wb};
-    trace_stream<true, COUNT, MOTION>((const uint4*)sc.nodes, sc.tris, sc.triMotion, sc.numNodes, n, &wb.counters[5], io, cnt, TraceTune{sc.tuneRefillMin, sc.tuneTriNum, sc.tuneTriDen});
+    trace_stream<true, COUNT, MOTION>((const uint4*)sc.nodes, sc.tris, sc.triMotion, sc.numNodes, n, &wb.counters[5], io, cnt, TraceTune{sc.tuneRefillMin, sc.tuneTriNum, sc.tuneTriDen, sc.tunePrefetch});
     if (COUNT) { atomicAdd(&wb.stats[4], (unsigned long long)cnt.nodes); atomicAdd(&wb.stats[5], (unsigned long long)cnt.tris); }
 }
 void launch_trace_shadow(const FrameConst& fc, const WavefrontBuffers& wb, LaunchCfg lc) {
@@ -239,12 +239,16 @@ void launch_trace_shadow(const FrameConst& fc, const WavefrontBuffers& wb, Launc
     else k_trace_shadow<false, false><<<lc.blocks, YRT_TRACE_THREADS, 0, lc.stream>>>(fc.scene, wb);
 }
 
+#ifndef YRT_USER_MINBLOCKS
+#define YRT_USER_MINBLOCKS 8      // 64 registers: 8 CTAs/SM like the wavefront kernels (r2 A/B on the config-5 soups: +1 % at 1e6 / 1e7 triangles, +4 % at 1e8 over 7 CTAs/SM)
+#endif
+#define YRT_USER_BOUNDS __launch_bounds__(YRT_TRACE_THREADS, YRT_USER_MINBLOCKS)
 template <bool ANY, bool COUNT>
-__global__ void __launch_bounds__(YRT_TRACE_THREADS) k_trace_user(SceneData sc, const float4* __restrict__ rays, float4* __restrict__ hits, uint32_t n,
+__global__ void YRT_USER_BOUNDS k_trace_user(SceneData sc, const float4* __restrict__ rays, float4* __restrict__ hits, uint32_t n,
                                                                   uint32_t* workCounter, unsigned long long* stats) {
     TraceCounters cnt = {0, 0, 0};
     UserIO io{rays, hits, stats ? stats + 7 : nullptr};
-    trace_stream<ANY, COUNT, false>((const uint4*)sc.nodes, sc.tris, nullptr, sc.numNodes, n, workCounter, io, cnt, TraceTune{sc.tuneRefillMin, sc.tuneTriNum, sc.tuneTriDen});
+    trace_stream<ANY, COUNT, false>((const uint4*)sc.nodes, sc.tris, nullptr, sc.numNodes, n, workCounter, io, cnt, TraceTune{sc.tuneRefillMin, sc.tuneTriNum, sc.tuneTriDen, sc.tunePrefetch});
     if (COUNT && stats) { atomicAdd(&stats[2], (unsigned long long)cnt.nodes); atomicAdd(&stats[3], (unsigned long long)cnt.tris); }
 }
 void launch_trace_user(const SceneData& sc, const float* rays, float* hits, size_t n, int closest, int countStats,
