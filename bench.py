@@ -476,8 +476,11 @@ def main():
 
     # ---- (2) end to end through the reference-facing loop, every frame read back to the host every step ----
     dev.set_readback(world == 1)           # N > 1: the bands are gathered on the GPU first, rank 0 copies the assembled frames to the host
-    for i in range(2):
-        render_step(dev, s, cams, fbs, args.per_face); gather_bands(to_host=True)
+    for i in range(2):                                     # the same body as the timed loop (first maps allocate staging / pinned buffers)
+        render_step(dev, s, cams, fbs, args.per_face)
+        for fb in fbs:
+            dev.rtSwapBuffers(fb); dev.rtMapFrameBuffer(fb); dev.rtUnmapFrameBuffer(fb)
+        gather_bands(to_host=True)
     barrier()
     e2e_rays = 0; h2d = d2h = 0
     t0 = time.perf_counter()

@@ -61,7 +61,15 @@ template <bool EXT>
 YRT_D void post_intersect(const SceneData& sc, V3 org, V3 dir, float t, float u, float v, int triIdx, float time, DG& dg) {
     // one 80-byte record per leaf-order triangle (bvh_build.cu: write_triangle) replaces geometry record -> indices -> 3 vertices
     const float4* h = sc.triShade + 5ull * (uint32_t)triIdx;
+#ifndef YRT_SHADE_REC_EVICT_LAST
+#define YRT_SHADE_REC_EVICT_LAST 1
+#endif
+#if YRT_SHADE_REC_EVICT_LAST
+    const uint64_t pol = bvh_policy();                            // shading records are re-used across paths: last to leave L2 (bvh.cuh)
+    const float4 r0 = bvh_ld(h, pol), r1 = bvh_ld(h + 1, pol), r2 = bvh_ld(h + 2, pol), r3 = bvh_ld(h + 3, pol), r4 = bvh_ld(h + 4, pol);
+#else
     const float4 r0 = __ldg(h), r1 = __ldg(h + 1), r2 = __ldg(h + 2), r3 = __ldg(h + 3), r4 = __ldg(h + 4);
+#endif
     const uint32_t flags = __float_as_uint(r0.w);
     const GeomRec& g = sc.geoms[flags >> 2];
     dg.material = g.material; dg.areaLight = g.areaLight; dg.illumMask = g.illumMask; dg.shadowMask = g.shadowMask;
