@@ -354,7 +354,7 @@ def main():
         config["partition"] = f"4-row bands round-robin over {in_process} GPUs of one process (group device), scene replicated"
     dev = Device.cuda(cfg=(f"gpus={in_process}" if in_process > 1 else f"gpu={local_rank},serverID={rank},serverCount={world}") + ("," + args.cfg if args.cfg else ""))
     s = build_workload(dev, args.workload, size, spp, depth, "RGB8")
-    dev.rtSetPrimitive(s.scene, 0, s.prims[0]); dev.rtCommit(s.scene)   # a second, full commit: the GPU BVH build without the first call's pool growth
+    dev.set_option("rebuild", 1); dev.rtCommit(s.scene); dev.set_option("rebuild", 0)   # a second, full commit: the GPU BVH build without the first call's pool growth
     st_build = dev.frame_stats()                           # CUDA-event time of the build (Morton sort, PLOC, SAH-optimal BVH8 collapse)
     cams = make_cameras(dev, s, faces)
     fbs = [s.framebuffer] + [dev.rtNewFrameBuffer("RGB8", size, size, 1) for _ in range(len(cams) - 1)]

@@ -203,7 +203,7 @@ YRT_API yrt_status yrtxRenderCubeMap(yrt_device*, yrt_handle renderer, const yrt
                                      yrt_handle tonemapper, const yrt_handle* frameBuffers, int accumulate);
 
 /* Changes one of the integer cfg keys of yrtCreateDevice on a live device (measurement / A-B only): "lanes" (1 | 2 concurrent chunk streams),
- * "tracectas", "shadectas" (persistent CTAs per SM), "syncmin", "timers", "verbose". Unknown keys are an error. */
+ * "tracectas", "shadectas" (persistent CTAs per SM), "syncmin", "timers", "verbose", "rebuild" (every scene commit re-flattens and rebuilds). Unknown keys are an error. */
 YRT_API yrt_status yrtxSetOption(yrt_device*, const char* key, long value);
 /* The roofline denominators SURVEY §8d asks to be measured on the box itself (csrc/microbench.cu; not on the render path):
  * kind 0: FP32 FMA issue, *result in TFLOP/s; kind 1: read bandwidth in GB/s of a `bytes` working set re-read with L1 bypassed (L2 read

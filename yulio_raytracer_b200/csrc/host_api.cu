@@ -765,6 +765,7 @@ yrt_status yrtxSetOption(yrt_device* dev, const char* key, long value) {
             else if (k == "syncmin") dev->syncMinPaths = (uint32_t)std::max(0l, value);
             else if (k == "timers") dev->useTimers = value != 0;
             else if (k == "verbose") dev->verbose = (int)value;
+            else if (k == "rebuild") dev->alwaysRebuild = value != 0;
             else throw std::runtime_error("device_cuda: unknown option " + k))
 }
 yrt_status yrtxMicrobench(yrt_device* dev, int kind, size_t bytes, double* result) { GUARD_S(const double v = yrt::microbench(dev, kind, bytes); if (result) *result = v) }
