@@ -497,7 +497,8 @@ def main():
         else:
             e2e_rays += st.rays_closest + st.rays_shadow
         h2d += st.h2d_bytes + 4096
-        d2h += (len(fbs) * size * stride) if (world > 1 and rank == 0) else (st.d2h_bytes if world == 1 else 0)
+        # bytes that reached the host this step: a plain device copies every frame inside the render call, a group device when its frames are mapped
+        d2h += (len(fbs) * size * stride) if (world > 1 and rank == 0) else (max(st.d2h_bytes, dev.frame_stats().d2h_bytes) if world == 1 else 0)
         if world == 1 and args.per_face:
             d2h += (len(fbs) - 1) * size * stride
         if s.view is not None:                             # C1 renders with the scene's one pinhole camera
