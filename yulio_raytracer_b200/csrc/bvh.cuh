@@ -5,8 +5,14 @@
 //   rtcOccluded   devices/device_singleray/integrators/pathtraceintegrator.cpp:160
 // Node format follows Ylitie/Karras/Laine, "Efficient Incoherent Ray Traversal on GPUs Through
 // Compressed Wide BVHs" (HPG 2017): 80 bytes = origin (12) + 3 exponents + imask (4) + child base,
-// triangle base (8) + 8 meta bytes + 6 x 8 quantised planes (48).  Triangles are 48 bytes
+// triangle base (8) + leaf-triangle mask (4) + 4 spare + 6 x 8 quantised planes (48).  Triangles are 48 bytes
 // (3 x float4) with geomID / primID / flags in the w lanes.
+// Unlike the paper's per-child meta bytes (a shifted unary count per hit child: ~8 ALU instructions per child, 66 per node in the r2
+// SASS, on the pipe that bounds the kernel), a node carries ONE mask: bit 8k + s = "slot s is a leaf child with more than k triangles".
+// The node test collects one bit per hit slot; inner hits are put into traversal order by a 2 KB table lookup, leaf hits become
+// triangle bits with one multiply and one AND: (hits * 0x010101) & triMask. A pending triangle set is (node index, bits); the
+// triangle of bit b is triBase + popc(triMask & ((1 << b) - 1)), fetched from the node's second 16 bytes when the triangle is tested
+// (1.6 triangle tests against 9.5 node tests per ray on BASELINE config 4).
 //
 // Arithmetic contract of the triangle test: "YRT-PLUECKER-1" (stated in oracle/embree2_shim.cpp,
 // which holds the CPU twin used by the oracle) — bit-exact (t,u,v,geomID,primID).
@@ -19,7 +25,7 @@ struct __align__(16) Node8 {
     float px, py, pz;
     uint8_t ex, ey, ez, imask;
     uint32_t childBase, triBase;
-    uint8_t meta[8];
+    uint32_t triMask, reserved;
     uint8_t qlox[8], qloy[8], qloz[8], qhix[8], qhiy[8], qhiz[8];
 };
 static_assert(sizeof(Node8) == 80, "Node8 must be 80 bytes");
@@ -100,10 +106,46 @@ YRT_D float byte_to_float(uint32_t packed, uint32_t magic, int i) {
     return __uint_as_float(r) - 8388608.0f;
 }
 
-// Intersects the 8 quantised child boxes of one node; returns the CWBVH hit mask:
-// bits 24..31 inner children at position 24 + (slot ^ octinv), bits 0..23 leaf triangles.
+// Packed FP32 (sm_100: FADD2 / FFMA2 work on two floats held in an aligned register pair, each half rounded exactly like the scalar
+// instruction): the near and the far plane of one axis share an instruction — {near byte, far byte} in one register pair, the axis
+// scale as a scalar (broadcast) operand, {near offset, far offset} as the addend pair — so the bias removal and the six plane
+// evaluations of a child take 3 + 3 instructions instead of 6 + 6. The results are bit-identical, only the instruction count changes.
+#ifndef YRT_NODE_F32X2
+#define YRT_NODE_F32X2 1
+#endif
+YRT_D uint64_t f2_pack(float lo, float hi) { uint64_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+YRT_D uint64_t f2_packu(uint32_t lo, uint32_t hi) { uint64_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi)); return r; }
+YRT_D void f2_unpack(uint64_t v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+YRT_D uint64_t f2_add(uint64_t a, uint64_t b) { uint64_t r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+YRT_D uint64_t f2_fma(uint64_t a, uint64_t b, uint64_t c) { uint64_t r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+YRT_D uint32_t byte_biased(uint32_t packed, uint32_t magic, int i) {       // the float 2^23 + byte i, as bits
+    uint32_t r;
+    switch (i) {
+    case 0: asm("prmt.b32 %0, %1, %2, 0x7650;" : "=r"(r) : "r"(packed), "r"(magic)); break;
+    case 1: asm("prmt.b32 %0, %1, %2, 0x7651;" : "=r"(r) : "r"(packed), "r"(magic)); break;
+    case 2: asm("prmt.b32 %0, %1, %2, 0x7652;" : "=r"(r) : "r"(packed), "r"(magic)); break;
+    default: asm("prmt.b32 %0, %1, %2, 0x7653;" : "=r"(r) : "r"(packed), "r"(magic)); break;
+    }
+    return r;
+}
+
+// Traversal order: the child in slot s is visited at position s ^ octinv (highest first). perm8 moves bit s of an 8-bit slot mask to
+// bit s ^ o; the streaming kernels look it up in a 2 KB shared-memory table (perm_lut_fill), the one-ray-per-thread path computes it.
+#define YRT_PERM_LUT_BYTES 2048
+YRT_D uint32_t perm8(uint32_t x, uint32_t o) {
+    if (o & 1u) x = ((x & 0x55u) << 1) | ((x >> 1) & 0x55u);
+    if (o & 2u) x = ((x & 0x33u) << 2) | ((x >> 2) & 0x33u);
+    if (o & 4u) x = ((x & 0x0fu) << 4) | (x >> 4);
+    return x;
+}
+YRT_D void perm_lut_fill(uint8_t* lut) {            // lut[o * 256 + x] = perm8(x, o); every thread of the CTA calls it, then a barrier
+    for (uint32_t e = threadIdx.x; e < YRT_PERM_LUT_BYTES; e += blockDim.x) lut[e] = (uint8_t)perm8(e & 0xffu, e >> 8);
+}
+
+// Intersects the 8 quantised child boxes of one node; returns the hit mask: bits 24..31 inner children at position 24 + (slot ^ octinv),
+// bits 0..23 leaf triangles in the node's triMask numbering (bit 8k + slot). permLut: perm_lut_fill's table, or nullptr.
 YRT_D uint32_t node_test(const uint4 n0, const uint4 n1, const uint4 n2, const uint4 n3, const uint4 n4,
-                         const RayPre& r, float tnear, float tbest) {
+                         const RayPre& r, float tnear, float tbest, const uint8_t* permLut) {
     const V3 p(__uint_as_float(n0.x), __uint_as_float(n0.y), __uint_as_float(n0.z));
     const uint32_t e = n0.w;
     const float sx = __uint_as_float((e & 0xffu) << 23) * r.idir.x;
@@ -113,42 +155,51 @@ YRT_D uint32_t node_test(const uint4 n0, const uint4 n1, const uint4 n2, const u
     const float padx = fabsf(ox) * YRT_BOX_PAD, pady = fabsf(oy) * YRT_BOX_PAD, padz = fabsf(oz) * YRT_BOX_PAD;
     const float oxn = ox - padx, oxf = ox + padx, oyn = oy - pady, oyf = oy + pady, ozn = oz - padz, ozf = oz + padz;
     const bool nx = r.idir.x < 0.f, ny = r.idir.y < 0.f, nz = r.idir.z < 0.f;
-    const uint32_t octinv4 = r.octinv * 0x01010101u;
     const float tfarPadded = tbest * (1.0f + YRT_BOX_PAD);
     const uint32_t magic = yrt_c_magic;
-    uint32_t hitmask = 0;
+    uint32_t hit8 = 0;
+#if YRT_NODE_F32X2
+    const uint64_t unbias = f2_pack(-8388608.0f, -8388608.0f);
+    const uint64_t sX2 = f2_pack(sx, sx), sY2 = f2_pack(sy, sy), sZ2 = f2_pack(sz, sz);
+    const uint64_t oX2 = f2_pack(oxn, oxf), oY2 = f2_pack(oyn, oyf), oZ2 = f2_pack(ozn, ozf);
+#endif
 #pragma unroll
     for (int half = 0; half < 2; half++) {
-        const uint32_t meta4 = half ? n1.w : n1.z;
         const uint32_t qlox = half ? n2.y : n2.x, qloy = half ? n2.w : n2.z;
         const uint32_t qloz = half ? n3.y : n3.x, qhix = half ? n3.w : n3.z;
         const uint32_t qhiy = half ? n4.y : n4.x, qhiz = half ? n4.w : n4.z;
         const uint32_t nearx = nx ? qhix : qlox, farx = nx ? qlox : qhix;
         const uint32_t neary = ny ? qhiy : qloy, fary = ny ? qloy : qhiy;
         const uint32_t nearz = nz ? qhiz : qloz, farz = nz ? qloz : qhiz;
-        const uint32_t isInner4 = (meta4 & (meta4 << 1)) & 0x10101010u;
-        const uint32_t innerMask4 = (isInner4 >> 4) * 0xffu;            // 0xff per inner byte
-        const uint32_t bitIndex4 = (meta4 ^ (octinv4 & innerMask4)) & 0x1f1f1f1fu;
-        const uint32_t childBits4 = (meta4 >> 5) & 0x07070707u;
 #pragma unroll
         for (int i = 0; i < 4; i++) {
-            const float tnx = __fmaf_rn(byte_to_float(nearx, magic, i), sx, oxn);
-            const float tny = __fmaf_rn(byte_to_float(neary, magic, i), sy, oyn);
-            const float tnz = __fmaf_rn(byte_to_float(nearz, magic, i), sz, ozn);
-            const float tfx = __fmaf_rn(byte_to_float(farx, magic, i), sx, oxf);
-            const float tfy = __fmaf_rn(byte_to_float(fary, magic, i), sy, oyf);
-            const float tfz = __fmaf_rn(byte_to_float(farz, magic, i), sz, ozf);
+            float tnx, tny, tnz, tfx, tfy, tfz;
+#if YRT_NODE_F32X2
+            f2_unpack(f2_fma(f2_add(f2_packu(byte_biased(nearx, magic, i), byte_biased(farx, magic, i)), unbias), sX2, oX2), tnx, tfx);
+            f2_unpack(f2_fma(f2_add(f2_packu(byte_biased(neary, magic, i), byte_biased(fary, magic, i)), unbias), sY2, oY2), tny, tfy);
+            f2_unpack(f2_fma(f2_add(f2_packu(byte_biased(nearz, magic, i), byte_biased(farz, magic, i)), unbias), sZ2, oZ2), tnz, tfz);
+#else
+            tnx = __fmaf_rn(byte_to_float(nearx, magic, i), sx, oxn);
+            tny = __fmaf_rn(byte_to_float(neary, magic, i), sy, oyn);
+            tnz = __fmaf_rn(byte_to_float(nearz, magic, i), sz, ozn);
+            tfx = __fmaf_rn(byte_to_float(farx, magic, i), sx, oxf);
+            tfy = __fmaf_rn(byte_to_float(fary, magic, i), sy, oyf);
+            tfz = __fmaf_rn(byte_to_float(farz, magic, i), sz, ozf);
+#endif
             const float tmin = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, tnear));
             const float tmax = fminf(fminf(tfx, tfy), fminf(tfz, tfarPadded));
-            if (tmin <= tmax) {
-                const uint32_t bits = (childBits4 >> (8 * i)) & 0xffu;
-                const uint32_t idx = (bitIndex4 >> (8 * i)) & 0xffu;
-                hitmask |= bits << idx;
-            }
+            if (tmin <= tmax) hit8 |= 1u << (4 * half + i);
         }
     }
-    return hitmask;
+    // an empty slot (inverted box) that a degenerate node lets through is neither in imask nor in triMask
+    const uint32_t imask = e >> 24;
+    const uint32_t inner = hit8 & imask;
+    const uint32_t ordered = permLut ? (uint32_t)permLut[(r.octinv << 8) + inner] : perm8(inner, r.octinv);
+    return (ordered << 24) | (((hit8 & ~imask) * 0x010101u) & n1.z);
 }
+
+// leaf-order index of the triangle behind bit `bit` of a pending set of node `nodeIdx` (see the node format above)
+YRT_D uint32_t tri_index(const uint4 nodeWord1, uint32_t bit) { return nodeWord1.y + (uint32_t)__popc(nodeWord1.z & ((1u << bit) - 1u)); }
 
 struct TraceCounters { uint32_t nodes, tris; uint32_t overflow; };   // overflow: a traversal stack ran out of its YRT_STACK_SIZE entries
 
@@ -162,9 +213,6 @@ struct TraceCounters { uint32_t nodes, tris; uint32_t overflow; };   // overflow
 #endif
 #ifndef YRT_STREAM_HINTS
 #define YRT_STREAM_HINTS 1
-#endif
-#ifndef YRT_TRI_BATCH
-#define YRT_TRI_BATCH 0
 #endif
 YRT_D uint64_t bvh_policy() {
 #if YRT_BVH_EVICT_LAST
@@ -213,15 +261,15 @@ YRT_D bool trace_ray(const uint4* __restrict__ nodes, const float4* __restrict__
             const uint4* np = nodes + 5ull * nodeIdx;
             const uint4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
             if (COUNT) cnt->nodes++;
-            const uint32_t hm = node_test(n0, n1, n2, n3, n4, r, tnear, tbest);
+            const uint32_t hm = node_test(n0, n1, n2, n3, n4, r, tnear, tbest, nullptr);
             G = make_uint2(n1.x, (hm & 0xff000000u) | (n0.w >> 24));
-            T = make_uint2(n1.y, hm & 0x00ffffffu);
+            T = make_uint2(nodeIdx, hm & 0x00ffffffu);
         }
 
         while (T.y) {
             const uint32_t bit = 31u - __clz(T.y);
             T.y &= ~(1u << bit);
-            const uint32_t triIdx = T.x + bit;
+            const uint32_t triIdx = tri_index(__ldg(nodes + 5ull * T.x + 1), bit);
             const float4* tp = tris + 3ull * triIdx;
             const float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
             if (COUNT) cnt->tris++;
@@ -281,10 +329,7 @@ template <bool ANY, bool COUNT, bool MOTION, class IO>
 YRT_D void trace_stream(const uint4* __restrict__ nodes, const float4* __restrict__ tris, const float4* __restrict__ triMotion, uint32_t numNodes,
                         uint32_t n, uint32_t* __restrict__ workCounter, IO io, TraceCounters& cnt, const TraceTune tune) {
     __shared__ uint2 smStack[YRT_SM_STACK * YRT_TRACE_THREADS];
-#if YRT_TRI_BATCH
-    __shared__ uint32_t smTriList[YRT_TRACE_THREADS / 32][32];      // owner lane << 27 | leaf-order triangle index (< 2^27)
-    __shared__ float4 smTriRes[YRT_TRACE_THREADS / 32][32];         // (t, u, v, triangle) of an accepted candidate, t = +inf otherwise
-#endif
+    __shared__ uint8_t smPerm[YRT_PERM_LUT_BYTES];
     uint2 lstack[YRT_STACK_SIZE - YRT_SM_STACK];
     const unsigned FULL = 0xffffffffu;
     const unsigned lane = threadIdx.x & 31u, ltmask = (1u << lane) - 1u;
@@ -302,6 +347,8 @@ YRT_D void trace_stream(const uint4* __restrict__ nodes, const float4* __restric
     uint2 G = make_uint2(0u, 0u), T = make_uint2(0u, 0u);
     int sp = 0;
     const uint64_t pol = bvh_policy();
+    perm_lut_fill(smPerm);
+    __syncthreads();
 
     while (true) {
         // ---- refill idle slots ---------------------------------------------------------------------
@@ -344,85 +391,11 @@ YRT_D void trace_stream(const uint4* __restrict__ nodes, const float4* __restric
         const int nN = __popc(__ballot_sync(FULL, nodeWork)), nT = __popc(__ballot_sync(FULL, triWork));
 
         if (nT != 0 && (nN == 0 || tune.triNum * nT >= tune.triDen * nN)) {
-#if YRT_TRI_BATCH
-            // ---- TRIANGLE phase, batched across the warp's rays --------------------------------------------
-            // The pending triangles of all participating lanes go into a shared-memory work list (prefix sum over the per-lane counts);
-            // the 32 lanes then test 32 list entries at a time, each fetching the owner's ray with shuffles, and write (t, u, v, triangle)
-            // back; every owner finally folds its own entries in list order. A lane with three pending triangles no longer needs three
-            // rounds of this phase with two thirds of the warp idle (ncu r2: the phase ran with 4-9 of 32 lanes). The result does not depend
-            // on the order: acceptance is the (t, geomID, primID) minimum / any accepted hit.
-            {
-                const uint32_t wid = threadIdx.x >> 5;
-                const uint32_t pend = triWork ? T.y : 0u;
-                const uint32_t myCnt = __popc(pend);
-                uint32_t incl = myCnt;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(FULL, incl, o); if (lane >= (uint32_t)o) incl += v; }
-                const uint32_t total = __shfl_sync(FULL, incl, 31), myOff = incl - myCnt;
-                for (uint32_t base = 0; base < total; base += 32u) {              // warp-uniform
-                    {   // owners publish their entries that fall into [base, base + 32)
-                        uint32_t tmp = pend, idx = myOff;
-                        while (tmp) {
-                            const uint32_t bit = 31u - __clz(tmp); tmp &= ~(1u << bit);
-                            if (idx >= base && idx < base + 32u) smTriList[wid][idx - base] = ((T.x + bit) & 0x07ffffffu) | (lane << 27);
-                            idx++;
-                        }
-                    }
-                    __syncwarp();
-                    const bool mine = base + lane < total;
-                    const uint32_t entry = mine ? smTriList[wid][lane] : (lane << 27);
-                    const uint32_t owner = entry >> 27, triIdx = entry & 0x07ffffffu;
-                    const float ox = __shfl_sync(FULL, r.O.x, owner), oy = __shfl_sync(FULL, r.O.y, owner), oz = __shfl_sync(FULL, r.O.z, owner);
-                    const float dx = __shfl_sync(FULL, r.D.x, owner), dy = __shfl_sync(FULL, r.D.y, owner), dz = __shfl_sync(FULL, r.D.z, owner);
-                    const float otn = __shfl_sync(FULL, tnear, owner), otb = __shfl_sync(FULL, tbest, owner);
-                    float otime = 0.f; if (MOTION) otime = __shfl_sync(FULL, time, owner);
-                    float4 res = make_float4(INFINITY, 0.f, 0.f, 0.f);
-                    if (mine) {
-                        const float4* tp = tris + 3ull * triIdx;
-                        const float4 a = bvh_ld(tp, pol), b = bvh_ld(tp + 1, pol), c = bvh_ld(tp + 2, pol);
-                        if (COUNT) cnt.tris++;
-                        V3 p0(a.x, a.y, a.z), p1(b.x, b.y, b.z), p2(c.x, c.y, c.z);
-                        if (MOTION && (__float_as_uint(c.w) & YRT_TRI_FLAG_MOTION)) {
-                            const float4* mp = triMotion + 3ull * triIdx;
-                            const float4 d0 = __ldg(mp), d1 = __ldg(mp + 1), d2 = __ldg(mp + 2);
-                            p0 = p0 + otime * V3(d0.x, d0.y, d0.z); p1 = p1 + otime * V3(d1.x, d1.y, d1.z); p2 = p2 + otime * V3(d2.x, d2.y, d2.z);
-                        }
-                        float t, u, v, den; V3 Ng;
-                        // candidates beyond the owner's current best cannot win (ties, t == best, are decided by the owner)
-                        if (tri_test(V3(ox, oy, oz), V3(dx, dy, dz), p0, p1, p2, t, u, v, Ng, den) && t > otn && (ANY ? t < otb : t <= otb) &&
-                            !((__float_as_uint(c.w) & YRT_TRI_FLAG_CULL) && den <= 0.f)) res = make_float4(t, u, v, __uint_as_float(triIdx));
-                    }
-                    smTriRes[wid][lane] = res;
-                    __syncwarp();
-                    if (myCnt) {                                                   // owners fold their entries of this window, in list order
-                        const uint32_t lo = myOff > base ? myOff : base, hi = (myOff + myCnt < base + 32u) ? myOff + myCnt : base + 32u;
-                        for (uint32_t i = lo; i < hi; i++) {
-                            const float4 q = smTriRes[wid][i - base];
-                            if (!(q.x < INFINITY) || (ANY && occluded)) continue;
-                            const uint32_t qTri = __float_as_uint(q.w);
-                            bool closer = q.x < tbest;
-                            if (!ANY && !closer && bestTri != YRT_NO_TRI && q.x == tbest) {      // tie: (geomID, primID) ascending
-                                const int g = __float_as_int(__ldg(tris + 3ull * qTri).w), pr = __float_as_int(__ldg(tris + 3ull * qTri + 1).w);
-                                const int bg = __float_as_int(__ldg(tris + 3ull * bestTri).w), bp = __float_as_int(__ldg(tris + 3ull * bestTri + 1).w);
-                                closer = (g < bg) || (g == bg && pr < bp);
-                            }
-                            if (ANY) closer = true;                                    // any accepted candidate inside (tnear, tfar] occludes
-                            if (closer) {
-                                tbest = q.x; bt = q.x; bu = q.y; bv = q.z; bestTri = qTri;
-                                if (ANY) { occluded = true; G.y = 0u; sp = 0; }
-                            }
-                        }
-                    }
-                    __syncwarp();
-                }
-                if (triWork) T.y = 0u;
-            }
-#else
             // ---- TRIANGLE phase: one triangle per participating lane -------------------------------------
             if (triWork) {
                 const uint32_t bit = 31u - __clz(T.y);
                 T.y &= ~(1u << bit);
-                const uint32_t triIdx = T.x + bit;
+                const uint32_t triIdx = tri_index(bvh_ld(nodes + 5ull * T.x + 1, pol), bit);     // the node's (child base, triangle base, triMask, -)
                 const float4* tp = tris + 3ull * triIdx;
                 const float4 a = bvh_ld(tp, pol), b = bvh_ld(tp + 1, pol), c = bvh_ld(tp + 2, pol);
                 if (COUNT) cnt.tris++;
@@ -447,7 +420,6 @@ YRT_D void trace_stream(const uint4* __restrict__ nodes, const float4* __restric
                     }
                 }
             }
-#endif
         } else if (nN != 0) {
             // ---- NODE phase: one compressed node per participating lane --------------------------------
             if (nodeWork) {
@@ -469,9 +441,9 @@ YRT_D void trace_stream(const uint4* __restrict__ nodes, const float4* __restric
                 const uint4* np = nodes + 5ull * nodeIdx;
                 const uint4 n0 = bvh_ld(np, pol), n1 = bvh_ld(np + 1, pol), n2 = bvh_ld(np + 2, pol), n3 = bvh_ld(np + 3, pol), n4 = bvh_ld(np + 4, pol);
                 if (COUNT) cnt.nodes++;
-                const uint32_t hm = node_test(n0, n1, n2, n3, n4, r, tnear, tbest);
+                const uint32_t hm = node_test(n0, n1, n2, n3, n4, r, tnear, tbest, smPerm);
                 G = make_uint2(n1.x, (hm & 0xff000000u) | (n0.w >> 24));
-                T = make_uint2(n1.y, hm & 0x00ffffffu);
+                T = make_uint2(nodeIdx, hm & 0x00ffffffu);
                 if (tune.prefetch) {
                     uint32_t m = G.y >> 24;
                     while (m) {
@@ -480,7 +452,7 @@ YRT_D void trace_stream(const uint4* __restrict__ nodes, const float4* __restric
                         const char* cp = (const char*)(nodes + 5ull * (G.x + __popc((G.y & 0xffu) & ~(0xffffffffu << sl))));
                         prefetch_l2(cp); prefetch_l2(cp + 64);
                     }
-                    if (T.y) prefetch_l2(tris + 3ull * (T.x + (31u - __clz(T.y))));
+                    if (T.y) prefetch_l2(tris + 3ull * tri_index(n1, 31u - __clz(T.y)));
                 }
             }
         }

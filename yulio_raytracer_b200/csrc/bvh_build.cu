@@ -552,25 +552,27 @@ __global__ void k_collapse(CollapseArgs a) {
     }
     nd.ex = ebyte[0]; nd.ey = ebyte[1]; nd.ez = ebyte[2];
 
-    uint32_t nInner = 0, nTris = 0, imask = 0;
+    // leaf triangles: bit 8k + s of triMask = "slot s is a leaf child with more than k triangles" (k < 3); the node's triangles are stored
+    // in the order of those bits, so the triangle of bit b is triBase + popc(triMask & ((1 << b) - 1)) (bvh.cuh)
+    uint32_t nInner = 0, nTris = 0, imask = 0, triMask = 0;
     for (int s = 0; s < 8; s++) {
         if (!slotValid[s]) continue;
         const uint32_t r = slotRef[s];
         const uint32_t cnt = ref_count(a, r);
-        if (!((slotLeaf >> s) & 1u)) { nInner++; imask |= 1u << s; } else nTris += cnt;
+        if (!((slotLeaf >> s) & 1u)) { nInner++; imask |= 1u << s; }
+        else { nTris += cnt; for (uint32_t k = 0; k < cnt; k++) triMask |= 1u << (8u * k + (uint32_t)s); }
     }
     nd.imask = (uint8_t)imask;
     const uint32_t childBase = nInner ? atomicAdd(&a.counters[0], nInner) : 0u;
     const uint32_t triBase = nTris ? atomicAdd(&a.counters[1], nTris) : 0u;
     const uint32_t taskBase = nInner ? atomicAdd(&a.counters[2], nInner) : 0u;
-    nd.childBase = childBase; nd.triBase = triBase;
+    nd.childBase = childBase; nd.triBase = triBase; nd.triMask = triMask; nd.reserved = 0u;
 
-    uint32_t innerSeen = 0, triOfs = 0;
+    uint32_t innerSeen = 0;
     uint8_t* qplanes[6] = {nd.qlox, nd.qloy, nd.qloz, nd.qhix, nd.qhiy, nd.qhiz};
     const float org[3] = {nlo[0], nlo[1], nlo[2]};
     for (int s = 0; s < 8; s++) {
         if (!slotValid[s]) {
-            nd.meta[s] = 0;
             for (int k = 0; k < 3; k++) { qplanes[k][s] = 255; qplanes[3 + k][s] = 0; }   // inverted box: never hit
             continue;
         }
@@ -585,17 +587,12 @@ __global__ void k_collapse(CollapseArgs a) {
             while (qh < 255 && fmaf((float)qh, scale[k], org[k]) < hi[k]) qh++;
             qplanes[k][s] = (uint8_t)ql; qplanes[3 + k][s] = (uint8_t)qh;
         }
-        const uint32_t cnt = ref_count(a, r);
         if (imask & (1u << s)) {
-            nd.meta[s] = (uint8_t)((1u << 5) | (24u + (uint32_t)s));
             a.tasksOut[taskBase + innerSeen] = make_uint2(r, childBase + innerSeen);
             innerSeen++;
         } else {
-            const uint32_t unary = cnt == 1 ? 1u : (cnt == 2 ? 3u : 7u);
-            nd.meta[s] = (uint8_t)((unary << 5) | triOfs);
             uint32_t leaves[3]; const uint32_t nl = ref_leaves(a, r, leaves);
-            for (uint32_t k = 0; k < nl; k++) write_triangle(a, leaves[k], triBase + triOfs + k);
-            triOfs += cnt;
+            for (uint32_t k = 0; k < nl; k++) write_triangle(a, leaves[k], triBase + (uint32_t)__popc(triMask & ((1u << (8u * k + (uint32_t)s)) - 1u)));
         }
     }
     a.nodes[task.y] = nd;

@@ -397,7 +397,6 @@ void scene_commit(yrt_device* dev, SceneHandle* sc) {
     sc->structureDirty = true;                                // a throw below leaves a scene that re-flattens on the next commit
     build_bvh(in, out, st);
     YRT_CK(cudaStreamSynchronize(st));
-    if (YRT_TRI_BATCH && out.numTris >= (1u << 27)) throw std::runtime_error("device_cuda: the batched triangle phase addresses 2^27 triangles per scene");
     sc->structureDirty = false;
     lap("bvh");
     sc->nodes = out.nodes; sc->tris = out.tris; sc->triShade = out.triShade; sc->triMotion = out.triMotion; sc->buildMs = out.buildMs; sc->buildLaunches = out.launches; sc->rebuildCount++;
