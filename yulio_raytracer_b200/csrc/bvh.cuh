@@ -113,13 +113,25 @@ YRT_D float byte_to_float(uint32_t packed, uint32_t magic, int i) {
 #ifndef YRT_NODE_F32X2
 #define YRT_NODE_F32X2 1
 #endif
+#ifndef YRT_NODE_SIGNBIT
+#define YRT_NODE_SIGNBIT 1
+#endif
 YRT_D uint64_t f2_pack(float lo, float hi) { uint64_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
 YRT_D uint64_t f2_packu(uint32_t lo, uint32_t hi) { uint64_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi)); return r; }
 YRT_D void f2_unpack(uint64_t v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
 YRT_D uint64_t f2_add(uint64_t a, uint64_t b) { uint64_t r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
 YRT_D uint64_t f2_fma(uint64_t a, uint64_t b, uint64_t c) { uint64_t r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+// Measured on B200 (tools/mb/pipes.cu): PRMT, SHF and FMNMX share the alu pipe at 2 warp instructions / clock / SM, IDP.4A runs at the same rate
+// on another pipe (PRMT + IDP.4A together: 3.9 / clock / SM). The node test is bound by the alu pipe, so the planes selected by
+// YRT_NODE_DP4A_MASK (bit 0..5 = near x, far x, near y, far y, near z, far z) are extracted with a dot product against a one-hot
+// byte vector — dp4a(word, 1 << 8i, 2^23 as bits) is the same 32-bit value the PRMT builds.
+#ifndef YRT_NODE_DP4A_MASK
+#define YRT_NODE_DP4A_MASK 0x15
+#endif
+template <bool DP4A>
 YRT_D uint32_t byte_biased(uint32_t packed, uint32_t magic, int i) {       // the float 2^23 + byte i, as bits
     uint32_t r;
+    if (DP4A) { asm("dp4a.u32.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(packed), "r"(1u << (8 * i)), "r"(magic)); return r; }
     switch (i) {
     case 0: asm("prmt.b32 %0, %1, %2, 0x7650;" : "=r"(r) : "r"(packed), "r"(magic)); break;
     case 1: asm("prmt.b32 %0, %1, %2, 0x7651;" : "=r"(r) : "r"(packed), "r"(magic)); break;
@@ -158,13 +170,17 @@ YRT_D uint32_t node_test(const uint4 n0, const uint4 n1, const uint4 n2, const u
     const float tfarPadded = tbest * (1.0f + YRT_BOX_PAD);
     const uint32_t magic = yrt_c_magic;
     uint32_t hit8 = 0;
+#if YRT_NODE_SIGNBIT
+    uint32_t miss8 = 0;           // slot 7 first: after eight shifts slot s sits at bit s
+#endif
 #if YRT_NODE_F32X2
     const uint64_t unbias = f2_pack(-8388608.0f, -8388608.0f);
     const uint64_t sX2 = f2_pack(sx, sx), sY2 = f2_pack(sy, sy), sZ2 = f2_pack(sz, sz);
     const uint64_t oX2 = f2_pack(oxn, oxf), oY2 = f2_pack(oyn, oyf), oZ2 = f2_pack(ozn, ozf);
 #endif
 #pragma unroll
-    for (int half = 0; half < 2; half++) {
+    for (int hh = 0; hh < 2; hh++) {
+        const int half = YRT_NODE_SIGNBIT ? 1 - hh : hh;
         const uint32_t qlox = half ? n2.y : n2.x, qloy = half ? n2.w : n2.z;
         const uint32_t qloz = half ? n3.y : n3.x, qhix = half ? n3.w : n3.z;
         const uint32_t qhiy = half ? n4.y : n4.x, qhiz = half ? n4.w : n4.z;
@@ -172,12 +188,15 @@ YRT_D uint32_t node_test(const uint4 n0, const uint4 n1, const uint4 n2, const u
         const uint32_t neary = ny ? qhiy : qloy, fary = ny ? qloy : qhiy;
         const uint32_t nearz = nz ? qhiz : qloz, farz = nz ? qloz : qhiz;
 #pragma unroll
-        for (int i = 0; i < 4; i++) {
+        for (int ii = 0; ii < 4; ii++) {
+            const int i = YRT_NODE_SIGNBIT ? 3 - ii : ii;
             float tnx, tny, tnz, tfx, tfy, tfz;
 #if YRT_NODE_F32X2
-            f2_unpack(f2_fma(f2_add(f2_packu(byte_biased(nearx, magic, i), byte_biased(farx, magic, i)), unbias), sX2, oX2), tnx, tfx);
-            f2_unpack(f2_fma(f2_add(f2_packu(byte_biased(neary, magic, i), byte_biased(fary, magic, i)), unbias), sY2, oY2), tny, tfy);
-            f2_unpack(f2_fma(f2_add(f2_packu(byte_biased(nearz, magic, i), byte_biased(farz, magic, i)), unbias), sZ2, oZ2), tnz, tfz);
+#define YRT_BB(plane, word) byte_biased<((YRT_NODE_DP4A_MASK >> plane) & 1) != 0>(word, magic, i)
+            f2_unpack(f2_fma(f2_add(f2_packu(YRT_BB(0, nearx), YRT_BB(1, farx)), unbias), sX2, oX2), tnx, tfx);
+            f2_unpack(f2_fma(f2_add(f2_packu(YRT_BB(2, neary), YRT_BB(3, fary)), unbias), sY2, oY2), tny, tfy);
+            f2_unpack(f2_fma(f2_add(f2_packu(YRT_BB(4, nearz), YRT_BB(5, farz)), unbias), sZ2, oZ2), tnz, tfz);
+#undef YRT_BB
 #else
             tnx = __fmaf_rn(byte_to_float(nearx, magic, i), sx, oxn);
             tny = __fmaf_rn(byte_to_float(neary, magic, i), sy, oyn);
@@ -188,9 +207,19 @@ YRT_D uint32_t node_test(const uint4 n0, const uint4 n1, const uint4 n2, const u
 #endif
             const float tmin = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, tnear));
             const float tmax = fminf(fminf(tfx, tfy), fminf(tfz, tfarPadded));
+#if YRT_NODE_SIGNBIT
+            // the sign of tmax - tmin (an FADD on the fma pipe) shifted into the mask (one SHF) instead of FSETP + SEL + ADD on the alu
+            // pipe, the pipe that bounds this kernel. It differs from tmin <= tmax only where the box must not be entered anyway or
+            // may be entered needlessly: tmax = -0 with tmin = +0 (everything inside lies at t <= 0 <= tnear) and inf - inf = NaN.
+            miss8 = __funnelshift_l(__float_as_uint(tmax - tmin), miss8, 1);
+#else
             if (tmin <= tmax) hit8 |= 1u << (4 * half + i);
+#endif
         }
     }
+#if YRT_NODE_SIGNBIT
+    hit8 = ~miss8 & 0xffu;
+#endif
     // an empty slot (inverted box) that a degenerate node lets through is neither in imask nor in triMask
     const uint32_t imask = e >> 24;
     const uint32_t inner = hit8 & imask;
@@ -209,7 +238,7 @@ struct TraceCounters { uint32_t nodes, tris; uint32_t overflow; };   // overflow
 // ld.global.cs / st.global.cs (evict-first, kernels.cu: ClosestIO / ShadowIO), and node / triangle fetches carry an L2 evict_last
 // policy (createpolicy.fractional.L2::evict_last + ld.global.nc.L2::cache_hint) so that they are the last lines L2 gives up.
 #ifndef YRT_BVH_EVICT_LAST
-#define YRT_BVH_EVICT_LAST 1
+#define YRT_BVH_EVICT_LAST 0      // measured r2 (profiles/README.md): no effect on C2-C4, and the policy's register pair costs 2.6 % on config 5 -> off
 #endif
 #ifndef YRT_STREAM_HINTS
 #define YRT_STREAM_HINTS 1

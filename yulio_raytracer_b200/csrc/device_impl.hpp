@@ -128,7 +128,9 @@ struct yrt_device {
     int serverID = 0, serverCount = 1;         // g_serverID / g_serverCount (api/singleray_device.cpp:109-110)
     uint32_t chunkPaths = 1u << 26;      // paths per wavefront pass: whole faces where memory allows (launch tails dominate small chunks)
     int countStats = 0, verbose = 0, alwaysRebuild = 0, useTimers = 1;
-    int tuneRefillMin = 8, tuneTriNum = 3, tuneTriDen = 1, tuneSimple = 0;
+    // node / triangle phase vote (bvh.cuh: TraceTune): triangle phase when tuneTriNum * nT >= tuneTriDen * nN. Measured with the r2 node format: the path
+    // tracer's bounce rays do best at 2:1 (C4 +1.5 %, C3 +1.9 %, C2 -1.7 % against 3:1), the raw ray API on the config-5 soup at 3:1 (2:1 costs 5 %)
+    int tuneRefillMin = 8, tuneTriNum = 2, tuneTriDen = 1, tuneUserTriNum = 3, tuneSimple = 0;
     int tunePrefetch = 0;                      // cfg prefetch=0|1 (bvh.cuh: TraceTune; measured slower, off)
     size_t l2Bytes = 0;
     int shadeCtas = 6, traceCtas = 8;

@@ -458,7 +458,7 @@ yrt_device* yrtCreateDevice(const char* parms, size_t numThreads, int threadsPri
         dev->serverID = (int)cfg_int(cfg, "serverID", 0);
         dev->serverCount = (int)cfg_int(cfg, "serverCount", 1);
         dev->tuneRefillMin = (int)cfg_int(cfg, "refill", dev->tuneRefillMin);
-        dev->tuneTriNum = (int)cfg_int(cfg, "trinum", dev->tuneTriNum); dev->tuneTriDen = (int)cfg_int(cfg, "triden", dev->tuneTriDen); dev->tuneSimple = cfg_int(cfg, "trav", 1) == 0;
+        dev->tuneTriNum = (int)cfg_int(cfg, "trinum", dev->tuneTriNum); dev->tuneUserTriNum = (int)cfg_int(cfg, "trinum", dev->tuneUserTriNum); dev->tuneTriDen = (int)cfg_int(cfg, "triden", dev->tuneTriDen); dev->tuneSimple = cfg_int(cfg, "trav", 1) == 0;
         dev->shadeCtas = (int)cfg_int(cfg, "shadectas", YRT_SHADE_MINBLOCKS); dev->traceCtas = (int)cfg_int(cfg, "tracectas", 8);
         dev->syncMinPaths = (uint32_t)cfg_int(cfg, "syncmin", dev->syncMinPaths);
         dev->bvhPloc = (int)cfg_int(cfg, "bvh", 1); dev->plocRadius = (int)cfg_int(cfg, "plocr", dev->plocRadius); dev->splitLeaves = (int)cfg_int(cfg, "splitleaves", 1);

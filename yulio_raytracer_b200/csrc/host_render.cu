@@ -859,7 +859,7 @@ void trace_rays(yrt_device* dev, SceneHandle* sc, size_t n, const float* rays, v
     YRT_CK(cudaEventRecord(a, st));
     if (n > 0xfffffff0ull) throw std::runtime_error("device_cuda: yrtxTraceRays is limited to 2^32 - 16 rays per call");
     YRT_CK(cudaMemsetAsync(dev->wf.wb.counters + 6, 0, sizeof(uint32_t), st));
-    SceneData sd = sc->data; sd.tuneRefillMin = dev->tuneRefillMin; sd.tuneTriNum = dev->tuneTriNum; sd.tuneTriDen = dev->tuneTriDen; sd.tuneSimple = dev->tuneSimple;
+    SceneData sd = sc->data; sd.tuneRefillMin = dev->tuneRefillMin; sd.tuneTriNum = dev->tuneUserTriNum; sd.tuneTriDen = dev->tuneTriDen; sd.tuneSimple = dev->tuneSimple;
     sd.tunePrefetch = dev->tunePrefetch > 0 ? 1 : 0;
     launch_trace_user(sd, rp, hp, n, closest, dev->countStats, dev->wf.wb.stats, dev->wf.wb.counters + 6, lc);
     YRT_CK(cudaEventRecord(b, st));
