@@ -385,6 +385,13 @@ YRT_D void trace_stream(const uint4* __restrict__ nodes, const float4* __restric
         if (idleMask) {
             const uint32_t nIdle = __popc(idleMask);
             if (nIdle >= (uint32_t)tune.refillMin && !(exhausted && sliceNext >= sliceEnd)) {
+                // results of the rays that finished since the last refill (sp < 0) are written here, refillMin or more slots at a time: writing
+                // each one when its ray ends put a store (and the wait for its address) into almost every macro step, for two or three lanes
+                if (!active && sp < 0) {
+                    if (ANY) io.store_any(tag, occluded);
+                    else io.store_hit(tag, bt, bu, bv, bestTri, tris);     // bestTri == YRT_NO_TRI: miss
+                    sp = 0;
+                }
                 if (sliceNext >= sliceEnd) {
                     uint32_t s = 0;
                     if (lane == 0) s = atomicAdd(workCounter, slice);
@@ -493,11 +500,14 @@ YRT_D void trace_stream(const uint4* __restrict__ nodes, const float4* __restric
                 const uint2 e = sp < YRT_SM_STACK ? smStack[sp * YRT_TRACE_THREADS + threadIdx.x] : lstack[sp - YRT_SM_STACK];
                 if (e.y & 0xff000000u) G = e; else T = e;
             } else {
-                if (ANY) io.store_any(tag, occluded);
-                else io.store_hit(tag, bt, bu, bv, bestTri, tris);     // bestTri == YRT_NO_TRI: miss
+                sp = -1;                                             // finished: the result waits in registers for the next refill
                 active = false;
             }
         }
+    }
+    if (sp < 0) {                                                    // the rays that finished after the last refill
+        if (ANY) io.store_any(tag, occluded);
+        else io.store_hit(tag, bt, bu, bv, bestTri, tris);
     }
 }
 
