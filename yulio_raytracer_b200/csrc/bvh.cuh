@@ -240,6 +240,9 @@ struct TraceCounters { uint32_t nodes, tris; uint32_t overflow; };   // overflow
 #ifndef YRT_BVH_EVICT_LAST
 #define YRT_BVH_EVICT_LAST 0      // measured r2 (profiles/README.md): no effect on C2-C4, and the policy's register pair costs 2.6 % on config 5 -> off
 #endif
+#ifndef YRT_IDLE_EVERY
+#define YRT_IDLE_EVERY 1          // look for idle slots every n-th macro step
+#endif
 #ifndef YRT_STREAM_HINTS
 #define YRT_STREAM_HINTS 1
 #endif
@@ -376,12 +379,19 @@ YRT_D void trace_stream(const uint4* __restrict__ nodes, const float4* __restric
     uint2 G = make_uint2(0u, 0u), T = make_uint2(0u, 0u);
     int sp = 0;
     const uint64_t pol = bvh_policy();
+#if YRT_IDLE_EVERY > 1
+    uint32_t iterNo = 0;
+#endif
     perm_lut_fill(smPerm);
     __syncthreads();
 
     while (true) {
         // ---- refill idle slots ---------------------------------------------------------------------
+#if YRT_IDLE_EVERY > 1
+        const unsigned idleMask = ((iterNo++ % YRT_IDLE_EVERY) == 0u) ? __ballot_sync(FULL, !active) : 0u;      // iterNo is warp-uniform
+#else
         const unsigned idleMask = __ballot_sync(FULL, !active);
+#endif
         if (idleMask) {
             const uint32_t nIdle = __popc(idleMask);
             if (nIdle >= (uint32_t)tune.refillMin && !(exhausted && sliceNext >= sliceEnd)) {
@@ -459,23 +469,24 @@ YRT_D void trace_stream(const uint4* __restrict__ nodes, const float4* __restric
         } else if (nN != 0) {
             // ---- NODE phase: one compressed node per participating lane --------------------------------
             if (nodeWork) {
-                if (T.y) {                                       // postpone the pending triangles
+                // the node's five loads go out first; the stack work below does not depend on them and covers part of their latency
+                const uint32_t bit = 31u - __clz(G.y);
+                G.y &= ~(1u << bit);
+                const uint32_t slot = (bit - 24u) ^ r.octinv;
+                const uint32_t nodeIdx = G.x + __popc((G.y & 0xffu) & ~(0xffffffffu << slot));
+                const uint4* np = nodes + 5ull * nodeIdx;
+                const uint4 n0 = bvh_ld(np, pol), n1 = bvh_ld(np + 1, pol), n2 = bvh_ld(np + 2, pol), n3 = bvh_ld(np + 3, pol), n4 = bvh_ld(np + 4, pol);
+                if (T.y) {                                       // postpone the pending triangles (below the rest of this node's children)
                     if (sp < YRT_SM_STACK) smStack[sp * YRT_TRACE_THREADS + threadIdx.x] = T;
                     else if (sp < YRT_STACK_SIZE) lstack[sp - YRT_SM_STACK] = T;
                     if (sp < YRT_STACK_SIZE) sp++; else io.overflow();     // reported (wb.stats[7] -> the call fails): never a silent drop
                     T.y = 0u;
                 }
-                const uint32_t bit = 31u - __clz(G.y);
-                G.y &= ~(1u << bit);
-                const uint32_t slot = (bit - 24u) ^ r.octinv;
-                const uint32_t nodeIdx = G.x + __popc((G.y & 0xffu) & ~(0xffffffffu << slot));
                 if (G.y & 0xff000000u) {
                     if (sp < YRT_SM_STACK) smStack[sp * YRT_TRACE_THREADS + threadIdx.x] = G;
                     else if (sp < YRT_STACK_SIZE) lstack[sp - YRT_SM_STACK] = G;
                     if (sp < YRT_STACK_SIZE) sp++; else io.overflow();
                 }
-                const uint4* np = nodes + 5ull * nodeIdx;
-                const uint4 n0 = bvh_ld(np, pol), n1 = bvh_ld(np + 1, pol), n2 = bvh_ld(np + 2, pol), n3 = bvh_ld(np + 3, pol), n4 = bvh_ld(np + 4, pol);
                 if (COUNT) cnt.nodes++;
                 const uint32_t hm = node_test(n0, n1, n2, n3, n4, r, tnear, tbest, smPerm);
                 G = make_uint2(n1.x, (hm & 0xff000000u) | (n0.w >> 24));
