@@ -217,11 +217,10 @@ void launch_trace_closest(const FrameConst& fc, const WavefrontBuffers& wb, int 
     else k_trace_closest<false, false><<<lc.blocks, YRT_TRACE_THREADS, 0, lc.stream>>>(fc.scene, wb, queueSel);
 }
 
-#ifdef YRT_SHADOW_MINBLOCKS
-#define YRT_SHADOW_BOUNDS __launch_bounds__(YRT_TRACE_THREADS, YRT_SHADOW_MINBLOCKS)
-#else
-#define YRT_SHADOW_BOUNDS __launch_bounds__(YRT_TRACE_THREADS)      // 64 registers without a bound: 8 CTAs/SM
+#ifndef YRT_SHADOW_MINBLOCKS
+#define YRT_SHADOW_MINBLOCKS 8      // 64 registers, no spills; without the bound ptxas takes 72 since the node loads moved up: 7 CTAs/SM
 #endif
+#define YRT_SHADOW_BOUNDS __launch_bounds__(YRT_TRACE_THREADS, YRT_SHADOW_MINBLOCKS)
 template <bool COUNT, bool MOTION>
 __global__ void YRT_SHADOW_BOUNDS k_trace_shadow(SceneData sc, WavefrontBuffers wb) {
     const uint32_t n = wb.counters[2];
