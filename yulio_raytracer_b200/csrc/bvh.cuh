@@ -365,16 +365,19 @@ YRT_D void trace_stream(const uint4* __restrict__ nodes, const float4* __restric
     uint2 lstack[YRT_STACK_SIZE - YRT_SM_STACK];
     const unsigned FULL = 0xffffffffu;
     const unsigned lane = threadIdx.x & 31u, ltmask = (1u << lane) - 1u;
-    uint32_t sliceNext = 0, sliceEnd = 0; bool exhausted = false;
+    // the warp's slice of the queue, (next, end), lives in shared memory: it is touched at refills only, and the traversal loop has no register to spare
+    __shared__ uint2 smSlice[YRT_TRACE_THREADS / 32];
+    const unsigned wid = threadIdx.x >> 5;
+    if (lane == 0) smSlice[wid] = make_uint2(0u, 0u);
+    bool drained = false;                          // the queue has no unclaimed rays left and the warp's slice is used up
     // rays claimed per atomic: a full YRT_SLICE for long queues, down to one warp's worth for short ones so that a
     // late, nearly empty bounce still spreads over all SMs instead of serialising on a few warps
     const uint32_t totalWarps = (gridDim.x * blockDim.x) >> 5;
-    uint32_t slice = (n / totalWarps) & ~31u;
-    slice = slice < 32u ? 32u : (slice > YRT_SLICE ? YRT_SLICE : slice);
+    const uint32_t sliceRaw = (n / totalWarps) & ~31u;
 
     bool active = false, occluded = false;
     RayPre r; r.O = V3(0.f); r.D = V3(0.f); r.idir = V3(0.f); r.octinv = 0;
-    float tnear = 0.f, tbest = 0.f, bt = 0.f, bu = 0.f, bv = 0.f, time = 0.f;
+    float tnear = 0.f, tbest = 0.f, bu = 0.f, bv = 0.f, time = 0.f;      // tbest: the ray's tfar until a hit is accepted, then the hit's t
     uint32_t bestTri = YRT_NO_TRI, tag = 0;
     uint2 G = make_uint2(0u, 0u), T = make_uint2(0u, 0u);
     int sp = 0;
@@ -394,39 +397,44 @@ YRT_D void trace_stream(const uint4* __restrict__ nodes, const float4* __restric
 #endif
         if (idleMask) {
             const uint32_t nIdle = __popc(idleMask);
-            if (nIdle >= (uint32_t)tune.refillMin && !(exhausted && sliceNext >= sliceEnd)) {
+            if (nIdle >= (uint32_t)tune.refillMin && !drained) {
                 // results of the rays that finished since the last refill (sp < 0) are written here, refillMin or more slots at a time: writing
                 // each one when its ray ends put a store (and the wait for its address) into almost every macro step, for two or three lanes
                 if (!active && sp < 0) {
                     if (ANY) io.store_any(tag, occluded);
-                    else io.store_hit(tag, bt, bu, bv, bestTri, tris);     // bestTri == YRT_NO_TRI: miss
+                    else io.store_hit(tag, tbest, bu, bv, bestTri, tris);     // bestTri == YRT_NO_TRI: miss
                     sp = 0;
                 }
-                if (sliceNext >= sliceEnd) {
+                uint2 sl = smSlice[wid];
+                if (sl.x >= sl.y) {
+                    const uint32_t slice = sliceRaw < 32u ? 32u : (sliceRaw > YRT_SLICE ? YRT_SLICE : sliceRaw);
                     uint32_t s = 0;
                     if (lane == 0) s = atomicAdd(workCounter, slice);
                     s = __shfl_sync(FULL, s, 0);
-                    if (s >= n) exhausted = true;
-                    else { sliceNext = s; sliceEnd = (n - s < slice) ? n : s + slice; }
+                    if (s >= n) drained = true;
+                    else { sl.x = s; sl.y = (n - s < slice) ? n : s + slice; }
                 }
-                const uint32_t avail = sliceEnd > sliceNext ? sliceEnd - sliceNext : 0u;
+                const uint32_t avail = sl.y > sl.x ? sl.y - sl.x : 0u;
                 const uint32_t my = __popc(idleMask & ltmask);
                 if (!active && my < avail) {
                     V3 O, D; float tfar;
-                    tag = io.load(sliceNext + my, O, D, tnear, tfar);
+                    tag = io.load(sl.x + my, O, D, tnear, tfar);
                     if (MOTION) time = io.time(tag);
                     r = ray_prepare(O, D);
-                    tbest = tfar; bt = tfar; bu = 0.f; bv = 0.f; bestTri = YRT_NO_TRI; occluded = false; sp = 0;
+                    tbest = tfar; bu = 0.f; bv = 0.f; bestTri = YRT_NO_TRI; occluded = false; sp = 0;
                     T = make_uint2(0u, 0u);
                     // root = "child 7^octinv of a virtual parent with imask 0"; an empty scene or an empty / NaN
                     // interval (pin P2) starts with no work and is retired below as a miss
                     G = make_uint2(0u, (numNodes != 0 && tnear <= tfar) ? 0x80000000u : 0u);
                     active = true;
                 }
-                sliceNext += nIdle < avail ? nIdle : avail;
+                sl.x += nIdle < avail ? nIdle : avail;
+                __syncwarp();
+                if (lane == 0) smSlice[wid] = sl;
+                __syncwarp();
             }
             if (!__any_sync(FULL, active)) {
-                if (exhausted && sliceNext >= sliceEnd) break;
+                if (drained) break;
                 continue;
             }
         }
@@ -461,7 +469,7 @@ YRT_D void trace_stream(const uint4* __restrict__ nodes, const float4* __restric
                     }
                     // back-face cull filter (shapes/trianglemesh_full.cpp:101-121): reject if dot(Ng, dir) <= 0
                     if (closer && !((__float_as_uint(c.w) & YRT_TRI_FLAG_CULL) && den <= 0.f)) {
-                        tbest = t; bt = t; bu = u; bv = v; bestTri = triIdx;
+                        tbest = t; bu = u; bv = v; bestTri = triIdx;
                         if (ANY) { occluded = true; G.y = 0u; T.y = 0u; sp = 0; }
                     }
                 }
@@ -518,7 +526,7 @@ YRT_D void trace_stream(const uint4* __restrict__ nodes, const float4* __restric
     }
     if (sp < 0) {                                                    // the rays that finished after the last refill
         if (ANY) io.store_any(tag, occluded);
-        else io.store_hit(tag, bt, bu, bv, bestTri, tris);
+        else io.store_hit(tag, tbest, bu, bv, bestTri, tris);
     }
 }
 
