@@ -338,7 +338,10 @@ YRT_D bool trace_ray(const uint4* __restrict__ nodes, const float4* __restrict__
 //     node pops and tests one compressed node) or the TRIANGLE phase (each lane with pending triangles tests one),
 //     postponing the minority kind of work on the per-lane stack (Aila/Laine speculative traversal, Ylitie et al.
 //     triangle postponing), so both phases run with most lanes participating,
-//   * the first YRT_SM_STACK stack entries live in shared memory, deeper ones spill to local memory.
+//   * the first YRT_SM_STACK stack entries live in shared memory, deeper ones spill to local memory,
+//   * a finished ray keeps its result in registers (sp = -1) until the warp's next refill writes the results of all idle slots at once,
+//   * the warp's slice of the queue and the slot-permutation table live in shared memory; the loop itself fits 64 registers
+//     (8 CTAs of 128 threads per SM) without a spill in the node phase.
 // Results are independent of the schedule: closest-hit acceptance is the (t, geomID, primID) minimum, any-hit is
 // an OR over accepted hits, and the triangle arithmetic is YRT-PLUECKER-1 exactly as in trace_ray.
 #define YRT_TRACE_THREADS 128
